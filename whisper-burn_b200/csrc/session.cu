@@ -1,0 +1,427 @@
+// Session: device buffers + the launch sequences of the hot path
+//   prep_audio (audio.rs:34-56) -> mel padding (transcribe.rs:161-177) -> forward_encoder
+//   (mod.rs:228-260) -> cross K/V (mod.rs:484-485, hoisted out of the step loop) -> decoder steps.
+// Windows of one call are batched: encoder rows of all windows are packed back to back.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "session.h"
+
+namespace wb {
+
+Session::Session(Model* model, int64_t max_w, int64_t max_b, int64_t max_text_len, int kv) : m(model) {
+    if (!m || !m->finalized) fail(WB_ERR_STATE, "session: model not finalized");
+    const wb_dims& D = m->dims;
+    WB_REQUIRE(max_w >= 1 && max_b >= 1 && max_w * max_b <= 4096, "session: bad max_windows / max_beams");
+    WB_REQUIRE(max_text_len >= 2 && max_text_len <= D.n_text_ctx, "session: max_text_len must be in [2, n_text_ctx]");
+    WB_REQUIRE(kv == WB_KV_F32, "session: only WB_KV_F32 is implemented in this build");
+    WB_CUDA(cudaSetDevice(m->device));
+    max_windows = (int)max_w;
+    max_beams = (int)max_b;
+    t_max = (int)max_text_len;
+    kv_dtype = kv;
+    Rmax = max_windows * max_beams;
+    TmS = D.n_audio_ctx + 2;
+    Tcap = (D.n_audio_ctx - 1) / 2 + 1;
+    Mcap = (int64_t)max_windows * Tcap;
+    const int d = D.n_audio_state, H = D.n_text_head, L = D.n_text_layer, V = D.n_vocab;
+    n_splits = std::max(1, std::min(16, (Tcap + 127) / 128));
+    while ((Tcap + n_splits - 1) / n_splits > dec_attn_max_keys_per_split()) ++n_splits;
+    WB_REQUIRE(t_max <= dec_attn_max_keys_per_split(), "session: max_text_len too large for the attention kernel");
+    kmax = std::max(8, max_beams);
+
+    WB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    for (auto& e : ev) WB_CUDA(cudaEventCreate(&e));
+    d_lmwin.alloc(max_windows); d_g1.alloc(max_windows); d_g2.alloc(max_windows); d_awin.alloc(max_windows);
+    d_win_row_off.alloc(max_windows); d_win_T.alloc(max_windows);
+    max_slots.alloc(max_windows);
+    mel_rows.alloc((size_t)max_windows * TmS * N_MELS);
+    h1.alloc((size_t)max_windows * TmS * d);
+    x.alloc(Mcap * d); xn.alloc(Mcap * d); att.alloc(Mcap * d); qkv.alloc(Mcap * 3 * d); hid.alloc(Mcap * 4 * d);
+    xa.alloc(Mcap * d);
+    ckv.alloc((size_t)L * Mcap * 2 * d);
+    kc.alloc((size_t)L * Rmax * t_max * d); vc.alloc((size_t)L * Rmax * t_max * d);
+    dx.alloc((size_t)Rmax * d); dq.alloc((size_t)Rmax * d); dhid.alloc((size_t)Rmax * 4 * d);
+    logits.alloc((size_t)Rmax * V);
+    part_o.alloc((size_t)Rmax * H * n_splits * 64); part_m.alloc((size_t)Rmax * H * n_splits);
+    part_l.alloc((size_t)Rmax * H * n_splits);
+    tokens.alloc((size_t)Rmax * t_max); lengths.alloc(Rmax); cur_tok.alloc(Rmax); finished.alloc(Rmax);
+    row_window.alloc(Rmax); anc0.alloc((size_t)Rmax * t_max); anc1.alloc((size_t)Rmax * t_max); parent.alloc(Rmax);
+    pos.alloc(1); n_unfinished.alloc(1);
+    topk_id.alloc((size_t)Rmax * kmax); topk_lp.alloc((size_t)Rmax * kmax);
+    is_special.alloc(V);
+    WB_CUDA(cudaMallocHost((void**)&h_int, sizeof(int) * (4 * (size_t)Rmax + 16 + (size_t)Rmax * kmax)));
+    WB_CUDA(cudaMallocHost((void**)&h_float, sizeof(float) * (size_t)Rmax * kmax));
+    WB_CUDA(cudaMemsetAsync(is_special.p, 0, V, st));
+    WB_CUDA(cudaStreamSynchronize(st));
+}
+
+Session::~Session() {
+    if (st) cudaStreamSynchronize(st);
+    if (h_int) cudaFreeHost(h_int);
+    if (h_float) cudaFreeHost(h_float);
+    for (auto& e : ev)
+        if (e) cudaEventDestroy(e);
+    if (st) cudaStreamDestroy(st);
+}
+
+// ---- geometry helpers -------------------------------------------------------------------------
+static void set_geometry(Session& s, const std::vector<int>& Tm) {
+    s.n_windows = (int)Tm.size();
+    s.win_Tm = Tm;
+    s.win_T.resize(Tm.size());
+    s.win_row_off.resize(Tm.size());
+    s.M_tot = 0;
+    s.max_T = 0;
+    s.max_Tm = 0;
+    for (size_t w = 0; w < Tm.size(); ++w) {
+        s.win_T[w] = (Tm[w] - 1) / 2 + 1;       // Conv1d k3 p1 s2 (mod.rs:179-182)
+        s.win_row_off[w] = s.M_tot;
+        s.M_tot += s.win_T[w];
+        s.max_T = std::max(s.max_T, s.win_T[w]);
+        s.max_Tm = std::max(s.max_Tm, Tm[w]);
+    }
+    const int d = s.m->dims.n_audio_state;
+    std::vector<GemmGroup> g1(Tm.size()), g2(Tm.size());
+    std::vector<AttnWindow> aw(Tm.size());
+    for (size_t w = 0; w < Tm.size(); ++w) {
+        // conv1: output frame t reads mel buffer rows t, t+1, t+2 (frames t-1, t, t+1), writes h1 row t+1
+        g1[w] = GemmGroup{(int64_t)w * s.TmS * N_MELS, ((int64_t)w * s.TmS + 1) * d, Tm[w]};
+        // conv2 (stride 2): output t reads h1 buffer rows 2t, 2t+1, 2t+2 (frames 2t-1, 2t, 2t+1)
+        g2[w] = GemmGroup{(int64_t)w * s.TmS * d, s.win_row_off[w] * d, s.win_T[w]};
+        aw[w] = AttnWindow{s.win_row_off[w], s.win_T[w]};
+    }
+    WB_CUDA(cudaMemcpyAsync(s.d_g1.p, g1.data(), g1.size() * sizeof(GemmGroup), cudaMemcpyHostToDevice, s.st));
+    WB_CUDA(cudaMemcpyAsync(s.d_g2.p, g2.data(), g2.size() * sizeof(GemmGroup), cudaMemcpyHostToDevice, s.st));
+    WB_CUDA(cudaMemcpyAsync(s.d_awin.p, aw.data(), aw.size() * sizeof(AttnWindow), cudaMemcpyHostToDevice, s.st));
+    WB_CUDA(cudaMemcpyAsync(s.d_win_row_off.p, s.win_row_off.data(), Tm.size() * sizeof(int64_t),
+                            cudaMemcpyHostToDevice, s.st));
+    WB_CUDA(cudaMemcpyAsync(s.d_win_T.p, s.win_T.data(), Tm.size() * sizeof(int), cudaMemcpyHostToDevice, s.st));
+    WB_CUDA(cudaStreamSynchronize(s.st));   // the host vectors above are temporaries
+}
+
+void Session::encode_from_device_wave(const float* wave_dev, const int64_t* offsets, const int64_t* lens, int64_t n) {
+    WB_REQUIRE(n >= 1 && n <= max_windows, "encode: n_windows out of range for this session");
+    const wb_dims& D = m->dims;
+    std::vector<LogMelWindow> lw((size_t)n);
+    std::vector<int> Tm((size_t)n);
+    win_F.resize((size_t)n);
+    int max_frames = 0;
+    for (int64_t w = 0; w < n; ++w) {
+        WB_REQUIRE(lens[w] >= N_FFT, "prep_audio: waveform shorter than n_fft (audio.rs:292)");
+        WB_REQUIRE(lens[w] < (int64_t)1 << 30, "prep_audio: waveform too long");
+        const int F = (int)(lens[w] / HOP);                        // frames after dropping the last one
+        const int keep = std::min(F, D.n_audio_ctx - MEL_PADDING);  // transcribe.rs:173
+        win_F[(size_t)w] = F;
+        Tm[(size_t)w] = keep + MEL_PADDING;
+        lw[(size_t)w] = LogMelWindow{offsets[w], (int)lens[w], F, keep, (int)w, ((int64_t)w * TmS + 1) * N_MELS};
+        max_frames = std::max(max_frames, F);
+    }
+    WB_CUDA(cudaMemcpyAsync(d_lmwin.p, lw.data(), lw.size() * sizeof(LogMelWindow), cudaMemcpyHostToDevice, st));
+    set_geometry(*this, Tm);   // syncs, so `lw` may go out of scope
+    WB_CUDA(cudaEventRecord(ev[0], st));
+    WB_CUDA(cudaMemsetAsync(mel_rows.p, 0, (size_t)n * TmS * N_MELS * sizeof(float), st));   // halo + 10 zero frames
+    launch_logmel(*m, wave_dev, d_lmwin.p, (int)n, max_frames, mel_rows.p, max_slots.p, (int)n, st);
+    WB_CUDA(cudaEventRecord(ev[1], st));
+    run_encoder();
+    WB_CUDA(cudaEventRecord(ev[2], st));
+}
+
+void Session::encode_waveforms_host(const float* const* waves, const int64_t* lens, int64_t n) {
+    WB_REQUIRE(n >= 1 && n <= max_windows, "encode: n_windows out of range for this session");
+    std::vector<int64_t> offs((size_t)n);
+    int64_t total = 0;
+    for (int64_t w = 0; w < n; ++w) {
+        WB_REQUIRE(waves[w] != nullptr && lens[w] >= 0, "encode: null waveform");
+        offs[(size_t)w] = total;
+        total += (lens[w] + 3) / 4 * 4;   // keep windows 16-byte aligned
+    }
+    wave.ensure((size_t)total);
+    for (int64_t w = 0; w < n; ++w)
+        WB_CUDA(cudaMemcpyAsync(wave.p + offs[(size_t)w], waves[w], (size_t)lens[w] * sizeof(float),
+                                cudaMemcpyHostToDevice, st));
+    encode_from_device_wave(wave.p, offs.data(), lens, n);
+}
+
+void Session::encode_mels_host(const float* mel, int64_t n, int64_t n_mels, int64_t n_ctx) {
+    const wb_dims& D = m->dims;
+    WB_REQUIRE(n_mels == D.n_mels, "Audio mel spectrum size must be n_mels (mod.rs:231-235)");
+    WB_REQUIRE(n_ctx >= 1 && n_ctx <= D.n_audio_ctx, "Audio length cannot exceed n_audio_ctx (mod.rs:236-241)");
+    WB_REQUIRE(n >= 1 && n <= max_windows, "encode: n_windows out of range for this session");
+    std::vector<int> Tm((size_t)n, (int)n_ctx);
+    set_geometry(*this, Tm);
+    DevBuf<float> tmp;
+    tmp.alloc((size_t)n * n_mels * n_ctx);
+    WB_CUDA(cudaMemcpyAsync(tmp.p, mel, tmp.n * sizeof(float), cudaMemcpyHostToDevice, st));
+    WB_CUDA(cudaMemsetAsync(mel_rows.p, 0, (size_t)n * TmS * N_MELS * sizeof(float), st));
+    for (int64_t w = 0; w < n; ++w)
+        launch_chan_to_rows(tmp.p + w * n_mels * n_ctx, mel_rows.p + ((int64_t)w * TmS + 1) * N_MELS, (int)n_ctx, n_ctx, st);
+    run_encoder();
+    WB_CUDA(cudaStreamSynchronize(st));
+}
+
+void Session::load_encoder_output_host(const float* xa_host, int64_t n, int64_t T) {
+    WB_REQUIRE(n >= 1 && n <= max_windows && T >= 1 && T <= Tcap, "forward_decoder: encoder output shape out of range");
+    std::vector<int> Tm((size_t)n, (int)(2 * T - 1));   // any Tm with (Tm-1)/2+1 == T
+    set_geometry(*this, Tm);
+    const int d = m->dims.n_audio_state;
+    WB_CUDA(cudaMemcpyAsync(xa.p, xa_host, (size_t)n * T * d * sizeof(float), cudaMemcpyHostToDevice, st));
+    run_cross_kv();
+    encoded = true;
+}
+
+// ---- encoder ------------------------------------------------------------------------------------
+void Session::run_encoder() {
+    const wb_dims& D = m->dims;
+    const int d = D.n_audio_state;
+    const int M = (int)M_tot;
+    const float qk_scale = (float)std::pow((double)d / (double)D.n_audio_head, -0.25);   // mod.rs:503
+    // halo rows of the conv1 output must read as zero padding
+    WB_CUDA(cudaMemsetAsync(h1.p, 0, (size_t)n_windows * TmS * d * sizeof(float), st));
+    GemmParams p;
+    // conv1 + GELU (mod.rs:243): K = 3*80 over three consecutive token-major mel rows
+    p = GemmParams{};
+    p.A = mel_rows.p; p.lda = N_MELS; p.B = m->conv1.w32; p.C = h1.p; p.ldc = d; p.N = d; p.K = 3 * N_MELS;
+    p.bias = m->conv1.b; p.act = ACT_GELU; p.groups = d_g1.p; p.n_groups = n_windows; p.max_rows = max_Tm;
+    launch_gemm(p, st);
+    // conv2 (stride 2) + GELU + transpose + positional embedding (mod.rs:244-252)
+    p = GemmParams{};
+    p.A = h1.p; p.lda = 2 * d; p.B = m->conv2.w32; p.C = x.p; p.ldc = d; p.N = d; p.K = 3 * d;
+    p.bias = m->conv2.b; p.act = ACT_GELU; p.pos = m->enc_pos; p.groups = d_g2.p; p.n_groups = n_windows;
+    p.max_rows = max_T;
+    launch_gemm(p, st);
+    for (int l = 0; l < D.n_audio_layer; ++l) {
+        const EncBlockW& B = m->enc[(size_t)l];
+        // x = x + attn(attn_ln(x))   (mod.rs:300)
+        launch_layernorm(x.p, xn.p, B.attn_ln, M, d, m->ln_eps_outside, st);
+        p = GemmParams{};
+        p.A = xn.p; p.lda = d; p.B = B.qkv.w32; p.C = qkv.p; p.ldc = 3 * d; p.N = 3 * d; p.K = d;
+        p.bias = B.qkv.b; p.scale = qk_scale; p.scale_cols = 2 * d; p.max_rows = M;
+        launch_gemm(p, st);
+        launch_encoder_attention(qkv.p, att.p, d_awin.p, n_windows, max_T, d, D.n_audio_head, st);
+        p = GemmParams{};
+        p.A = att.p; p.lda = d; p.B = B.out.w32; p.C = x.p; p.ldc = d; p.N = d; p.K = d;
+        p.bias = B.out.b; p.residual = x.p; p.max_rows = M;
+        launch_gemm(p, st);
+        // x = x + mlp(mlp_ln(x))     (mod.rs:301)
+        launch_layernorm(x.p, xn.p, B.mlp_ln, M, d, m->ln_eps_outside, st);
+        p = GemmParams{};
+        p.A = xn.p; p.lda = d; p.B = B.mlp1.w32; p.C = hid.p; p.ldc = 4 * d; p.N = 4 * d; p.K = d;
+        p.bias = B.mlp1.b; p.act = ACT_GELU; p.max_rows = M;
+        launch_gemm(p, st);
+        p = GemmParams{};
+        p.A = hid.p; p.lda = 4 * d; p.B = B.mlp2.w32; p.C = x.p; p.ldc = d; p.N = d; p.K = 4 * d;
+        p.bias = B.mlp2.b; p.residual = x.p; p.max_rows = M;
+        launch_gemm(p, st);
+    }
+    launch_layernorm(x.p, xa.p, m->ln_post, M, d, m->ln_eps_outside, st);   // mod.rs:259
+    run_cross_kv();
+    encoded = true;
+}
+
+void Session::run_cross_kv() {
+    const wb_dims& D = m->dims;
+    const int d = D.n_text_state;
+    const float qk_scale = (float)std::pow((double)d / (double)D.n_text_head, -0.25);
+    for (int l = 0; l < D.n_text_layer; ++l) {
+        const DecBlockW& B = m->dec[(size_t)l];
+        GemmParams p;
+        p.A = xa.p; p.lda = d; p.B = B.ckv.w32; p.C = ckv.p + (size_t)l * Mcap * 2 * d; p.ldc = 2 * d;
+        p.N = 2 * d; p.K = d; p.bias = B.ckv.b; p.scale = qk_scale; p.scale_cols = d; p.max_rows = (int)M_tot;
+        launch_gemm(p, st);
+    }
+}
+
+// ---- decoder --------------------------------------------------------------------------------------
+void Session::set_special(const uint8_t* sp) {
+    if (sp) {
+        WB_CUDA(cudaMemcpyAsync(is_special.p, sp, (size_t)m->dims.n_vocab, cudaMemcpyHostToDevice, st));
+        WB_CUDA(cudaStreamSynchronize(st));
+        have_special = true;
+    }
+}
+
+void Session::begin(const int64_t* prompt, int64_t prompt_len) {
+    if (!encoded) fail(WB_ERR_STATE, "session: begin before encode");
+    WB_REQUIRE(prompt_len >= 1 && prompt_len < t_max, "begin: prompt length out of range");
+    const int V = m->dims.n_vocab;
+    R = n_windows;
+    WB_REQUIRE(R <= Rmax, "begin: too many rows");
+    std::vector<int> tk((size_t)R * t_max, 0), rw((size_t)R), first((size_t)R);
+    for (int r = 0; r < R; ++r) {
+        for (int64_t i = 0; i < prompt_len; ++i) {
+            WB_REQUIRE(prompt[i] >= 0 && prompt[i] < V, "begin: prompt token out of range");
+            tk[(size_t)r * t_max + i] = (int)prompt[i];
+        }
+        rw[(size_t)r] = r;
+        first[(size_t)r] = (int)prompt[0];
+    }
+    WB_CUDA(cudaMemcpyAsync(tokens.p, tk.data(), tk.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    WB_CUDA(cudaMemcpyAsync(row_window.p, rw.data(), rw.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    WB_CUDA(cudaMemcpyAsync(cur_tok.p, first.data(), first.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    WB_CUDA(cudaMemsetAsync(finished.p, 0, sizeof(int) * Rmax, st));
+    WB_CUDA(cudaMemsetAsync(pos.p, 0, sizeof(int), st));
+    std::vector<int> len((size_t)R, (int)prompt_len);
+    WB_CUDA(cudaMemcpyAsync(lengths.p, len.data(), len.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    anc_identity = true;
+    anc_cur = 0;
+    host_pos = 0;
+    // feed prompt[0 .. prompt_len-1): no logits needed
+    for (int64_t i = 0; i + 1 < prompt_len; ++i) {
+        step_core(false, 0, 1, false, -1, nullptr);
+        std::vector<int> nxt((size_t)R, (int)prompt[i + 1]);
+        WB_CUDA(cudaMemcpyAsync(cur_tok.p, nxt.data(), nxt.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        WB_CUDA(cudaStreamSynchronize(st));
+    }
+    WB_CUDA(cudaStreamSynchronize(st));
+}
+
+void Session::step_core(bool with_logits, int mask_mode, int k, bool greedy, int eot, float* logprob_out) {
+    const wb_dims& D = m->dims;
+    const int d = D.n_text_state, H = D.n_text_head, L = D.n_text_layer, V = D.n_vocab;
+    const bool h16 = m->fp16_exact;
+    const float qk_scale = (float)std::pow((double)d / (double)H, -0.25);
+    const int* anc = anc_identity ? nullptr : (anc_cur == 0 ? anc0.p : anc1.p);
+    launch_dec_embed(cur_tok.p, m->tok_emb32, m->dec_pos, pos.p, dx.p, R, d, st);
+    auto wptr = [&](const LinearW& w) -> const void* { return h16 ? (const void*)w.w16 : (const void*)w.w32; };
+    for (int l = 0; l < L; ++l) {
+        const DecBlockW& B = m->dec[(size_t)l];
+        float* kcl = kc.p + (size_t)l * Rmax * t_max * d;
+        float* vcl = vc.p + (size_t)l * Rmax * t_max * d;
+        // ---- self attention (mod.rs:346)
+        GemvArgs g;
+        g.W = wptr(B.qkv); g.bias = B.qkv.b; g.N = 3 * d; g.K = d; g.R = R; g.in_mode = IN_LN; g.in = dx.p;
+        g.ln_g = B.attn_ln.g; g.ln_b = B.attn_ln.b; g.ln_eps = B.attn_ln.eps; g.eps_outside = m->ln_eps_outside;
+        g.n_seg = 3; g.pos = pos.p;
+        g.seg[0] = GemvSeg{0, dq.p, d, 0, qk_scale};
+        g.seg[1] = GemvSeg{d, kcl, (int64_t)t_max * d, d, qk_scale};
+        g.seg[2] = GemvSeg{2 * d, vcl, (int64_t)t_max * d, d, 1.0f};
+        launch_dec_gemv(g, h16, st);
+        DecAttnArgs a;
+        a.q = dq.p; a.q_ld = d; a.K = kcl; a.V = vcl; a.kv_ld = d; a.is_cross = 0; a.anc = anc; a.t_max = t_max;
+        a.pos = pos.p; a.part_o = part_o.p; a.part_m = part_m.p; a.part_l = part_l.p;
+        launch_dec_attn(a, H, R, 1, st);
+        g = GemvArgs{};
+        g.W = wptr(B.out); g.bias = B.out.b; g.N = d; g.K = d; g.R = R; g.in_mode = IN_ATTN_MERGE;
+        g.part_o = part_o.p; g.part_m = part_m.p; g.part_l = part_l.p; g.n_splits = 1; g.residual = 1;
+        g.seg[0] = GemvSeg{0, dx.p, d, 0, 1.0f};
+        launch_dec_gemv(g, h16, st);
+        // ---- cross attention (mod.rs:347)
+        g = GemvArgs{};
+        g.W = wptr(B.cq); g.bias = B.cq.b; g.N = d; g.K = d; g.R = R; g.in_mode = IN_LN; g.in = dx.p;
+        g.ln_g = B.cross_ln.g; g.ln_b = B.cross_ln.b; g.ln_eps = B.cross_ln.eps; g.eps_outside = m->ln_eps_outside;
+        g.seg[0] = GemvSeg{0, dq.p, d, 0, qk_scale};
+        launch_dec_gemv(g, h16, st);
+        a = DecAttnArgs{};
+        const float* ckvl = ckv.p + (size_t)l * Mcap * 2 * d;
+        a.q = dq.p; a.q_ld = d; a.K = ckvl; a.V = ckvl + d; a.kv_ld = 2 * d; a.is_cross = 1;
+        a.row_window = row_window.p; a.win_row_off = d_win_row_off.p; a.win_T = d_win_T.p; a.pos = pos.p;
+        a.part_o = part_o.p; a.part_m = part_m.p; a.part_l = part_l.p;
+        launch_dec_attn(a, H, R, n_splits, st);
+        g = GemvArgs{};
+        g.W = wptr(B.cout); g.bias = B.cout.b; g.N = d; g.K = d; g.R = R; g.in_mode = IN_ATTN_MERGE;
+        g.part_o = part_o.p; g.part_m = part_m.p; g.part_l = part_l.p; g.n_splits = n_splits; g.residual = 1;
+        g.seg[0] = GemvSeg{0, dx.p, d, 0, 1.0f};
+        launch_dec_gemv(g, h16, st);
+        // ---- MLP (mod.rs:348)
+        g = GemvArgs{};
+        g.W = wptr(B.mlp1); g.bias = B.mlp1.b; g.N = 4 * d; g.K = d; g.R = R; g.in_mode = IN_LN; g.in = dx.p;
+        g.ln_g = B.mlp_ln.g; g.ln_b = B.mlp_ln.b; g.ln_eps = B.mlp_ln.eps; g.eps_outside = m->ln_eps_outside;
+        g.act = ACT_GELU;
+        g.seg[0] = GemvSeg{0, dhid.p, 4 * d, 0, 1.0f};
+        launch_dec_gemv(g, h16, st);
+        g = GemvArgs{};
+        g.W = wptr(B.mlp2); g.bias = B.mlp2.b; g.N = d; g.K = 4 * d; g.R = R; g.in_mode = IN_COPY; g.in = dhid.p;
+        g.residual = 1;
+        g.seg[0] = GemvSeg{0, dx.p, d, 0, 1.0f};
+        launch_dec_gemv(g, h16, st);
+    }
+    if (with_logits) {
+        GemvArgs g;
+        g.W = h16 ? (const void*)m->tok_emb16 : (const void*)m->tok_emb32;
+        g.bias = nullptr; g.N = V; g.K = d; g.R = R; g.in_mode = IN_LN; g.in = dx.p;
+        g.ln_g = m->dec_ln.g; g.ln_b = m->dec_ln.b; g.ln_eps = m->dec_ln.eps; g.eps_outside = m->ln_eps_outside;
+        g.seg[0] = GemvSeg{0, logits.p, V, 0, 1.0f};
+        launch_dec_gemv(g, h16, st);
+        LogSoftmaxArgs s;
+        s.logits = logits.p; s.V = V; s.is_special = have_special ? is_special.p : nullptr; s.mask_mode = mask_mode;
+        s.pos = pos.p; s.k = k; s.topk_id = topk_id.p; s.topk_lp = topk_lp.p; s.logprob_out = logprob_out;
+        s.greedy = greedy ? 1 : 0; s.tokens = tokens.p; s.lengths = lengths.p; s.cur_tok = cur_tok.p;
+        s.finished = finished.p; s.t_max = t_max; s.eot = eot;
+        launch_logsoftmax_topk(s, R, st);
+    }
+    launch_dec_advance(pos.p, greedy ? finished.p : nullptr, R, n_unfinished.p, st);
+    ++host_pos;
+}
+
+void Session::step_beams(int64_t n_rows, const int32_t* window_of_row, const int32_t* parent_row, const int64_t* token,
+                         int apply_mask, int k, int64_t* topk_ids_out, float* topk_lp_out) {
+    if (!encoded) fail(WB_ERR_STATE, "session: step before encode/begin");
+    WB_REQUIRE(n_rows >= 1 && n_rows <= Rmax, "step: n_rows out of range");
+    WB_REQUIRE(k >= 1 && k <= kmax, "step: k out of range");
+    WB_REQUIRE(host_pos + 1 < t_max, "step: session max_text_len exceeded");
+    const int V = m->dims.n_vocab;
+    int* hp = h_int;                  // parent
+    int* hw = h_int + Rmax;           // window
+    int* ht = h_int + 2 * Rmax;       // token
+    for (int64_t r = 0; r < n_rows; ++r) {
+        WB_REQUIRE(parent_row[r] >= 0 && parent_row[r] < R, "step: parent_row out of range");
+        WB_REQUIRE(window_of_row[r] >= 0 && window_of_row[r] < n_windows, "step: window_of_row out of range");
+        WB_REQUIRE(token[r] >= 0 && token[r] < V, "step: token out of range");
+        hp[r] = parent_row[r];
+        hw[r] = window_of_row[r];
+        ht[r] = (int)token[r];
+    }
+    WB_CUDA(cudaMemcpyAsync(parent.p, hp, sizeof(int) * n_rows, cudaMemcpyHostToDevice, st));
+    WB_CUDA(cudaMemcpyAsync(row_window.p, hw, sizeof(int) * n_rows, cudaMemcpyHostToDevice, st));
+    WB_CUDA(cudaMemcpyAsync(cur_tok.p, ht, sizeof(int) * n_rows, cudaMemcpyHostToDevice, st));
+    if (anc_identity) {   // rows so far (prompt) live in their own cache rows
+        launch_dec_anc_identity(anc0.p, Rmax, t_max, st);
+        anc_cur = 0;
+        anc_identity = false;
+    }
+    {
+        int* cur = anc_cur == 0 ? anc0.p : anc1.p;
+        int* nxt = anc_cur == 0 ? anc1.p : anc0.p;
+        R = (int)n_rows;
+        launch_dec_reorder(cur, nxt, parent.p, pos.p, R, t_max, st);
+        anc_cur ^= 1;
+    }
+    step_core(true, apply_mask ? 1 : 0, k, false, -1, nullptr);
+    int* hid_ = h_int + 4 * Rmax + 16;
+    WB_CUDA(cudaMemcpyAsync(hid_, topk_id.p, sizeof(int) * n_rows * k, cudaMemcpyDeviceToHost, st));
+    WB_CUDA(cudaMemcpyAsync(h_float, topk_lp.p, sizeof(float) * n_rows * k, cudaMemcpyDeviceToHost, st));
+    WB_CUDA(cudaStreamSynchronize(st));
+    for (int64_t i = 0; i < n_rows * k; ++i) {
+        topk_ids_out[i] = hid_[i];
+        topk_lp_out[i] = h_float[i];
+    }
+}
+
+void Session::greedy_decode(const int64_t* prompt, int64_t prompt_len, int max_depth, int64_t eot,
+                            std::vector<std::vector<int64_t>>& out) {
+    WB_REQUIRE(prompt_len + max_depth <= t_max, "greedy: prompt + max_depth exceeds the session's max_text_len");
+    begin(prompt, prompt_len);
+    // beam_search with beam_size 1 (beam.rs:9-37): stop when the (only) beam ends in EOT or after max_depth steps
+    int done_steps = 0;
+    const int poll = 16;
+    while (done_steps < max_depth) {
+        const int n = std::min(poll, max_depth - done_steps);
+        for (int i = 0; i < n; ++i) step_core(true, 2, 1, true, (int)eot, nullptr);
+        done_steps += n;
+        WB_CUDA(cudaMemcpyAsync(h_int, n_unfinished.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        WB_CUDA(cudaStreamSynchronize(st));
+        if (h_int[0] == 0) break;
+    }
+    last_steps = done_steps;
+    std::vector<int> tk((size_t)R * t_max), len((size_t)R);
+    WB_CUDA(cudaMemcpyAsync(tk.data(), tokens.p, tk.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+    WB_CUDA(cudaMemcpyAsync(len.data(), lengths.p, len.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+    WB_CUDA(cudaStreamSynchronize(st));
+    out.assign((size_t)R, {});
+    for (int r = 0; r < R; ++r)
+        for (int i = 0; i < len[(size_t)r]; ++i) out[(size_t)r].push_back(tk[(size_t)r * t_max + i]);
+}
+
+}  // namespace wb

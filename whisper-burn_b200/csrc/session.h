@@ -1,0 +1,99 @@
+// Decoding session: all device state between prep_audio and the emitted token ids.  Internal.
+#pragma once
+#include <vector>
+
+#include "decoder.h"
+#include "wb_internal.h"
+
+namespace wb {
+
+constexpr int MEL_PADDING = 10;   // transcribe.rs:33
+
+struct Session {
+    Model* m = nullptr;
+    cudaStream_t st = nullptr;
+    int max_windows = 0, max_beams = 0, t_max = 0, kv_dtype = WB_KV_F32;
+    int Rmax = 0;        // max_windows * max_beams decode rows
+    int TmS = 0;         // rows per window in the token-major mel / conv1 buffers (n_audio_ctx + 2 halo rows)
+    int Tcap = 0;        // max encoder positions per window
+    int64_t Mcap = 0;    // max packed encoder rows
+    int n_splits = 1;    // split-KV factor of the cross attention
+    int kmax = 8;        // max top-k
+
+    // ---- geometry of the windows currently encoded (host mirrors)
+    int n_windows = 0;
+    std::vector<int> win_F, win_Tm, win_T;
+    std::vector<int64_t> win_row_off;
+    int64_t M_tot = 0;
+    int max_T = 0, max_Tm = 0;
+    bool encoded = false;
+
+    // ---- device: descriptors
+    DevBuf<LogMelWindow> d_lmwin;
+    DevBuf<GemmGroup> d_g1, d_g2;
+    DevBuf<AttnWindow> d_awin;
+    DevBuf<int64_t> d_win_row_off;
+    DevBuf<int> d_win_T;
+    // ---- device: frontend + encoder activations
+    DevBuf<float> wave;
+    DevBuf<int> max_slots;
+    DevBuf<float> mel_rows, h1, x, xn, att, qkv, hid, xa;
+    DevBuf<float> ckv;     // [L][Mcap][2d]  cross keys (scaled) | values, projected once per window
+    // ---- device: decode state
+    DevBuf<float> kc, vc;  // [L][Rmax][t_max][d] self keys (scaled) / values
+    DevBuf<float> dx, dq, dhid, logits;
+    DevBuf<float> part_o, part_m, part_l;
+    DevBuf<int> tokens, lengths, cur_tok, finished, row_window, anc0, anc1, parent, pos, n_unfinished, topk_id;
+    DevBuf<float> topk_lp;
+    DevBuf<uint8_t> is_special;
+    bool have_special = false;
+    int anc_cur = 0;       // which ancestry table is current
+    bool anc_identity = true;
+    int R = 0;             // live rows
+    int host_pos = 0;      // host mirror of *pos
+    // pinned host staging
+    int* h_int = nullptr;      // [4 * Rmax + 16]
+    float* h_float = nullptr;  // [Rmax * kmax]
+    // timings of the last transcribe call
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    float last_ms[4] = {0, 0, 0, 0};
+    int64_t last_steps = 0;
+
+    Session(Model* model, int64_t max_windows, int64_t max_beams, int64_t max_text_len, int kv_dtype);
+    ~Session();
+    Session(const Session&) = delete;
+    Session& operator=(const Session&) = delete;
+
+    // waveforms already in `wave` (device) at offsets[i], lens[i] samples each
+    void encode_from_device_wave(const float* wave_dev, const int64_t* offsets, const int64_t* lens, int64_t n);
+    void encode_waveforms_host(const float* const* waves, const int64_t* lens, int64_t n);
+    void encode_mels_host(const float* mel, int64_t n, int64_t n_mels, int64_t n_ctx);
+    // xa rows provided directly (stateless forward_decoder): n windows of T rows each
+    void load_encoder_output_host(const float* xa_host, int64_t n, int64_t T);
+    void run_encoder();      // conv stems .. ln_post .. cross K/V, from mel_rows
+    void run_cross_kv();
+
+    void set_special(const uint8_t* is_special_host);
+    void begin(const int64_t* prompt, int64_t prompt_len);
+    // one decoder position for R rows; tokens come from cur_tok
+    void step_core(bool with_logits, int mask_mode, int k, bool greedy, int eot, float* logprob_out);
+    void step_beams(int64_t n_rows, const int32_t* window_of_row, const int32_t* parent_row, const int64_t* token,
+                    int apply_mask, int k, int64_t* topk_ids_out, float* topk_lp_out);
+    // greedy loop on the device; returns per-window token lists
+    void greedy_decode(const int64_t* prompt, int64_t prompt_len, int max_depth, int64_t eot,
+                       std::vector<std::vector<int64_t>>& out);
+};
+
+// host pipeline (transcribe.cu)
+void transcribe_windows(Session& s, int beam_size, int max_depth, const wb_special_ids& ids,
+                        const uint8_t* is_special, std::vector<std::vector<int64_t>>& out);
+std::vector<std::pair<int64_t, int64_t>> window_bounds(int64_t n_samples, int64_t sample_rate, int64_t window_len);
+bool find_chunk_overlap(const int64_t* prev, int64_t n_prev, const int64_t* curr, int64_t n_curr, int64_t max_n_offsets,
+                        int64_t min_n_overlaps, int64_t* prev_index, int64_t* curr_index);
+
+// model.cu
+void model_set_tensor(Model& m, const char* path, const float* data, const int64_t* shape, int ndim);
+void model_finalize(Model& m);
+const std::string& last_error_string();
+
+}  // namespace wb
