@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""Benchmark of the whisper-burn hot path on B200 (contract: see the task statement / DESIGN.md).
+
+    python bench.py --gpus 1 --steps 5 --warmup 3                 # our arm  (C ABI -> sm_100a kernels)
+    python bench.py --impl reference --gpus 1 --steps 1 --warmup 0  # reference arm: CPU oracle, reference-cost mode
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Metric (BASELINE.json): audio-seconds/sec.  A "step" = one pass of the hot path (log-mel -> encoder ->
+cross K/V -> greedy decode to EOT or 100 steps) over this rank's batch of synthetic 30 s chunks.
+Workload at N=1: BASELINE configs[1], tiny.en, ONE 30 s chunk = 3 reference windows, greedy.
+N>1: weak scaling, every rank decodes its own chunk(s) (no data-path collective), then ONE NCCL
+all-gather of the token buffers; value = 30 s * total chunks / max-over-ranks step time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+CHUNK_SAMPLES = 480000
+CHUNK_SECONDS = 30.0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="tiny.en")
+    ap.add_argument("--chunks-per-gpu", type=int, default=1)
+    ap.add_argument("--beam", type=int, default=1)
+    ap.add_argument("--max-depth", type=int, default=100)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-baseline-windows", type=int, default=0, help="windows of chunk 0 timed on the CPU (0 = all)")
+    return ap.parse_args()
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        j = json.loads(p.read_text())
+        return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload(args, rank: int, world: int):
+    from oracle import synth
+    dims, w_np, _ = synth.make_weights(args.model, seed=0)
+    sp = synth.special_tokens(dims)
+    chunk_ids = [rank * args.chunks_per_gpu + i for i in range(args.chunks_per_gpu)]
+    chunks = [synth.chunk_waveform(c, CHUNK_SAMPLES) for c in chunk_ids]
+    return dims, w_np, sp, chunk_ids, chunks
+
+
+def cpu_reference_pass(args, dims, w_t, sp, chunk, n_windows: int):
+    """The reference's own CPU path restated (oracle, reference-cost mode: no KV cache, full-prefix
+    recompute, all-position logits, per-window DFT/filterbank rebuild) on windows of one chunk."""
+    import torch
+    from oracle import audio as o_audio, transcribe as o_tr
+    window_len = o_audio.max_waveform_samples(dims.n_audio_ctx - o_tr.PADDING)
+    bounds = o_tr.window_bounds(len(chunk), 16000, window_len)
+    if n_windows > 0:
+        bounds = bounds[:n_windows]
+    t0 = time.perf_counter()
+    n_tok = 0
+    for (s, e) in bounds:
+        mel = o_audio.prep_audio(torch.from_numpy(np.ascontiguousarray(chunk[s:e]))[None])
+        toks = o_tr.mels_to_tokens(w_t, dims, sp, mel, beam_size=args.beam, max_depth=args.max_depth, use_cache=False)
+        n_tok += len(toks)
+    dt = time.perf_counter() - t0
+    # audio covered by the sample: windows overlap by 3 s; count the span they cover
+    span = (bounds[-1][1] - bounds[0][0]) / 16000.0
+    return span, dt, len(bounds), n_tok
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the Rust/libtorch
+    original cannot be built here: no cargo/rustc, un-vendored crates) on this box's host cores."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    dims, w_np, w_t = synth.make_weights(args.model, seed=0)
+    sp = synth.special_tokens(dims)
+    chunk = synth.chunk_waveform(0, CHUNK_SAMPLES)
+    nwin = args.cpu_baseline_windows
+    for _ in range(args.warmup):
+        cpu_reference_pass(args, dims, w_t, sp, chunk, 1)
+    times, span = [], None
+    for _ in range(max(args.steps, 1)):
+        span, dt, nw, _ = cpu_reference_pass(args, dims, w_t, sp, chunk, nwin)
+        times.append(dt)
+    ms = 1000.0 * float(np.mean(times))
+    val = span / (ms / 1000.0)
+    sample = f"{nw} of 3 reference windows of chunk 0 ({span:.2f} s of audio), greedy depth {args.max_depth}, no KV cache"
+    line = {
+        "impl": "reference", "metric": "audio-seconds/sec", "value": val, "unit": "audio-s/s", "n_gpus": args.gpus,
+        "steps": max(args.steps, 1), "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.model}, 30 s synthetic chunk, R-mode windows, greedy (beam {args.beam}), CPU reference-cost path",
+                   "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import wb200  # noqa: F401
+    from whisper_burn_b200 import ffi, model, shard, transcribe
+    from oracle import audio as o_audio, transcribe as o_tr
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    dims, w_np, sp, chunk_ids, chunks = workload(args, rank, world)
+    is_special = (np.arange(dims.n_vocab) >= sp.first_special).astype(np.uint8)
+    wh = model.Whisper(dims, w_np, device=local_rank)
+    window_len = o_audio.max_waveform_samples(dims.n_audio_ctx - o_tr.PADDING)
+    bounds = o_tr.window_bounds(CHUNK_SAMPLES, 16000, window_len)
+    n_win = len(bounds) * len(chunks)
+    sess = transcribe.Session(wh, max_windows=n_win, max_beams=max(args.beam, 1), max_text_len=4 + args.max_depth + 1)
+
+    # ---- inputs resident in HBM (value) and in pinned host memory (e2e)
+    flat = np.concatenate(chunks)
+    wave_dev = torch.from_numpy(flat).to(dev)
+    offsets = [ci * CHUNK_SAMPLES + s for ci in range(len(chunks)) for (s, e) in bounds]
+    lens = [e - s for _ in range(len(chunks)) for (s, e) in bounds]
+    wave_pinned = torch.from_numpy(flat).pin_memory()
+    pinned_np = wave_pinned.numpy()
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    total_units = world * len(chunks)
+    cap = 4 + args.max_depth + 1
+
+    def step_device():
+        toks = sess.transcribe_windows_dev(wave_dev.data_ptr(), offsets, lens, sp, is_special, args.beam, args.max_depth)
+        if world > 1:   # the one exchange step: final token gather over NCCL/NVLink
+            shard.gather_tokens(toks, world * n_win, cap, device=dev)
+        return toks
+
+    def step_e2e():
+        out = []
+        for ci in range(len(chunks)):
+            out.append(sess.waveform_to_tokens(pinned_np[ci * CHUNK_SAMPLES:(ci + 1) * CHUNK_SAMPLES], sp, is_special,
+                                               16000, args.beam, args.max_depth))
+        if world > 1:
+            shard.gather_tokens(out, total_units, cap * 4, device=dev)
+        return out
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+        step_e2e()
+    # ---- timed region: device path
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    ffi.lib().wb_kernel_launch_count_reset()
+    dev_ms, wall_ms, phase = [], [], {"logmel": 0.0, "encoder": 0.0, "decode": 0.0}
+    toks = None
+    for _ in range(args.steps):
+        flush_buf.fill_(1)              # flush L2 between timed iterations
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        toks = step_device()
+        torch.cuda.synchronize()
+        wall_ms.append(1000.0 * (time.perf_counter() - t0))
+        t = sess.last_timings_ms()      # CUDA events on the library's stream
+        dev_ms.append(t["total"])
+        for k in phase:
+            phase[k] += t[k] / args.steps
+    launches = int(ffi.lib().wb_kernel_launch_count())
+    barrier()
+    # ---- timed region: end to end through the user-facing call, host buffers
+    e2e_ms = []
+    for _ in range(args.steps):
+        flush_buf.fill_(1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        step_e2e()
+        torch.cuda.synchronize()
+        e2e_ms.append(1000.0 * (time.perf_counter() - t0))
+    barrier()
+    clocks = sampler.stop()
+    steps_run = sess.last_steps()
+
+    # max over ranks of the per-step time
+    def max_over_ranks(v: float) -> float:
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ms_step = max_over_ranks(float(np.mean(wall_ms)))
+    ms_dev = max_over_ranks(float(np.mean(dev_ms)))
+    ms_e2e = max_over_ranks(float(np.mean(e2e_ms)))
+    audio_s = CHUNK_SECONDS * total_units
+    value = audio_s / (ms_step / 1000.0)
+    e2e_val = audio_s / (ms_e2e / 1000.0)
+
+    # ---- roofline of the dominant kernel: the logits GEMV (tied-embedding projection, mod.rs:156),
+    # timed alone with CUDA events on the library stream over re-runs of the decode steps
+    hbm_peak, peak_src = peaks()
+    roof = None
+    if rank == 0:
+        d, V, R = dims.n_text_state, dims.n_vocab, n_win
+        wbytes = 2 if wh.weights_fp16_exact else 4
+        alg_bytes = V * d * wbytes + R * d * 4 + R * V * 4
+        try:
+            k_ms, step_ms_prof = sess.profile_decode(sp, min(50, args.max_depth))
+            ach = alg_bytes / (k_ms * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": "dec_gemv_kernel (logits, LN prologue)", "achieved": ach, "peak": hbm_peak,
+                    "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": k_ms * 1e3,
+                    "share_of_decode_step": k_ms / step_ms_prof, "decode_step_us": step_ms_prof * 1e3,
+                    "note": "weights (39.8 MB fp16) stay L2-resident between steps, so frac may exceed HBM-only expectations"}
+        except Exception as ex:   # noqa: BLE001
+            roof = {"bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": None,
+                    "error": str(ex)}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import synth
+        torch.set_num_threads(os.cpu_count() or 1)
+        w_t = synth.to_torch(w_np)
+        span, dt, nw, _ = cpu_reference_pass(args, dims, w_t, sp, chunks[0], args.cpu_baseline_windows)
+        cpu = {"value": span / dt, "unit": "audio-s/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{nw} of 3 reference windows of chunk {chunk_ids[0]} ({span:.2f} s audio), greedy depth {args.max_depth}, "
+                         f"oracle reference-cost mode (no KV cache), {dt:.2f} s CPU"}
+
+    if rank == 0:
+        h2d = int(sum(lens)) * 4
+        d2h = int(n_win * (cap + 1) * 4 + ((args.max_depth + 15) // 16) * 4)
+        line = {
+            "metric": "audio-seconds/sec", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 (fp16-exact weights, fp32 activations/accumulate)", "data": "synthetic",
+            "config": {"workload": f"{args.model}, {len(chunks)}x30 s synthetic chunk(s) per GPU, R-mode ({len(bounds)} reference windows/chunk), "
+                                   f"greedy (beam {args.beam}), max_depth {args.max_depth}",
+                       "parallelism": f"dp{world} (windows sharded, weights replicated, one NCCL token all-gather)",
+                       "l2": "flushed between timed iterations (256 MB write)", "timing": "wall clock around the synchronous C-ABI call, "
+                       "torch.cuda.synchronize() both sides; device_ms = CUDA events on the library stream",
+                       "decode_steps_executed": steps_run, "windows_per_gpu": n_win},
+            "device_ms_per_step": ms_dev, "phase_ms": phase,
+            "rtf": (ms_step / 1000.0) / audio_s,
+            "e2e": {"value": e2e_val, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e, "api": "wb_waveform_to_tokens (windowing + decode + overlap merge), pinned host waveform"},
+            "gpu_launches": launches // max(args.steps, 1),
+            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "tokens_checksum": int(sum(sum(t) for t in toks) % (1 << 31)),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -88,6 +88,10 @@ int wb_model_create(const wb_dims* dims, int device, wb_model** out);
  * (dump.py:141-145), Conv1d weights [out, in, k], embeddings [rows, d], LayerNorm eps is a
  * 1-element tensor.  Data is copied. */
 int wb_model_set_tensor(wb_model* m, const char* path, const float* data, const int64_t* shape, int ndim);
+/* burn's nn::LayerNorm is third-party and un-vendored: burn 0.9 (the reference's pin, Cargo.lock:242-244)
+ * normalises by (sqrt(var) + eps); later burn releases by sqrt(var + eps).  outside != 0 selects the
+ * former (default).  Must be called before wb_model_finalize. */
+int wb_model_set_layernorm_eps_mode(wb_model* m, int outside);
 /* Validates that every tensor of the tree is present, uploads and re-lays the weights. */
 int wb_model_finalize(wb_model* m);
 void wb_model_destroy(wb_model* m);
@@ -172,6 +176,11 @@ void wb_kernel_launch_count_reset(void);
  * wb_transcribe_windows* call, in milliseconds: [0]=log-mel, [1]=encoder+cross-KV, [2]=decode, [3]=total */
 int wb_session_last_timings(wb_session* s, float* ms_out4);
 int wb_session_last_steps(wb_session* s, int64_t* n_steps_out);
+/* roofline aid: re-runs n_steps greedy decoder steps on the currently encoded windows with CUDA
+ * events (session stream) around the dominant kernel of the step -- the logits GEMV -- and around
+ * each whole step; returns the average durations in milliseconds. */
+int wb_session_profile_decode(wb_session* s, const wb_special_ids* ids, int n_steps, float* logits_kernel_ms,
+                              float* step_ms);
 
 #ifdef __cplusplus
 }

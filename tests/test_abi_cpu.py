@@ -1,0 +1,79 @@
+"""CPU tests of the C-ABI boundary: the library loads, exports every symbol include/whisper_b200.h
+declares, its host-side logic (beam.rs / windowing restated in C++) matches the oracle, and
+compute entry points fail loudly without a GPU (no CPU fallback)."""
+import ctypes as C
+import json
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+import wb200  # noqa: F401
+from oracle import beam as o_beam, transcribe as o_tr
+from whisper_burn_b200 import audio, beam, ffi, transcribe
+
+ROOT = Path(__file__).resolve().parent.parent
+G = Path(__file__).resolve().parent / "golden"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    if not ffi.library_path().exists():
+        import __graft_entry__ as ge
+        ge.build()
+
+
+def test_header_symbols_exported():
+    header = (ROOT / "include" / "whisper_b200.h").read_text()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)      # drop comments
+    declared = set(re.findall(r"\b(wb_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(ffi.SYMBOLS), declared ^ set(ffi.SYMBOLS)
+    lib = ffi.lib()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert b"sm_100a" in lib.wb_version()
+
+
+def test_max_waveform_samples_and_windows_match_oracle():
+    for n in (0, 1, 10, 1490, 2990):
+        assert audio.max_waveform_samples(n) == 160 * (n + 1) - 1
+    for n_samples in (0, 1, 399, 238559, 238560, 480000, 1000000):
+        assert transcribe.window_bounds(n_samples, 16000, 238559) == o_tr.window_bounds(n_samples, 16000, 238559)
+    assert transcribe.window_bounds(5000, 16000, 100) == o_tr.window_bounds(5000, 16000, 100)   # shift saturates to 1
+
+
+def test_get_top_elements_matches_beam_rs_table():
+    for c in json.loads((G / "beam_ties.json").read_text()):
+        assert beam.get_top_elements(c["scores"], c["num"]) == c["expect"]
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        s = rng.integers(-4, 5, size=int(rng.integers(0, 40))).astype(np.float64)
+        k = int(rng.integers(1, 7))
+        assert beam.get_top_elements(s, k) == o_beam.get_top_elements(list(range(len(s))), lambda i: s[i], k)
+
+
+def test_find_chunk_overlap_matches_oracle():
+    rng = np.random.default_rng(1)
+    for _ in range(300):
+        a = [int(v) for v in rng.integers(0, 6, size=int(rng.integers(0, 60)))]
+        b = [int(v) for v in rng.integers(0, 6, size=int(rng.integers(0, 60)))]
+        assert transcribe.find_chunk_overlap(a, b, 40, 3) == o_tr.find_chunk_overlap(a, b, 40, 3)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU error path")
+def test_compute_fails_loudly_without_gpu():
+    with pytest.raises(ffi.WbError) as e:
+        audio.prep_audio(np.zeros((1, 1600), np.float32))
+    assert e.value.code == ffi.WB_ERR_CUDA and "no CPU fallback" in e.value.msg
+    h = C.c_void_p()
+    dims = ffi.Dims(80, 1500, 128, 2, 2, 1024, 448, 128, 2, 2)
+    assert ffi.lib().wb_model_create(C.byref(dims), 0, C.byref(h)) == ffi.WB_ERR_CUDA
+
+
+def test_contract_violations_are_invalid_arg():
+    # the reference panics (audio.rs:292); the ABI reports WB_ERR_INVALID_ARG before touching the device
+    with pytest.raises(ffi.WbError) as e:
+        audio.prep_audio(np.zeros((1, 399), np.float32))
+    assert e.value.code == ffi.WB_ERR_INVALID_ARG

@@ -182,6 +182,14 @@ int wb_model_set_tensor(wb_model* m, const char* path, const float* data, const 
     });
 }
 
+int wb_model_set_layernorm_eps_mode(wb_model* m, int outside) {
+    return guarded([&] {
+        WB_REQUIRE(m != nullptr, "null model");
+        if (m->impl.finalized) wb::fail(WB_ERR_STATE, "model already finalized");
+        m->impl.ln_eps_outside = outside ? 1 : 0;
+    });
+}
+
 int wb_model_finalize(wb_model* m) {
     return guarded([&] {
         WB_REQUIRE(m != nullptr, "null model");
@@ -440,6 +448,15 @@ int wb_session_last_timings(wb_session* s, float* ms_out4) {
     return guarded([&] {
         WB_REQUIRE(s && ms_out4, "null pointer");
         for (int i = 0; i < 4; ++i) ms_out4[i] = s->impl->last_ms[i];
+    });
+}
+
+int wb_session_profile_decode(wb_session* s, const wb_special_ids* ids, int n_steps, float* logits_kernel_ms,
+                              float* step_ms) {
+    return guarded([&] {
+        WB_REQUIRE(s && ids && logits_kernel_ms && step_ms, "null pointer");
+        const int64_t prompt[4] = {ids->sot, ids->lang, ids->transcribe, ids->notimestamps};
+        s->impl->profile_decode(prompt, 4, n_steps, ids->eot, logits_kernel_ms, step_ms);
     });
 }
 

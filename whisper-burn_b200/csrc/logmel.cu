@@ -26,7 +26,7 @@ constexpr int JC = 16;                  // samples per basis stage
 constexpr int XROW = 161;               // smem stride of one hop row (160 samples + 1 pad)
 constexpr int NHOP = FR + 2;            // hop rows touched by FR frames: (FR-1)*160 + 400 samples
 constexpr int NSAMP = (FR - 1) * HOP + N_FFT;
-constexpr int XS_FLOATS = NHOP * XROW;
+constexpr int XS_FLOATS = (NHOP * XROW + 3) / 4 * 4;   // keeps the stage buffer 16-byte aligned
 constexpr int PS_STRIDE = FR + 1;
 constexpr int STAGE_FLOATS = KPAD * PS_STRIDE;   // >= JC * 2 * KPAD, shared by basis stage and power tile
 constexpr int LOGMEL_THREADS = 256;

@@ -59,6 +59,7 @@ Session::Session(Model* model, int64_t max_w, int64_t max_b, int64_t max_text_le
 
 Session::~Session() {
     if (st) cudaStreamSynchronize(st);
+    for (auto& e : prof_ev) cudaEventDestroy(e);
     if (h_int) cudaFreeHost(h_int);
     if (h_float) cudaFreeHost(h_float);
     for (auto& e : ev)
@@ -283,6 +284,8 @@ void Session::step_core(bool with_logits, int mask_mode, int k, bool greedy, int
     const bool h16 = m->fp16_exact;
     const float qk_scale = (float)std::pow((double)d / (double)H, -0.25);
     const int* anc = anc_identity ? nullptr : (anc_cur == 0 ? anc0.p : anc1.p);
+    const bool pe = prof && with_logits && (size_t)(4 * prof_n + 3) < prof_ev.size();
+    if (pe) WB_CUDA(cudaEventRecord(prof_ev[(size_t)4 * prof_n + 0], st));
     launch_dec_embed(cur_tok.p, m->tok_emb32, m->dec_pos, pos.p, dx.p, R, d, st);
     auto wptr = [&](const LinearW& w) -> const void* { return h16 ? (const void*)w.w16 : (const void*)w.w32; };
     for (int l = 0; l < L; ++l) {
@@ -343,7 +346,9 @@ void Session::step_core(bool with_logits, int mask_mode, int k, bool greedy, int
         g.bias = nullptr; g.N = V; g.K = d; g.R = R; g.in_mode = IN_LN; g.in = dx.p;
         g.ln_g = m->dec_ln.g; g.ln_b = m->dec_ln.b; g.ln_eps = m->dec_ln.eps; g.eps_outside = m->ln_eps_outside;
         g.seg[0] = GemvSeg{0, logits.p, V, 0, 1.0f};
+        if (pe) WB_CUDA(cudaEventRecord(prof_ev[(size_t)4 * prof_n + 1], st));
         launch_dec_gemv(g, h16, st);
+        if (pe) WB_CUDA(cudaEventRecord(prof_ev[(size_t)4 * prof_n + 2], st));
         LogSoftmaxArgs s;
         s.logits = logits.p; s.V = V; s.is_special = have_special ? is_special.p : nullptr; s.mask_mode = mask_mode;
         s.pos = pos.p; s.k = k; s.topk_id = topk_id.p; s.topk_lp = topk_lp.p; s.logprob_out = logprob_out;
@@ -352,7 +357,37 @@ void Session::step_core(bool with_logits, int mask_mode, int k, bool greedy, int
         launch_logsoftmax_topk(s, R, st);
     }
     launch_dec_advance(pos.p, greedy ? finished.p : nullptr, R, n_unfinished.p, st);
+    if (pe) {
+        WB_CUDA(cudaEventRecord(prof_ev[(size_t)4 * prof_n + 3], st));
+        ++prof_n;
+    }
     ++host_pos;
+}
+
+void Session::profile_decode(const int64_t* prompt, int64_t prompt_len, int n_steps, int64_t eot, float* logits_ms,
+                             float* step_ms) {
+    WB_REQUIRE(n_steps >= 1 && prompt_len + n_steps <= t_max, "profile: n_steps out of range");
+    while (prof_ev.size() < (size_t)4 * n_steps) {
+        cudaEvent_t e;
+        WB_CUDA(cudaEventCreate(&e));
+        prof_ev.push_back(e);
+    }
+    begin(prompt, prompt_len);
+    prof = true;
+    prof_n = 0;
+    for (int i = 0; i < n_steps; ++i) step_core(true, 2, 1, true, (int)eot, nullptr);
+    prof = false;
+    WB_CUDA(cudaStreamSynchronize(st));
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < prof_n; ++i) {
+        float t = 0.f;
+        WB_CUDA(cudaEventElapsedTime(&t, prof_ev[(size_t)4 * i + 1], prof_ev[(size_t)4 * i + 2]));
+        a += t;
+        WB_CUDA(cudaEventElapsedTime(&t, prof_ev[(size_t)4 * i + 0], prof_ev[(size_t)4 * i + 3]));
+        b += t;
+    }
+    *logits_ms = (float)(a / std::max(prof_n, 1));
+    *step_ms = (float)(b / std::max(prof_n, 1));
 }
 
 void Session::step_beams(int64_t n_rows, const int32_t* window_of_row, const int32_t* parent_row, const int64_t* token,

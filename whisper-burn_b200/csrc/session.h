@@ -58,6 +58,11 @@ struct Session {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float last_ms[4] = {0, 0, 0, 0};
     int64_t last_steps = 0;
+    // optional per-kernel profiling (wb_session_profile_decode)
+    bool prof = false;
+    std::vector<cudaEvent_t> prof_ev;   // 4 per step: step begin, logits begin, logits end, step end
+    int prof_n = 0;
+    void profile_decode(const int64_t* prompt, int64_t prompt_len, int n_steps, int64_t eot, float* logits_ms, float* step_ms);
 
     Session(Model* model, int64_t max_windows, int64_t max_beams, int64_t max_text_len, int kv_dtype);
     ~Session();

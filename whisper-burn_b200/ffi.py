@@ -48,6 +48,7 @@ SYMBOLS = {
     "wb_prep_audio_dev": (C.c_int, [C.c_int, _P, C.c_int64, C.c_int64, _P, _I64]),
     "wb_model_create": (C.c_int, [C.POINTER(Dims), C.c_int, C.POINTER(_P)]),
     "wb_model_set_tensor": (C.c_int, [_P, C.c_char_p, _F, _I64, C.c_int]),
+    "wb_model_set_layernorm_eps_mode": (C.c_int, [_P, C.c_int]),
     "wb_model_finalize": (C.c_int, [_P]),
     "wb_model_destroy": (None, [_P]),
     "wb_model_get_dims": (C.c_int, [_P, C.POINTER(Dims)]),
@@ -77,6 +78,7 @@ SYMBOLS = {
     "wb_kernel_launch_count_reset": (None, []),
     "wb_session_last_timings": (C.c_int, [_P, _F]),
     "wb_session_last_steps": (C.c_int, [_P, _I64]),
+    "wb_session_profile_decode": (C.c_int, [_P, C.POINTER(SpecialIds), C.c_int, _F, _F]),
 }
 
 _lib = None

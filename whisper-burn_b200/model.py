@@ -31,7 +31,7 @@ class Whisper:
     """model::Whisper (mod.rs:41-71).  ``tensors`` uses the reference's npy-tree paths
     (load.rs / dump.py), Linear weights in burn layout [d_in, d_out]."""
 
-    def __init__(self, config, tensors: dict, device: int = 0):
+    def __init__(self, config, tensors: dict, device: int = 0, ln_eps_outside: bool = True):
         self.config = config
         self._h = C.c_void_p()
         dims = config.to_c() if hasattr(config, "to_c") else ffi.Dims(*[getattr(config, f) for f, _ in ffi.Dims._fields_])
@@ -42,6 +42,7 @@ class Whisper:
                 a = np.ascontiguousarray(np.asarray(arr, dtype=np.float32))
                 shape = np.asarray(a.shape if a.ndim else (1,), dtype=np.int64)
                 ffi.check(L.wb_model_set_tensor(self._h, path.encode(), ffi.fptr(a.reshape(-1)), ffi.i64ptr(shape), len(shape)))
+            ffi.check(L.wb_model_set_layernorm_eps_mode(self._h, 1 if ln_eps_outside else 0))
             ffi.check(L.wb_model_finalize(self._h))
         except Exception:
             L.wb_model_destroy(self._h)

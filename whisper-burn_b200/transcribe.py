@@ -124,6 +124,13 @@ class Session:
         ffi.check(ffi.lib().wb_session_last_timings(self._h, ffi.fptr(buf)))
         return {"logmel": float(buf[0]), "encoder": float(buf[1]), "decode": float(buf[2]), "total": float(buf[3])}
 
+    def profile_decode(self, special, n_steps: int = 50):
+        """(average logits-GEMV ms, average whole-step ms) over n_steps re-run greedy steps."""
+        ids = ffi.SpecialIds(special.sot, special.lang, special.transcribe, special.notimestamps, special.eot)
+        a, b = C.c_float(0), C.c_float(0)
+        ffi.check(ffi.lib().wb_session_profile_decode(self._h, C.byref(ids), n_steps, C.byref(a), C.byref(b)))
+        return float(a.value), float(b.value)
+
     def last_steps(self) -> int:
         n = C.c_int64(0)
         ffi.check(ffi.lib().wb_session_last_steps(self._h, C.byref(n)))
