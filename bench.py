@@ -96,8 +96,9 @@ class ClockSampler:
 
 
 def workload(args, rank: int, world: int):
-    from oracle import synth
-    dims, w_np, _ = synth.make_weights(args.model, seed=0)
+    import wb200  # noqa: F401
+    from whisper_burn_b200 import synth
+    dims, w_np = synth.make_weights(args.model, seed=0)
     sp = synth.special_tokens(dims)
     chunk_ids = [rank * args.chunks_per_gpu + i for i in range(args.chunks_per_gpu)]
     chunks = [synth.chunk_waveform(c, CHUNK_SAMPLES) for c in chunk_ids]
@@ -108,7 +109,7 @@ def cpu_reference_pass(args, dims, w_t, sp, chunk, n_windows: int):
     """The reference's own CPU path restated (oracle, reference-cost mode: no KV cache, full-prefix
     recompute, all-position logits, per-window DFT/filterbank rebuild) on windows of one chunk."""
     import torch
-    from oracle import audio as o_audio, transcribe as o_tr
+    from oracle import audio as o_audio, transcribe as o_tr  # CPU-baseline leg only
     window_len = o_audio.max_waveform_samples(dims.n_audio_ctx - o_tr.PADDING)
     bounds = o_tr.window_bounds(len(chunk), 16000, window_len)
     if n_windows > 0:
@@ -164,8 +165,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     import wb200  # noqa: F401
-    from whisper_burn_b200 import ffi, model, shard, transcribe
-    from oracle import audio as o_audio, transcribe as o_tr
+    from whisper_burn_b200 import audio, ffi, model, shard, transcribe
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -181,8 +181,8 @@ def run_ours(args):
     dims, w_np, sp, chunk_ids, chunks = workload(args, rank, world)
     is_special = (np.arange(dims.n_vocab) >= sp.first_special).astype(np.uint8)
     wh = model.Whisper(dims, w_np, device=local_rank)
-    window_len = o_audio.max_waveform_samples(dims.n_audio_ctx - o_tr.PADDING)
-    bounds = o_tr.window_bounds(CHUNK_SAMPLES, 16000, window_len)
+    window_len = audio.max_waveform_samples(dims.n_audio_ctx - 10)        # transcribe.rs:32-34 (C ABI, host side)
+    bounds = transcribe.window_bounds(CHUNK_SAMPLES, 16000, window_len)   # transcribe.rs:114-138
     n_win = len(bounds) * len(chunks)
     sess = transcribe.Session(wh, max_windows=n_win, max_beams=max(args.beam, 1), max_text_len=4 + args.max_depth + 1)
 
@@ -293,9 +293,9 @@ def run_ours(args):
     # ---- CPU baseline beside it (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import synth
+        from oracle import synth as o_synth
         torch.set_num_threads(os.cpu_count() or 1)
-        w_t = synth.to_torch(w_np)
+        w_t = o_synth.to_torch(w_np)
         span, dt, nw, _ = cpu_reference_pass(args, dims, w_t, sp, chunks[0], args.cpu_baseline_windows)
         cpu = {"value": span / dt, "unit": "audio-s/s", "cores": torch.get_num_threads(), "kind": "port",
                "sample": f"{nw} of 3 reference windows of chunk {chunk_ids[0]} ({span:.2f} s audio), greedy depth {args.max_depth}, "
