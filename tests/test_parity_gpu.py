@@ -76,12 +76,13 @@ def test_prep_audio_golden_and_errors():
 
 
 def test_prep_audio_scale_property_full_size():
-    """Size-independent property at the full 30 s size: scaling the waveform by 2^k shifts every
-    un-floored log-mel value by exactly k*log10(2)/2 (the global max shifts with it)."""
+    """Size-independent property at the full 30 s size: scaling the waveform by 1/4 shifts every
+    log-mel value by log10(1/16)/4 (power scales by 1/16; the max-8 clamp floor shifts with the max)."""
     w = synth.chunk_waveform(3) * 0.5
     a = audio.prep_audio(w[None])
     b = audio.prep_audio((w * 0.25)[None])
-    assert np.abs(a - b).max() < 5e-6          # both normalised by their own max -> identical up to rounding
+    assert a.shape == (1, 80, 3000)
+    assert np.abs((a - b) - np.log10(16.0) / 4.0).max() < 2e-6
 
 
 # ---------------------------------------------------------------- encoder / decoder (mod.rs)
