@@ -46,6 +46,19 @@ def parse_args():
     return ap.parse_args()
 
 
+def host_cores() -> int:
+    """Threads the CPU arm can really use: affinity mask capped by the cgroup CPU quota (the GPU
+    boxes expose 128 logical CPUs under a 16-CPU quota; oversubscribing MKL there is ~100x slower)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = Path("/sys/fs/cgroup/cpu.max").read_text().split()
+        if q != "max":
+            n = min(n, max(1, int(float(q) / float(per))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
 def peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -134,7 +147,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import synth
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(host_cores())
     dims, w_np, w_t = synth.make_weights(args.model, seed=0)
     sp = synth.special_tokens(dims)
     chunk = synth.chunk_waveform(0, CHUNK_SAMPLES)
@@ -294,7 +307,7 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import synth as o_synth
-        torch.set_num_threads(os.cpu_count() or 1)
+        torch.set_num_threads(host_cores())
         w_t = o_synth.to_torch(w_np)
         span, dt, nw, _ = cpu_reference_pass(args, dims, w_t, sp, chunks[0], args.cpu_baseline_windows)
         cpu = {"value": span / dt, "unit": "audio-s/s", "cores": torch.get_num_threads(), "kind": "port",
