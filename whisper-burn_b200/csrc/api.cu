@@ -229,6 +229,7 @@ int wb_forward_decoder(wb_model* m, const int64_t* tokens, int64_t n_batch, int6
         const int V = D.n_vocab;
         wb::Session s(&m->impl, n_batch, 1, std::min<int64_t>(D.n_text_ctx, std::max<int64_t>(seq_len, 2)), WB_KV_F32);
         s.load_encoder_output_host(encoder_output, n_batch, n_enc_ctx);
+        s.full_logits = true;
         // position by position through the cached step; logits of every position are kept
         wb::DevBuf<float> all;
         all.alloc((size_t)n_batch * seq_len * V);

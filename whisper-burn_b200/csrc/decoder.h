@@ -77,6 +77,113 @@ struct LogSoftmaxArgs {
     int eot = -1;
 };
 
+// ---- fused step, version 2 (decoder2.cu) ----------------------------------------------------------
+constexpr int DEC2_KC = 8;   // top candidates kept per logits CTA and row (>= k + 1)
+
+struct Dec2SelfArgs {
+    float* x = nullptr;            // [R][d] residual stream (complete on entry, updated on exit)
+    int R = 0, d = 0;
+    const float* ln_g = nullptr;
+    const float* ln_b = nullptr;
+    float ln_eps = 1e-5f;
+    int eps_outside = 1;
+    const void* Wqkv = nullptr;    // [3d][d]
+    const float* bqkv = nullptr;
+    const void* Wo = nullptr;      // [d][d]
+    const float* bo = nullptr;
+    float qk_scale = 1.0f;
+    float* kc = nullptr;           // this layer's self K cache [Rmax][t_max][d]
+    float* vc = nullptr;
+    const int* anc = nullptr;      // [R][t_max] or null (identity)
+    int t_max = 0;
+    const int* pos = nullptr;
+    float* ypart = nullptr;        // [H][R][d]
+    unsigned int* counter = nullptr;
+};
+
+struct Dec2CrossArgs {
+    float* x = nullptr;
+    int R = 0, d = 0;
+    const float* ln_g = nullptr;
+    const float* ln_b = nullptr;
+    float ln_eps = 1e-5f;
+    int eps_outside = 1;
+    const void* Wq = nullptr;      // [d][d]
+    const float* bq = nullptr;
+    const void* Wo = nullptr;
+    const float* bo = nullptr;
+    float qk_scale = 1.0f;
+    const float* ckv = nullptr;    // this layer's cross K|V rows [M][2d]
+    const int* row_window = nullptr;
+    const int64_t* win_row_off = nullptr;
+    const int* win_T = nullptr;
+    int kmax = 0;                  // max keys per split
+    float* ypart = nullptr;        // [H][S][R][d]
+    float* part_m = nullptr;       // [H][S][R]
+    float* part_l = nullptr;
+    unsigned int* counter = nullptr;
+};
+
+struct Dec2MlpArgs {
+    float* x = nullptr;
+    int R = 0, d = 0;
+    const float* ln_g = nullptr;
+    const float* ln_b = nullptr;
+    float ln_eps = 1e-5f;
+    int eps_outside = 1;
+    const void* W1 = nullptr;      // [4d][d]
+    const float* b1 = nullptr;
+    const void* W2 = nullptr;      // [d][4d]
+    const float* b2 = nullptr;
+    float* ypart = nullptr;        // [4d/32][R][d]
+    unsigned int* counter = nullptr;
+};
+
+struct Dec2LogitsArgs {
+    const float* x = nullptr;
+    int R = 0, d = 0, V = 0;
+    const float* ln_g = nullptr;
+    const float* ln_b = nullptr;
+    float ln_eps = 1e-5f;
+    int eps_outside = 1;
+    const void* E = nullptr;       // token embedding [V][d]
+    const uint8_t* is_special = nullptr;
+    int mask_mode = 0;
+    const int* pos = nullptr;
+    float* logits_out = nullptr;   // optional [R][V] raw logits (stateless forward_decoder)
+    float* part_m = nullptr;       // [n_ctas][R]
+    float* part_s = nullptr;
+    float* part_v = nullptr;       // [n_ctas][R][KC]
+    int* part_i = nullptr;
+};
+
+struct Dec2FinishArgs {
+    int n_parts = 0;
+    const float* part_m = nullptr;
+    const float* part_s = nullptr;
+    const float* part_v = nullptr;
+    const int* part_i = nullptr;
+    int k = 1;
+    int* topk_id = nullptr;
+    float* topk_lp = nullptr;
+    int greedy = 0;
+    int* tokens = nullptr;
+    int* lengths = nullptr;
+    int* cur_tok = nullptr;
+    int* finished = nullptr;
+    int t_max = 0;
+    int eot = -1;
+    int* pos = nullptr;
+    int* n_unfinished = nullptr;
+    unsigned int* counter = nullptr;
+};
+
+void launch_dec2_self(const Dec2SelfArgs& a, int H, bool w_half, cudaStream_t st);
+void launch_dec2_cross(const Dec2CrossArgs& a, int H, int S, bool w_half, cudaStream_t st);
+void launch_dec2_mlp(const Dec2MlpArgs& a, bool w_half, cudaStream_t st);
+void launch_dec2_logits(const Dec2LogitsArgs& a, int n_ctas, bool w_half, cudaStream_t st);
+void launch_dec2_finish(const Dec2FinishArgs& a, int R, cudaStream_t st);
+
 void launch_dec_embed(const int* tok, const float* emb, const float* pos_emb, const int* pos_ptr, float* x, int R,
                       int d, cudaStream_t st);
 void launch_dec_gemv(const GemvArgs& a, bool w_half, cudaStream_t st);

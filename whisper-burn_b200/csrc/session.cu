@@ -4,6 +4,7 @@
 // Windows of one call are batched: encoder rows of all windows are packed back to back.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "session.h"
@@ -51,6 +52,19 @@ Session::Session(Model* model, int64_t max_w, int64_t max_b, int64_t max_text_le
     pos.alloc(1); n_unfinished.alloc(1);
     topk_id.alloc((size_t)Rmax * kmax); topk_lp.alloc((size_t)Rmax * kmax);
     is_special.alloc(V);
+    {
+        const char* e = getenv("WB200_DECODER");
+        if (e && e[0] == '1') dec_version = 1;
+        cudaDeviceProp prop;
+        WB_CUDA(cudaGetDeviceProperties(&prop, m->device));
+        n_logit_ctas = 2 * prop.multiProcessorCount;
+        const size_t n_part = (size_t)std::max(H * n_splits, 4 * d / 32);
+        ypart.alloc(n_part * Rmax * d);
+        lg_m.alloc((size_t)n_logit_ctas * Rmax); lg_s.alloc((size_t)n_logit_ctas * Rmax);
+        lg_v.alloc((size_t)n_logit_ctas * Rmax * DEC2_KC); lg_i.alloc((size_t)n_logit_ctas * Rmax * DEC2_KC);
+        tickets.alloc(8);
+        WB_CUDA(cudaMemsetAsync(tickets.p, 0, 8 * sizeof(unsigned int), st));
+    }
     WB_CUDA(cudaMallocHost((void**)&h_int, sizeof(int) * (4 * (size_t)Rmax + 16 + (size_t)Rmax * kmax)));
     WB_CUDA(cudaMallocHost((void**)&h_float, sizeof(float) * (size_t)Rmax * kmax));
     WB_CUDA(cudaMemsetAsync(is_special.p, 0, V, st));
@@ -278,7 +292,71 @@ void Session::begin(const int64_t* prompt, int64_t prompt_len) {
     WB_CUDA(cudaStreamSynchronize(st));
 }
 
+// One decoder position, fused kernels (decoder2.cu): embed, 3 kernels per layer, logits + finish.
+void Session::step_core_v2(bool with_logits, int mask_mode, int k, bool greedy, int eot) {
+    const wb_dims& D = m->dims;
+    const int d = D.n_text_state, H = D.n_text_head, L = D.n_text_layer, V = D.n_vocab;
+    const bool h16 = m->fp16_exact;
+    const float qk_scale = (float)std::pow((double)d / (double)H, -0.25);
+    const int* anc = anc_identity ? nullptr : (anc_cur == 0 ? anc0.p : anc1.p);
+    auto wptr = [&](const LinearW& w) -> const void* { return h16 ? (const void*)w.w16 : (const void*)w.w32; };
+    const bool pe = prof && with_logits && (size_t)(4 * prof_n + 3) < prof_ev.size();
+    if (pe) WB_CUDA(cudaEventRecord(prof_ev[(size_t)4 * prof_n + 0], st));
+    launch_dec_embed(cur_tok.p, m->tok_emb32, m->dec_pos, pos.p, dx.p, R, d, st);
+    for (int l = 0; l < L; ++l) {
+        const DecBlockW& B = m->dec[(size_t)l];
+        Dec2SelfArgs sa;
+        sa.x = dx.p; sa.R = R; sa.d = d; sa.ln_g = B.attn_ln.g; sa.ln_b = B.attn_ln.b; sa.ln_eps = B.attn_ln.eps;
+        sa.eps_outside = m->ln_eps_outside; sa.Wqkv = wptr(B.qkv); sa.bqkv = B.qkv.b; sa.Wo = wptr(B.out);
+        sa.bo = B.out.b; sa.qk_scale = qk_scale; sa.kc = kc.p + (size_t)l * Rmax * t_max * d;
+        sa.vc = vc.p + (size_t)l * Rmax * t_max * d; sa.anc = anc; sa.t_max = t_max; sa.pos = pos.p;
+        sa.ypart = ypart.p; sa.counter = tickets.p + 0;
+        launch_dec2_self(sa, H, h16, st);
+        Dec2CrossArgs ca;
+        ca.x = dx.p; ca.R = R; ca.d = d; ca.ln_g = B.cross_ln.g; ca.ln_b = B.cross_ln.b; ca.ln_eps = B.cross_ln.eps;
+        ca.eps_outside = m->ln_eps_outside; ca.Wq = wptr(B.cq); ca.bq = B.cq.b; ca.Wo = wptr(B.cout); ca.bo = B.cout.b;
+        ca.qk_scale = qk_scale; ca.ckv = ckv.p + (size_t)l * Mcap * 2 * d; ca.row_window = row_window.p;
+        ca.win_row_off = d_win_row_off.p; ca.win_T = d_win_T.p; ca.kmax = (Tcap + n_splits - 1) / n_splits;
+        ca.ypart = ypart.p; ca.part_m = part_m.p; ca.part_l = part_l.p; ca.counter = tickets.p + 1;
+        launch_dec2_cross(ca, H, n_splits, h16, st);
+        Dec2MlpArgs ma;
+        ma.x = dx.p; ma.R = R; ma.d = d; ma.ln_g = B.mlp_ln.g; ma.ln_b = B.mlp_ln.b; ma.ln_eps = B.mlp_ln.eps;
+        ma.eps_outside = m->ln_eps_outside; ma.W1 = wptr(B.mlp1); ma.b1 = B.mlp1.b; ma.W2 = wptr(B.mlp2);
+        ma.b2 = B.mlp2.b; ma.ypart = ypart.p; ma.counter = tickets.p + 2;
+        launch_dec2_mlp(ma, h16, st);
+    }
+    if (with_logits) {
+        Dec2LogitsArgs la;
+        la.x = dx.p; la.R = R; la.d = d; la.V = V; la.ln_g = m->dec_ln.g; la.ln_b = m->dec_ln.b;
+        la.ln_eps = m->dec_ln.eps; la.eps_outside = m->ln_eps_outside;
+        la.E = h16 ? (const void*)m->tok_emb16 : (const void*)m->tok_emb32;
+        la.is_special = have_special ? is_special.p : nullptr; la.mask_mode = mask_mode; la.pos = pos.p;
+        la.logits_out = full_logits ? logits.p : nullptr;
+        la.part_m = lg_m.p; la.part_s = lg_s.p; la.part_v = lg_v.p; la.part_i = lg_i.p;
+        if (pe) WB_CUDA(cudaEventRecord(prof_ev[(size_t)4 * prof_n + 1], st));
+        launch_dec2_logits(la, n_logit_ctas, h16, st);
+        if (pe) WB_CUDA(cudaEventRecord(prof_ev[(size_t)4 * prof_n + 2], st));
+        Dec2FinishArgs fa;
+        fa.n_parts = n_logit_ctas; fa.part_m = lg_m.p; fa.part_s = lg_s.p; fa.part_v = lg_v.p; fa.part_i = lg_i.p;
+        fa.k = k; fa.topk_id = topk_id.p; fa.topk_lp = topk_lp.p; fa.greedy = greedy ? 1 : 0; fa.tokens = tokens.p;
+        fa.lengths = lengths.p; fa.cur_tok = cur_tok.p; fa.finished = finished.p; fa.t_max = t_max; fa.eot = eot;
+        fa.pos = pos.p; fa.n_unfinished = n_unfinished.p; fa.counter = tickets.p + 3;
+        launch_dec2_finish(fa, R, st);
+    } else {
+        launch_dec_advance(pos.p, nullptr, R, n_unfinished.p, st);
+    }
+    if (pe) {
+        WB_CUDA(cudaEventRecord(prof_ev[(size_t)4 * prof_n + 3], st));
+        ++prof_n;
+    }
+    ++host_pos;
+}
+
 void Session::step_core(bool with_logits, int mask_mode, int k, bool greedy, int eot, float* logprob_out) {
+    if (dec_version == 2 && k <= DEC2_KC - 1) {
+        step_core_v2(with_logits, mask_mode, k, greedy, eot);
+        return;
+    }
     const wb_dims& D = m->dims;
     const int d = D.n_text_state, H = D.n_text_head, L = D.n_text_layer, V = D.n_vocab;
     const bool h16 = m->fp16_exact;

@@ -58,6 +58,14 @@ struct Session {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float last_ms[4] = {0, 0, 0, 0};
     int64_t last_steps = 0;
+    // fused decoder step (decoder2.cu): partial buffers, tickets, switches
+    int dec_version = 2;         // WB200_DECODER=1 selects the unfused decoder.cu path (A/B testing)
+    bool full_logits = false;    // also write raw logits [R][V] (stateless forward_decoder)
+    int n_logit_ctas = 0;
+    DevBuf<float> ypart, lg_m, lg_s, lg_v;
+    DevBuf<int> lg_i;
+    DevBuf<unsigned int> tickets;
+    void step_core_v2(bool with_logits, int mask_mode, int k, bool greedy, int eot);
     // optional per-kernel profiling (wb_session_profile_decode)
     bool prof = false;
     std::vector<cudaEvent_t> prof_ev;   // 4 per step: step begin, logits begin, logits end, step end
