@@ -100,62 +100,87 @@ __device__ __forceinline__ void ln_rows(const float* __restrict__ x, int r0, int
     }
 }
 
-// acc[q][rr] = sum_k W[row_q][k] * xs[rr][k] for NF weight rows at once (all lanes get the sums)
-template <typename WT, int RC, int NF>
-__device__ __forceinline__ void dot_rows(const WT* (&wrow)[NF], const float* xs, int K, float (&acc)[NF][RC]) {
-    const int lane = threadIdx.x & 31;
+// Dot products of a block of weight rows with the RC activation rows in shared memory.
+// 8 lanes share one weight row (16 bytes each per step), so a warp instruction covers 4 rows and
+// the cross-lane reduction is 3 shuffles for 4 rows at once.  G row-groups are processed together
+// and the K loop is unrolled so that >= 2*G independent 16-byte loads are in flight per lane.
+// After the call lane (sub*8) holds acc[g][rr] for row (group g, sub).
+template <typename WT, int RC, int G>
+__device__ __forceinline__ void dot_groups(const WT* (&wrow)[G], const float* xs, int K, float (&acc)[G][RC]) {
+    const int l = threadIdx.x & 7;
 #pragma unroll
-    for (int q = 0; q < NF; ++q)
+    for (int g = 0; g < G; ++g)
 #pragma unroll
-        for (int rr = 0; rr < RC; ++rr) acc[q][rr] = 0.0f;
-    for (int v = lane; v < K / 8; v += 32) {
-        float w[NF][8];
+        for (int rr = 0; rr < RC; ++rr) acc[g][rr] = 0.0f;
+#pragma unroll 2
+    for (int k0 = l * 8; k0 < K; k0 += 64) {
+        float w[G][8];
 #pragma unroll
-        for (int q = 0; q < NF; ++q) load8(wrow[q] + v * 8, w[q]);
+        for (int g = 0; g < G; ++g) load8(wrow[g] + k0, w[g]);
 #pragma unroll
         for (int rr = 0; rr < RC; ++rr) {
-            const float4 x0 = *reinterpret_cast<const float4*>(xs + rr * K + v * 8);
-            const float4 x1 = *reinterpret_cast<const float4*>(xs + rr * K + v * 8 + 4);
+            const float4 x0 = *reinterpret_cast<const float4*>(xs + rr * K + k0);
+            const float4 x1 = *reinterpret_cast<const float4*>(xs + rr * K + k0 + 4);
             const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
-            for (int q = 0; q < NF; ++q)
+            for (int g = 0; g < G; ++g)
 #pragma unroll
-                for (int i = 0; i < 8; ++i) acc[q][rr] = fmaf(w[q][i], xv[i], acc[q][rr]);
+                for (int i = 0; i < 8; ++i) acc[g][rr] = fmaf(w[g][i], xv[i], acc[g][rr]);
         }
     }
 #pragma unroll
-    for (int q = 0; q < NF; ++q)
+    for (int g = 0; g < G; ++g)
 #pragma unroll
-        for (int rr = 0; rr < RC; ++rr) acc[q][rr] = warp_sum(acc[q][rr]);
+        for (int rr = 0; rr < RC; ++rr) {
+            float v = acc[g][rr];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            acc[g][rr] = v;
+        }
 }
 
-// y[rr][n] = sum_{c<KS} W[n][col0 + c] * a[rr][c] for all n < N (a slice of the columns of W);
-// LPR lanes cooperate on one weight row (KS values = LPR * 8).  Output: ypart[rr*ld + n].
+// y[rr][n] = sum_{c<KS} W[n][col0 + c] * a[rr][c] for all n < N (a column slice of W, KS = 32 or 64);
+// KS/8 lanes per weight row, U row-groups in flight.  Output: ypart[(r0+rr)*row_ld + n].
 template <typename WT, int RC, int KS>
 __device__ __forceinline__ void slice_matvec(const WT* __restrict__ W, int N, int K, int col0, const float* a_s /*[RC][KS]*/,
                                              float* __restrict__ ypart, int64_t row_ld, int r0, int R) {
     constexpr int LPR = KS / 8;           // lanes per weight row
     constexpr int RPI = 32 / LPR;         // weight rows per warp instruction
+    constexpr int U = 4;                  // row-groups in flight
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int sub = lane / LPR, l = lane % LPR;
-    for (int nb = warp * RPI; nb < N; nb += NW * RPI) {
-        const int n = nb + sub;
-        float w[8];
-        if (n < N) load8(W + (int64_t)n * K + col0 + l * 8, w);
-        else {
+    float av[RC][8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) w[i] = 0.0f;
+    for (int rr = 0; rr < RC; ++rr) {
+        const float4 a0 = *reinterpret_cast<const float4*>(a_s + rr * KS + l * 8);
+        const float4 a1 = *reinterpret_cast<const float4*>(a_s + rr * KS + l * 8 + 4);
+        av[rr][0] = a0.x; av[rr][1] = a0.y; av[rr][2] = a0.z; av[rr][3] = a0.w;
+        av[rr][4] = a1.x; av[rr][5] = a1.y; av[rr][6] = a1.z; av[rr][7] = a1.w;
+    }
+    for (int nb = warp * RPI; nb < N; nb += NW * RPI * U) {
+        float w[U][8];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int n = nb + u * NW * RPI + sub;
+            if (n < N) load8(W + (int64_t)n * K + col0 + l * 8, w[u]);
+            else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) w[u][i] = 0.0f;
+            }
         }
 #pragma unroll
-        for (int rr = 0; rr < RC; ++rr) {
-            const float4 a0 = *reinterpret_cast<const float4*>(a_s + rr * KS + l * 8);
-            const float4 a1 = *reinterpret_cast<const float4*>(a_s + rr * KS + l * 8 + 4);
-            float s = w[0] * a0.x;
-            s = fmaf(w[1], a0.y, s); s = fmaf(w[2], a0.z, s); s = fmaf(w[3], a0.w, s);
-            s = fmaf(w[4], a1.x, s); s = fmaf(w[5], a1.y, s); s = fmaf(w[6], a1.z, s); s = fmaf(w[7], a1.w, s);
+        for (int u = 0; u < U; ++u) {
+            const int n = nb + u * NW * RPI + sub;
 #pragma unroll
-            for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (l == 0 && n < N && r0 + rr < R) ypart[(int64_t)(r0 + rr) * row_ld + n] = s;
+            for (int rr = 0; rr < RC; ++rr) {
+                float s = w[u][0] * av[rr][0];
+#pragma unroll
+                for (int i = 1; i < 8; ++i) s = fmaf(w[u][i], av[rr][i], s);
+#pragma unroll
+                for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (l == 0 && n < N && r0 + rr < R) ypart[(int64_t)(r0 + rr) * row_ld + n] = s;
+            }
         }
     }
 }
@@ -176,6 +201,102 @@ __device__ __forceinline__ bool last_block_ticket(unsigned int* counter, unsigne
     return s_last != 0;
 }
 
+// One-pass (online softmax) attention of one query row over n keys; 4 lanes per key (16 dims each),
+// 8 keys per warp step, 2 steps unrolled -> 16 independent 16-byte loads in flight per lane.
+// key j lives at kptr(j) / vptr(j) (64 floats, 16-byte aligned); keys j = first, first+stride, ...
+// Result: every lane holds (m, l) of the warp and its 16 dims of the unnormalised output o[16]
+// (dims (lane&3)*16 .. +15), identical across the 8 key sub-groups.
+struct AttnAcc {
+    float m, l, o[16];
+};
+template <typename KF, typename VF>
+__device__ __forceinline__ void attn_warp(const float* qrow, int n_keys, int first, int stride, KF&& kptr, VF&& vptr,
+                                          AttnAcc& A) {
+    const int lane = threadIdx.x & 31, sub = lane >> 2, l4 = lane & 3;
+    float q[16];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float4 t = *reinterpret_cast<const float4*>(qrow + l4 * 16 + c * 4);
+        q[c * 4] = t.x; q[c * 4 + 1] = t.y; q[c * 4 + 2] = t.z; q[c * 4 + 3] = t.w;
+    }
+    A.m = -INFINITY;
+    A.l = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) A.o[c] = 0.0f;
+    constexpr int UK = 2;
+    for (int jb = first; jb < n_keys; jb += stride * 8 * UK) {   // warp-uniform trip count
+        float4 kk[UK][4], vv[UK][4];
+        bool ok[UK];
+#pragma unroll
+        for (int u = 0; u < UK; ++u) {
+            const int j = jb + (u * 8 + sub) * stride;
+            ok[u] = j < n_keys;
+            if (ok[u]) {
+                const float4* kp = reinterpret_cast<const float4*>(kptr(j)) + l4 * 4;
+                const float4* vp = reinterpret_cast<const float4*>(vptr(j)) + l4 * 4;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { kk[u][c] = __ldcg(kp + c); vv[u][c] = __ldcg(vp + c); }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { kk[u][c] = make_float4(0.f, 0.f, 0.f, 0.f); vv[u][c] = kk[u][c]; }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UK; ++u) {
+            float s = 0.0f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                s = fmaf(q[c * 4], kk[u][c].x, s); s = fmaf(q[c * 4 + 1], kk[u][c].y, s);
+                s = fmaf(q[c * 4 + 2], kk[u][c].z, s); s = fmaf(q[c * 4 + 3], kk[u][c].w, s);
+            }
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            if (ok[u]) {
+                const float mn = fmaxf(A.m, s);
+                const float corr = expf(A.m - mn);   // exp(-inf) = 0 on the first key
+                const float e = expf(s - mn);
+                A.l = A.l * corr + e;
+                A.m = mn;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    A.o[c * 4] = fmaf(e, vv[u][c].x, A.o[c * 4] * corr);
+                    A.o[c * 4 + 1] = fmaf(e, vv[u][c].y, A.o[c * 4 + 1] * corr);
+                    A.o[c * 4 + 2] = fmaf(e, vv[u][c].z, A.o[c * 4 + 2] * corr);
+                    A.o[c * 4 + 3] = fmaf(e, vv[u][c].w, A.o[c * 4 + 3] * corr);
+                }
+            }
+        }
+    }
+    // merge the 8 key sub-groups of the warp (lanes with equal lane&3)
+#pragma unroll
+    for (int off = 4; off < 32; off <<= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, A.m, off);
+        const float l2 = __shfl_xor_sync(0xffffffffu, A.l, off);
+        const float mn = fmaxf(A.m, m2);
+        const float c1 = A.m > -INFINITY ? expf(A.m - mn) : 0.0f;
+        const float c2 = m2 > -INFINITY ? expf(m2 - mn) : 0.0f;
+        A.l = A.l * c1 + l2 * c2;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const float o2 = __shfl_xor_sync(0xffffffffu, A.o[c], off);
+            A.o[c] = A.o[c] * c1 + o2 * c2;
+        }
+        A.m = mn;
+    }
+}
+
+// Combines the per-warp results of one row (WPR warps) into at[rr][64]; normalised iff `normalise`.
+// wm/wl: [RC][NW], wo: [RC][NW][64] in shared memory; returns (M, L) through smem scalars.
+template <int RC>
+__device__ __forceinline__ void attn_store_warp(const AttnAcc& A, int rr, int ws, float* wm, float* wl, float* wo) {
+    const int lane = threadIdx.x & 31;
+    if (lane < 4) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) wo[(rr * NW + ws) * 64 + lane * 16 + c] = A.o[c];
+    }
+    if (lane == 0) { wm[rr * NW + ws] = A.m; wl[rr * NW + ws] = A.l; }
+}
+
 // ------------------------------------------------------------------------------------------------
 // self-attention block
 template <typename WT, int RC>
@@ -186,109 +307,68 @@ dec2_self_kernel(const Dec2SelfArgs a) {
     const int p = *a.pos;
     float* xs = sm;                       // [RC][d]
     float* qs = xs + RC * d;              // [RC][64]
-    float* ks = qs + RC * 64;             // [RC][64]  new key (scaled)
-    float* vs = ks + RC * 64;             // [RC][64]  new value
-    float* at = vs + RC * 64;             // [RC][64]  attention output
-    float* sc = at + RC * 64;             // [RC][t_max + 1] scores / weights
-    float* wm = sc + RC * (a.t_max + 1);  // [RC][NW] per-warp max
+    float* at = qs + RC * 64;             // [RC][64]  attention output
+    float* wm = at + RC * 64;             // [RC][NW] per-warp max
     float* wl = wm + RC * NW;             // [RC][NW] per-warp sum
     float* wo = wl + RC * NW;             // [RC][NW][64] per-warp unnormalised output
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int sub = lane >> 3, l8 = lane & 7;
     const WT* Wqkv = reinterpret_cast<const WT*>(a.Wqkv);
     const WT* Wo = reinterpret_cast<const WT*>(a.Wo);
 
     ln_rows<RC>(a.x, r0, R, d, a.ln_g, a.ln_b, a.ln_eps, a.eps_outside, xs);
     __syncthreads();
-    // ---- q, k, v of head h: 192 weight rows, 4 at a time per warp
-    for (int f0 = warp * 4; f0 < 192; f0 += NW * 4) {
-        const WT* rows[4];
-        int nn[4];
+    // ---- q, k, v of head h: 3 blocks of 64 contiguous weight rows; a warp takes 2 row-groups (8 rows) at a time
+    for (int f0 = warp * 8; f0 < 192; f0 += NW * 8) {
+        const WT* rows[2];
+        int nn[2], ff[2];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int f = f0 + q;
-            nn[q] = (f >> 6) * d + h * 64 + (f & 63);
-            rows[q] = Wqkv + (int64_t)nn[q] * d;
+        for (int g = 0; g < 2; ++g) {
+            ff[g] = f0 + g * 4 + sub;
+            nn[g] = (ff[g] >> 6) * d + h * 64 + (ff[g] & 63);
+            rows[g] = Wqkv + (int64_t)nn[g] * d;
         }
-        float acc[4][RC];
-        dot_rows<WT, RC, 4>(rows, xs, d, acc);
+        float acc[2][RC];
+        dot_groups<WT, RC, 2>(rows, xs, d, acc);
+        if (l8 == 0) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
+            for (int g = 0; g < 2; ++g) {
+                const int part = ff[g] >> 6, j = ff[g] & 63;
+                const float bias = a.bqkv[nn[g]];
 #pragma unroll
-            for (int rr = 0; rr < RC; ++rr)
-                if (lane == q * RC + rr) {
-                    const int f = f0 + q, part = f >> 6, j = f & 63;
-                    float v = __fadd_rn(acc[q][rr], a.bqkv[nn[q]]);
+                for (int rr = 0; rr < RC; ++rr) {
+                    float v = __fadd_rn(acc[g][rr], bias);
                     if (part < 2) v = __fmul_rn(v, a.qk_scale);
-                    (part == 0 ? qs : (part == 1 ? ks : vs))[rr * 64 + j] = v;
                     const int r = r0 + rr;
-                    if (part > 0 && r < R) {
-                        float* cache = part == 1 ? a.kc : a.vc;
-                        cache[((int64_t)r * a.t_max + p) * d + h * 64 + j] = v;
-                    }
+                    if (part == 0) qs[rr * 64 + j] = v;
+                    else if (r < R) (part == 1 ? a.kc : a.vc)[((int64_t)r * a.t_max + p) * d + h * 64 + j] = v;
                 }
+            }
+        }
     }
-    __syncthreads();
-    // ---- attention of each row over positions 0..p (position p comes from shared memory)
+    __syncthreads();   // q in smem, this step's k/v visible in global memory to the whole CTA
+    // ---- attention of each row over positions 0..p of its ancestry
     constexpr int WPR = NW / RC;   // warps per row
     {
         const int rr = warp / WPR, ws = warp % WPR;
         const int r = r0 + rr;
-        const int n_keys = p + 1;
-        const int* anc = (a.anc && r < R) ? a.anc + (int64_t)r * a.t_max : nullptr;
-        const float* qrow = qs + rr * 64;
-        float lmax = -INFINITY;
-        if (r < R) {
-            for (int j = ws * 32 + lane; j < n_keys; j += WPR * 32) {
-                float s = 0.0f;
-                if (j == p) {
-#pragma unroll 16
-                    for (int c = 0; c < 64; ++c) s = fmaf(qrow[c], ks[rr * 64 + c], s);
-                } else {
-                    const int src = anc ? anc[j] : r;
-                    const float4* kp = reinterpret_cast<const float4*>(a.kc + ((int64_t)src * a.t_max + j) * d + h * 64);
-                    float4 kv[16];
+        if (rr < RC) {
+            AttnAcc A;
+            if (r < R) {
+                const int* anc = a.anc ? a.anc + (int64_t)r * a.t_max : nullptr;
+                const float* kc = a.kc + h * 64;
+                const float* vc = a.vc + h * 64;
+                const int t_max = a.t_max;
+                auto kp = [&](int j) { return kc + ((int64_t)((anc && j < p) ? anc[j] : r) * t_max + j) * d; };
+                auto vp = [&](int j) { return vc + ((int64_t)((anc && j < p) ? anc[j] : r) * t_max + j) * d; };
+                attn_warp(qs + rr * 64, p + 1, ws, WPR, kp, vp, A);
+            } else {
+                A.m = -INFINITY; A.l = 0.0f;
 #pragma unroll
-                    for (int c = 0; c < 16; ++c) kv[c] = __ldcg(kp + c);
-#pragma unroll
-                    for (int c = 0; c < 16; ++c) {
-                        const float4 q4 = *reinterpret_cast<const float4*>(qrow + c * 4);
-                        s = fmaf(q4.x, kv[c].x, s); s = fmaf(q4.y, kv[c].y, s);
-                        s = fmaf(q4.z, kv[c].z, s); s = fmaf(q4.w, kv[c].w, s);
-                    }
-                }
-                sc[rr * (a.t_max + 1) + j] = s;
-                lmax = fmaxf(lmax, s);
+                for (int c = 0; c < 16; ++c) A.o[c] = 0.0f;
             }
+            attn_store_warp<RC>(A, rr, ws, wm, wl, wo);
         }
-        lmax = warp_max(lmax);
-        // weights relative to this warp's max, then weighted values: lane owns dims lane, lane+32
-        float l = 0.0f, o0 = 0.0f, o1 = 0.0f;
-        if (r < R && lmax > -INFINITY) {
-            for (int jb = ws * 32; jb < n_keys; jb += WPR * 32) {
-                const int jn = min(32, n_keys - jb);
-                __syncwarp();
-                for (int jj = 0; jj < jn; ++jj) {
-                    const int j = jb + jj;
-                    const float e = expf(sc[rr * (a.t_max + 1) + j] - lmax);
-                    l += e;
-                    float v0, v1;
-                    if (j == p) {
-                        v0 = vs[rr * 64 + lane];
-                        v1 = vs[rr * 64 + 32 + lane];
-                    } else {
-                        const int src = anc ? anc[j] : r;
-                        const float* vp = a.vc + ((int64_t)src * a.t_max + j) * d + h * 64;
-                        v0 = __ldcg(vp + lane);
-                        v1 = __ldcg(vp + 32 + lane);
-                    }
-                    o0 = fmaf(e, v0, o0);
-                    o1 = fmaf(e, v1, o1);
-                }
-            }
-        }
-        if (lane == 0) { wm[rr * NW + ws] = lmax; wl[rr * NW + ws] = l; }
-        wo[(rr * NW + ws) * 64 + lane] = o0;
-        wo[(rr * NW + ws) * 64 + 32 + lane] = o1;
     }
     __syncthreads();
     for (int i = tid; i < RC * 64; i += NT) {
@@ -331,95 +411,61 @@ dec2_cross_kernel(const Dec2CrossArgs a) {
     float* xs = sm;                        // [RC][d]
     float* qs = xs + RC * d;               // [RC][64]
     float* at = qs + RC * 64;              // [RC][64]  unnormalised split output
-    float* sc = at + RC * 64;              // [RC][KMAX] scores
-    float* wm = sc + RC * a.kmax;          // [RC][NW]
+    float* wm = at + RC * 64;              // [RC][NW]
     float* wl = wm + RC * NW;
     float* wo = wl + RC * NW;              // [RC][NW][64]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int sub = lane >> 3, l8 = lane & 7;
     const WT* Wq = reinterpret_cast<const WT*>(a.Wq);
     const WT* Wo = reinterpret_cast<const WT*>(a.Wo);
 
     ln_rows<RC>(a.x, r0, R, d, a.ln_g, a.ln_b, a.ln_eps, a.eps_outside, xs);
     __syncthreads();
-    for (int f0 = warp * 4; f0 < 64; f0 += NW * 4) {
-        const WT* rows[4];
+    {   // q of head h: 64 rows = 16 row-groups, 2 per warp
+        const int f0 = warp * 8;
+        const WT* rows[2];
+        int ff[2];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) rows[q] = Wq + (int64_t)(h * 64 + f0 + q) * d;
-        float acc[4][RC];
-        dot_rows<WT, RC, 4>(rows, xs, d, acc);
+        for (int g = 0; g < 2; ++g) {
+            ff[g] = h * 64 + f0 + g * 4 + sub;
+            rows[g] = Wq + (int64_t)ff[g] * d;
+        }
+        float acc[2][RC];
+        dot_groups<WT, RC, 2>(rows, xs, d, acc);
+        if (l8 == 0) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
+            for (int g = 0; g < 2; ++g) {
+                const float bias = a.bq[ff[g]];
 #pragma unroll
-            for (int rr = 0; rr < RC; ++rr)
-                if (lane == q * RC + rr)
-                    qs[rr * 64 + f0 + q] = __fmul_rn(__fadd_rn(acc[q][rr], a.bq[h * 64 + f0 + q]), a.qk_scale);
+                for (int rr = 0; rr < RC; ++rr) qs[rr * 64 + (ff[g] - h * 64)] = __fmul_rn(__fadd_rn(acc[g][rr], bias), a.qk_scale);
+            }
+        }
     }
     __syncthreads();
     constexpr int WPR = NW / RC;
     {
         const int rr = warp / WPR, ws = warp % WPR;
         const int r = r0 + rr;
-        float lmax = -INFINITY, l = 0.0f, o0 = 0.0f, o1 = 0.0f;
-        int kb = 0, nk = 0;
-        const float* kbase = nullptr;
-        if (r < R) {
-            const int w = a.row_window[r];
-            const int T = a.win_T[w];
-            const int per = (T + S - 1) / S;
-            kb = sp * per;
-            nk = max(0, min(T, kb + per) - kb);
-            kbase = a.ckv + (a.win_row_off[w] + kb) * (int64_t)(2 * d) + h * 64;   // K at +0, V at +d
-        }
-        const float* qrow = qs + rr * 64;
-        for (int j = ws * 32 + lane; j < nk; j += WPR * 32) {
-            const float4* kp = reinterpret_cast<const float4*>(kbase + (int64_t)j * 2 * d);
-            float4 kv[16];
+        if (rr < RC) {
+            AttnAcc A;
+            if (r < R) {
+                const int w = a.row_window[r];
+                const int T = a.win_T[w];
+                const int per = (T + S - 1) / S;
+                const int kb = sp * per;
+                const int nk = max(0, min(T, kb + per) - kb);
+                const float* kbase = a.ckv + (a.win_row_off[w] + kb) * (int64_t)(2 * d) + h * 64;   // K at +0, V at +d
+                const int64_t ld = 2 * (int64_t)d;
+                auto kp = [&](int j) { return kbase + j * ld; };
+                auto vp = [&](int j) { return kbase + j * ld + d; };
+                attn_warp(qs + rr * 64, nk, ws, WPR, kp, vp, A);
+            } else {
+                A.m = -INFINITY; A.l = 0.0f;
 #pragma unroll
-            for (int c = 0; c < 16; ++c) kv[c] = __ldg(kp + c);
-            float s = 0.0f;
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                const float4 q4 = *reinterpret_cast<const float4*>(qrow + c * 4);
-                s = fmaf(q4.x, kv[c].x, s); s = fmaf(q4.y, kv[c].y, s);
-                s = fmaf(q4.z, kv[c].z, s); s = fmaf(q4.w, kv[c].w, s);
+                for (int c = 0; c < 16; ++c) A.o[c] = 0.0f;
             }
-            sc[rr * a.kmax + j] = s;
-            lmax = fmaxf(lmax, s);
+            attn_store_warp<RC>(A, rr, ws, wm, wl, wo);
         }
-        lmax = warp_max(lmax);
-        if (lmax > -INFINITY) {
-            for (int jb = ws * 32; jb < nk; jb += WPR * 32) {
-                const int jn = min(32, nk - jb);
-                __syncwarp();
-                int jj = 0;
-                for (; jj + 4 <= jn; jj += 4) {   // 4 keys in flight
-                    float e[4], v0[4], v1[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const float* vp = kbase + (int64_t)(jb + jj + u) * 2 * d + d;
-                        v0[u] = __ldg(vp + lane);
-                        v1[u] = __ldg(vp + 32 + lane);
-                        e[u] = expf(sc[rr * a.kmax + jb + jj + u] - lmax);
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        l += e[u];
-                        o0 = fmaf(e[u], v0[u], o0);
-                        o1 = fmaf(e[u], v1[u], o1);
-                    }
-                }
-                for (; jj < jn; ++jj) {
-                    const float* vp = kbase + (int64_t)(jb + jj) * 2 * d + d;
-                    const float e = expf(sc[rr * a.kmax + jb + jj] - lmax);
-                    l += e;
-                    o0 = fmaf(e, __ldg(vp + lane), o0);
-                    o1 = fmaf(e, __ldg(vp + 32 + lane), o1);
-                }
-            }
-        }
-        if (lane == 0) { wm[rr * NW + ws] = lmax; wl[rr * NW + ws] = l; }
-        wo[(rr * NW + ws) * 64 + lane] = o0;
-        wo[(rr * NW + ws) * 64 + 32 + lane] = o1;
     }
     __syncthreads();
     for (int i = tid; i < RC * 64; i += NT) {
@@ -462,16 +508,21 @@ dec2_cross_kernel(const Dec2CrossArgs a) {
         __syncthreads();
         for (int i = tid; i < R * d; i += NT) {
             const int r = i / d;
-            float s = 0.0f;
-            for (int hs = 0; hs < H * S; ++hs) s = fmaf(wgt[hs * R + r], __ldcg(a.ypart + (int64_t)hs * R * d + i), s);
-            a.x[i] = __fadd_rn(a.x[i], __fadd_rn(s, a.bo[i % d]));
+            float s0 = 0.0f, s1 = 0.0f;
+            int hs = 0;
+            for (; hs + 2 <= H * S; hs += 2) {
+                s0 = fmaf(wgt[hs * R + r], __ldcg(a.ypart + (int64_t)hs * R * d + i), s0);
+                s1 = fmaf(wgt[(hs + 1) * R + r], __ldcg(a.ypart + (int64_t)(hs + 1) * R * d + i), s1);
+            }
+            for (; hs < H * S; ++hs) s0 = fmaf(wgt[hs * R + r], __ldcg(a.ypart + (int64_t)hs * R * d + i), s0);
+            a.x[i] = __fadd_rn(a.x[i], __fadd_rn(s0 + s1, a.bo[i % d]));
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// MLP block: 32 hidden features per CTA
-constexpr int MLP_SLICE = 32;
+// MLP block: 64 hidden features per CTA
+constexpr int MLP_SLICE = 64;
 
 template <typename WT, int RC>
 __global__ void __launch_bounds__(NT)
@@ -479,24 +530,32 @@ dec2_mlp_kernel(const Dec2MlpArgs a) {
     extern __shared__ __align__(16) float sm[];
     const int d = a.d, c0 = blockIdx.x * MLP_SLICE, r0 = blockIdx.y * RC, R = a.R;
     float* xs = sm;                 // [RC][d]
-    float* hs = xs + RC * d;        // [RC][32]
+    float* hs = xs + RC * d;        // [RC][64]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int sub = lane >> 3, l8 = lane & 7;
     const WT* W1 = reinterpret_cast<const WT*>(a.W1);
     const WT* W2 = reinterpret_cast<const WT*>(a.W2);
     ln_rows<RC>(a.x, r0, R, d, a.ln_g, a.ln_b, a.ln_eps, a.eps_outside, xs);
     __syncthreads();
-    {
-        const int f0 = warp * 4;    // 8 warps x 4 = 32 features
-        const WT* rows[4];
+    {   // 64 features = 16 row-groups, 2 per warp
+        const int f0 = warp * 8;
+        const WT* rows[2];
+        int ff[2];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) rows[q] = W1 + (int64_t)(c0 + f0 + q) * d;
-        float acc[4][RC];
-        dot_rows<WT, RC, 4>(rows, xs, d, acc);
+        for (int g = 0; g < 2; ++g) {
+            ff[g] = c0 + f0 + g * 4 + sub;
+            rows[g] = W1 + (int64_t)ff[g] * d;
+        }
+        float acc[2][RC];
+        dot_groups<WT, RC, 2>(rows, xs, d, acc);
+        if (l8 == 0) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
+            for (int g = 0; g < 2; ++g) {
+                const float bias = a.b1[ff[g]];
 #pragma unroll
-            for (int rr = 0; rr < RC; ++rr)
-                if (lane == q * RC + rr) hs[rr * MLP_SLICE + f0 + q] = gelu_erf(__fadd_rn(acc[q][rr], a.b1[c0 + f0 + q]));
+                for (int rr = 0; rr < RC; ++rr) hs[rr * MLP_SLICE + (ff[g] - c0)] = gelu_erf(__fadd_rn(acc[g][rr], bias));
+            }
+        }
     }
     __syncthreads();
     slice_matvec<WT, RC, MLP_SLICE>(W2, d, 4 * d, c0, hs, a.ypart + (int64_t)blockIdx.x * R * d, d, r0, R);
@@ -548,6 +607,7 @@ __global__ void __launch_bounds__(NT)
 dec2_logits_kernel(const Dec2LogitsArgs a) {
     extern __shared__ __align__(16) float sm[];
     constexpr int KC = DEC2_KC;
+    constexpr int G = 2;                              // row-groups (4 rows each) per warp step
     const int d = a.d, R = a.R, V = a.V;
     float* xs = sm;                                   // [RC][d]
     float* red_m = xs + RC * d;                       // [NW][RC]
@@ -555,6 +615,7 @@ dec2_logits_kernel(const Dec2LogitsArgs a) {
     float* red_v = red_s + NW * RC;                   // [NW][RC][KC]
     int* red_i = reinterpret_cast<int*>(red_v + NW * RC * KC);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int sub = lane >> 3;
     const WT* E = reinterpret_cast<const WT*>(a.E);
     const int p = *a.pos;
     const bool use_mask = a.is_special != nullptr && (a.mask_mode == 1 || (a.mask_mode == 2 && p + 1 <= 5));
@@ -566,33 +627,35 @@ dec2_logits_kernel(const Dec2LogitsArgs a) {
         float m_run = -INFINITY, s_run = 0.0f;   // lane rr (< RC) tracks row rr
         Cand<KC> cand;
         cand.init();
-        const int n_groups = (V + 3) / 4;
-        for (int grp = blockIdx.x * NW + warp; grp < n_groups; grp += gridDim.x * NW) {
-            const int n0 = grp * 4;
-            const WT* rows[4];
+        const int n_steps = (V + 4 * G - 1) / (4 * G);
+        for (int stp = blockIdx.x * NW + warp; stp < n_steps; stp += gridDim.x * NW) {
+            const int n0 = stp * 4 * G;
+            const WT* rows[G];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) rows[q] = E + (int64_t)min(n0 + q, V - 1) * d;
-            float acc[4][RC];
-            dot_rows<WT, RC, 4>(rows, xs, d, acc);
+            for (int g = 0; g < G; ++g) rows[g] = E + (int64_t)min(n0 + g * 4 + sub, V - 1) * d;
+            float acc[G][RC];
+            dot_groups<WT, RC, G>(rows, xs, d, acc);
+            // lane (sub*8) holds the 4*G logits of this step for every row; hand row rr to lane rr
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int n = n0 + q;
-                if (n >= V) continue;
-                const bool masked = use_mask && a.is_special[n];
+            for (int g = 0; g < G; ++g)
 #pragma unroll
-                for (int rr = 0; rr < RC; ++rr) {
-                    if (lane == rr && r0 + rr < R) {
-                        const float raw = acc[q][rr];
-                        if (a.logits_out) a.logits_out[(int64_t)(r0 + rr) * V + n] = raw;
-                        const float v = masked ? __fadd_rn(raw, -INFINITY) : raw;
-                        if (v > -INFINITY) {
-                            if (v > m_run) { s_run = s_run * expf(m_run - v) + 1.0f; m_run = v; }
-                            else s_run += expf(v - m_run);
+                for (int s4 = 0; s4 < 4; ++s4) {
+                    const int n = n0 + g * 4 + s4;
+                    const bool masked = n < V && use_mask && a.is_special[n];
+#pragma unroll
+                    for (int rr = 0; rr < RC; ++rr) {
+                        const float raw = __shfl_sync(0xffffffffu, acc[g][rr], s4 * 8);
+                        if (lane == rr && n < V && r0 + rr < R) {
+                            if (a.logits_out) a.logits_out[(int64_t)(r0 + rr) * V + n] = raw;
+                            const float v = masked ? __fadd_rn(raw, -INFINITY) : raw;
+                            if (v > -INFINITY) {
+                                if (v > m_run) { s_run = s_run * expf(m_run - v) + 1.0f; m_run = v; }
+                                else s_run += expf(v - m_run);
+                            }
+                            cand.push(v, n);
                         }
-                        cand.push(v, n);
                     }
                 }
-            }
         }
         if (lane < RC) {
             red_m[warp * RC + lane] = m_run;
@@ -721,7 +784,7 @@ void set_smem(KernelT k, size_t smem) {
 
 template <typename WT, int RC>
 void launch_self_t(const Dec2SelfArgs& a, int H, cudaStream_t st) {
-    const size_t smem = sizeof(float) * ((size_t)RC * a.d + 4 * RC * 64 + (size_t)RC * (a.t_max + 1) + 2 * RC * NW + (size_t)RC * NW * 64);
+    const size_t smem = sizeof(float) * ((size_t)RC * a.d + 2 * RC * 64 + 2 * RC * NW + (size_t)RC * NW * 64);
     auto k = dec2_self_kernel<WT, RC>;
     set_smem(k, smem);
     k<<<dim3(H, (a.R + RC - 1) / RC), NT, smem, st>>>(a);
@@ -729,7 +792,7 @@ void launch_self_t(const Dec2SelfArgs& a, int H, cudaStream_t st) {
 }
 template <typename WT, int RC>
 void launch_cross_t(const Dec2CrossArgs& a, int H, int S, cudaStream_t st) {
-    size_t fl = (size_t)RC * a.d + 2 * RC * 64 + (size_t)RC * a.kmax + 2 * RC * NW + (size_t)RC * NW * 64;
+    size_t fl = (size_t)RC * a.d + 2 * RC * 64 + 2 * RC * NW + (size_t)RC * NW * 64;
     fl = std::max(fl, (size_t)H * S * a.R);   // resolve weights reuse the buffer
     const size_t smem = sizeof(float) * fl;
     auto k = dec2_cross_kernel<WT, RC>;
@@ -754,7 +817,7 @@ void launch_logits_t(const Dec2LogitsArgs& a, int n_ctas, cudaStream_t st) {
     WB_LAUNCH_CHECK();
 }
 
-int pick_rc(int R) { return R <= 1 ? 1 : (R <= 2 ? 2 : (R <= 4 ? 4 : 8)); }
+int pick_rc(int R) { return R <= 1 ? 1 : (R <= 2 ? 2 : (R <= 4 ? 4 : 8)); }   // NW % RC == 0
 
 }  // namespace
 
