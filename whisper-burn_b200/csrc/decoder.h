@@ -178,6 +178,53 @@ struct Dec2FinishArgs {
     unsigned int* counter = nullptr;
 };
 
+// ---- persistent cooperative decoder (decoder3.cu) ------------------------------------------------------
+struct Dec3Layer {
+    const float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *ln3_g, *ln3_b;
+    float ln1_eps, ln2_eps, ln3_eps;
+    const void *Wqkv, *Wo, *Wcq, *Wco, *W1, *W2;     // [N][K] fp16 or fp32
+    const float *bqkv, *bo, *bcq, *bco, *b1, *b2;
+};
+struct Dec3Args {
+    int R = 0, Rmax = 0, d = 0, H = 0, L = 0, V = 0, t_max = 0;
+    int64_t Mcap = 0;
+    int eps_outside = 1;
+    float qk_scale = 1.0f;
+    const Dec3Layer* layers = nullptr;    // device array [L]
+    const float* tok_emb = nullptr;       // fp32 [V][d] (embedding lookup)
+    const float* pos_emb = nullptr;
+    const void* E = nullptr;              // logits matrix [V][d] fp16 or fp32
+    const float *lnf_g = nullptr, *lnf_b = nullptr;
+    float lnf_eps = 1e-5f;
+    // state
+    float *x = nullptr, *q = nullptr, *att = nullptr, *hid = nullptr;
+    float *kc = nullptr, *vc = nullptr;   // [L][Rmax][t_max][d]
+    const float* ckv = nullptr;           // [L][Mcap][2d]
+    const int* row_window = nullptr;
+    const int64_t* win_row_off = nullptr;
+    const int* win_T = nullptr;
+    const int* anc = nullptr;
+    int n_splits = 1;
+    float *part_o = nullptr, *part_m = nullptr, *part_l = nullptr;   // [R][H][S][64], [R][H][S]
+    // tokens / control
+    int* tokens = nullptr;                // [Rmax][t_max]
+    const int* cur_tok = nullptr;
+    int use_cur_tok = 0;
+    int pos0 = 0, n_steps = 1, logits_from = 0;
+    const uint8_t* is_special = nullptr;
+    int mask_mode = 0;
+    int k = 1, greedy = 0, eot = -1;
+    int *lengths = nullptr, *finished = nullptr;
+    int *topk_id = nullptr;
+    float* topk_lp = nullptr;
+    float* logits_out = nullptr;
+    float *lg_m = nullptr, *lg_s = nullptr, *lg_v = nullptr;
+    int* lg_i = nullptr;
+    int *pos = nullptr, *n_unfinished = nullptr, *steps_done = nullptr;
+    unsigned int* bar = nullptr;          // [2] arrival count, generation
+};
+void launch_dec3(const Dec3Args& a, int n_ctas, bool w_half, cudaStream_t st);
+
 void launch_dec2_self(const Dec2SelfArgs& a, int H, bool w_half, cudaStream_t st);
 void launch_dec2_cross(const Dec2CrossArgs& a, int H, int S, bool w_half, cudaStream_t st);
 void launch_dec2_mlp(const Dec2MlpArgs& a, bool w_half, cudaStream_t st);

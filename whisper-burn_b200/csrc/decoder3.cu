@@ -1,0 +1,790 @@
+// Persistent cooperative decoder ("megakernel") for sm_100a.
+//
+// Reference math: TextDecoder::forward src/model/mod.rs:131-157, ResidualDecoderAttentionBlock::forward
+// :345-350, MultiHead{Self,Cross}Attention::forward :428-436 / :482-490, qkv_attention :493-533,
+// MLP::forward :376-382, and the search closure beamsearch_next src/transcribe.rs:253-307 (special-token
+// mask :271-275, log_softmax :276); greedy = beam::beam_search with beam_size 1 (src/beam.rs:9-37).
+//
+// Why one kernel: at the batch sizes of this workload (3 rows for BASELINE configs[1]) a decoder step
+// is ~60 MB of L2-resident weight/KV traffic but a chain of ~35 dependent stages; as separate kernels
+// each stage costs a launch + drain + cold prologue (measured 10-35 us each, profiles/).  Here ONE
+// cooperative launch (one CTA per SM, all co-resident) runs prompt prefill and every greedy step; the
+// stages are separated by a grid barrier (atomic arrive + generation flag in L2, ~1 us) and every stage
+// spreads its output features over all warps of the grid (weight-slice GEMV: a warp owns whole output
+// features, reads each weight row once for all rows of the batch, fp32 accumulate, no cross-CTA
+// reduction).  Per layer: LN+QKV | self-attention | out-proj+residual | LN+Q | cross-attention (split
+// over keys) | merge+out-proj+residual | LN+MLP1+GELU | MLP2+residual; then LN+logits with fused
+// special-token mask / online softmax / top-k candidates per warp, and a per-row finish.
+//
+// Everything another CTA wrote during the launch is read with ld.global.cg (L2), never through L1.
+#include <cooperative_groups.h>
+
+#include <algorithm>
+#include <cfloat>
+#include <climits>
+
+#include "decoder.h"
+#include "wb_internal.h"
+
+namespace wb {
+
+namespace {
+
+constexpr int NT = 256;
+constexpr int NW = 8;
+
+__device__ __forceinline__ float gelu_erf(float x) {
+    const float t = __fadd_rn(erff(__fdiv_rn(x, 1.41421356237309504880f)), 1.0f);
+    return __fdiv_rn(__fmul_rn(x, t), 2.0f);
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ void cvt8(const uint4& u, float (&w)[8]) {
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(h[i]);
+        w[2 * i] = f.x;
+        w[2 * i + 1] = f.y;
+    }
+}
+__device__ __forceinline__ unsigned int ld_acquire(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Grid barrier: bar[0] = arrival count, bar[1] = generation.  All CTAs are co-resident (cooperative launch).
+__device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int& gen) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&bar[0], 1u) == gridDim.x - 1u) {
+            bar[0] = 0u;
+            __threadfence();
+            atomicAdd(&bar[1], 1u);
+        } else {
+            long long t0 = clock64();
+            while (ld_acquire(&bar[1]) == gen) {
+                if (clock64() - t0 > 4000000000LL) __trap();   // ~2 s: fail loudly instead of hanging the GPU
+            }
+        }
+        __threadfence();
+    }
+    gen++;
+    __syncthreads();
+}
+
+// ---- input staging ---------------------------------------------------------------------------------
+// LayerNorm (burn 0.9 form, see encoder.cu) of rows [r0, r0+RC) of src (L2) into xs[RC][d]; warp per row.
+template <int RC>
+__device__ __forceinline__ void stage_ln(const float* src, int r0, int R, int d, const float* __restrict__ g,
+                                         const float* __restrict__ b, float eps, int eps_outside, float* xs) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int rr = warp; rr < RC; rr += NW) {
+        float* xr = xs + rr * d;
+        const int r = r0 + rr;
+        if (r >= R) {
+            for (int c = lane; c < d; c += 32) xr[c] = 0.0f;
+            continue;
+        }
+        const float* s = src + (int64_t)r * d;
+        float sum = 0.0f;
+        for (int c = lane; c < d; c += 32) {
+            const float v = __ldcg(s + c);
+            xr[c] = v;
+            sum += v;
+        }
+        sum = warp_sum(sum);
+        const float mean = __fdiv_rn(sum, (float)d);
+        float q = 0.0f;
+        for (int c = lane; c < d; c += 32) {
+            const float dv = __fsub_rn(xr[c], mean);
+            xr[c] = dv;
+            q = __fadd_rn(q, __fmul_rn(dv, dv));
+        }
+        q = warp_sum(q);
+        const float var = __fdiv_rn(q, (float)d);
+        const float den = eps_outside ? __fadd_rn(__fsqrt_rn(var), eps) : __fsqrt_rn(__fadd_rn(var, eps));
+        for (int c = lane; c < d; c += 32) xr[c] = __fadd_rn(__fmul_rn(__fdiv_rn(xr[c], den), __ldg(g + c)), __ldg(b + c));
+    }
+}
+
+template <int RC>
+__device__ __forceinline__ void stage_copy(const float* src, int r0, int R, int K, float* xs) {
+    const int n4 = RC * K / 4;
+    for (int i = threadIdx.x; i < n4; i += NT) {
+        const int rr = (i * 4) / K, c = (i * 4) % K;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r0 + rr < R) v = __ldcg(reinterpret_cast<const float4*>(src + (int64_t)(r0 + rr) * K + c));
+        *reinterpret_cast<float4*>(xs + rr * K + c) = v;
+    }
+}
+
+// ---- weight-slice GEMV --------------------------------------------------------------------------------
+// Every warp of the grid owns output features n = gw, gw + n_warps, ...; two features are in flight.
+// emit(n, rr, value) is called by lane 0 semantics-free (all lanes hold the sums; lane rr handles row rr).
+template <int RC>
+__device__ __forceinline__ float dot8_acc(const float (&w)[8], const float* xs, float acc) {
+    const float4 x0 = *reinterpret_cast<const float4*>(xs);
+    const float4 x1 = *reinterpret_cast<const float4*>(xs + 4);
+    acc = fmaf(w[0], x0.x, acc); acc = fmaf(w[1], x0.y, acc); acc = fmaf(w[2], x0.z, acc); acc = fmaf(w[3], x0.w, acc);
+    acc = fmaf(w[4], x1.x, acc); acc = fmaf(w[5], x1.y, acc); acc = fmaf(w[6], x1.z, acc); acc = fmaf(w[7], x1.w, acc);
+    return acc;
+}
+
+// dots of G weight rows (K elements each, full warp per row, lane-strided 16-byte vectors) with the RC
+// staged rows; all G rows' loads are issued before any is consumed; results in all lanes.
+template <typename WT, int RC, int G>
+__device__ __forceinline__ void rows_dot(const WT* (&wrow)[G], int K, const float* xs, float (&acc)[G][RC]) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int rr = 0; rr < RC; ++rr) acc[g][rr] = 0.0f;
+    const int nv = K / 8;
+    constexpr int U = (sizeof(WT) == 2) ? (G == 1 ? 6 : 3) : (G == 1 ? 3 : 2);   // vectors per lane and row in flight
+    for (int v0 = 0; v0 < nv; v0 += 32 * U) {
+        if constexpr (sizeof(WT) == 2) {
+            uint4 raw[G][U];
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+#pragma unroll
+                for (int i = 0; i < U; ++i) {
+                    const int v = v0 + i * 32 + lane;
+                    raw[g][i] = v < nv ? __ldg(reinterpret_cast<const uint4*>(wrow[g]) + v) : make_uint4(0, 0, 0, 0);
+                }
+#pragma unroll
+            for (int i = 0; i < U; ++i) {
+                const int v = v0 + i * 32 + lane;
+                if (v < nv) {
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        float w[8];
+                        cvt8(raw[g][i], w);
+#pragma unroll
+                        for (int rr = 0; rr < RC; ++rr) acc[g][rr] = dot8_acc<RC>(w, xs + rr * K + v * 8, acc[g][rr]);
+                    }
+                }
+            }
+        } else {
+            float4 ra[G][U], rb[G][U];
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+#pragma unroll
+                for (int i = 0; i < U; ++i) {
+                    const int v = v0 + i * 32 + lane;
+                    if (v < nv) {
+                        ra[g][i] = __ldg(reinterpret_cast<const float4*>(wrow[g]) + 2 * v);
+                        rb[g][i] = __ldg(reinterpret_cast<const float4*>(wrow[g]) + 2 * v + 1);
+                    } else {
+                        ra[g][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        rb[g][i] = ra[g][i];
+                    }
+                }
+#pragma unroll
+            for (int i = 0; i < U; ++i) {
+                const int v = v0 + i * 32 + lane;
+                if (v < nv) {
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        const float w[8] = {ra[g][i].x, ra[g][i].y, ra[g][i].z, ra[g][i].w, rb[g][i].x, rb[g][i].y, rb[g][i].z, rb[g][i].w};
+#pragma unroll
+                        for (int rr = 0; rr < RC; ++rr) acc[g][rr] = dot8_acc<RC>(w, xs + rr * K + v * 8, acc[g][rr]);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int rr = 0; rr < RC; ++rr) acc[g][rr] = warp_sum(acc[g][rr]);
+}
+
+// Weight-slice GEMV phase: output features n = gw, gw + n_gw, ... two at a time; emit(n, acc[RC]) in all lanes.
+template <typename WT, int RC, typename Emit>
+__device__ __forceinline__ void gemv_phase(const WT* W, int N, int K, const float* xs, int gw, int n_gw, Emit&& emit) {
+    for (int n = gw; n < N; n += 2 * n_gw) {
+        const int n2 = n + n_gw;
+        if (n2 < N) {
+            const WT* rows[2] = {W + (int64_t)n * K, W + (int64_t)n2 * K};
+            float acc[2][RC];
+            rows_dot<WT, RC, 2>(rows, K, xs, acc);
+            emit(n, acc[0]);
+            emit(n2, acc[1]);
+        } else {
+            const WT* rows[1] = {W + (int64_t)n * K};
+            float acc[1][RC];
+            rows_dot<WT, RC, 1>(rows, K, xs, acc);
+            emit(n, acc[0]);
+        }
+    }
+}
+
+// 8 lanes per weight row: a warp instruction covers 4 consecutive rows, G such groups in flight; after the
+// call every lane of sub-group `sub` holds acc[g][rr] of row (g*4 + sub).  Used by the logits stage.
+template <typename WT, int RC, int G>
+__device__ __forceinline__ void dot_groups(const WT* (&wrow)[G], const float* xs, int K, float (&acc)[G][RC]) {
+    const int l = threadIdx.x & 7;
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int rr = 0; rr < RC; ++rr) acc[g][rr] = 0.0f;
+#pragma unroll 3
+    for (int k0 = l * 8; k0 < K; k0 += 64) {
+        float w[G][8];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            if constexpr (sizeof(WT) == 2) {
+                cvt8(__ldg(reinterpret_cast<const uint4*>(wrow[g] + k0)), w[g]);
+            } else {
+                const float4 a4 = __ldg(reinterpret_cast<const float4*>(wrow[g] + k0));
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(wrow[g] + k0) + 1);
+                w[g][0] = a4.x; w[g][1] = a4.y; w[g][2] = a4.z; w[g][3] = a4.w;
+                w[g][4] = b4.x; w[g][5] = b4.y; w[g][6] = b4.z; w[g][7] = b4.w;
+            }
+        }
+#pragma unroll
+        for (int rr = 0; rr < RC; ++rr)
+#pragma unroll
+            for (int g = 0; g < G; ++g) acc[g][rr] = dot8_acc<RC>(w[g], xs + rr * K + k0, acc[g][rr]);
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int rr = 0; rr < RC; ++rr) {
+            float v = acc[g][rr];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            acc[g][rr] = v;
+        }
+}
+
+template <int RC>
+__device__ __forceinline__ float pick_row(const float (&acc)[RC], int rr) {
+    float v = acc[0];
+#pragma unroll
+    for (int i = 1; i < RC; ++i) v = (rr == i) ? acc[i] : v;
+    return v;
+}
+
+// ---- attention of one query row over keys, one warp, 4 lanes per key, online softmax ------------------
+struct AttnAcc {
+    float m, l, o[16];
+};
+template <typename KF, typename VF>
+__device__ __forceinline__ void attn_warp(const float* q_smem, int n_keys, int first, int stride, KF&& kptr, VF&& vptr,
+                                          AttnAcc& A) {
+    const int lane = threadIdx.x & 31, sub = lane >> 2, l4 = lane & 3;
+    float q[16];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float4 t = *reinterpret_cast<const float4*>(q_smem + l4 * 16 + c * 4);
+        q[c * 4] = t.x; q[c * 4 + 1] = t.y; q[c * 4 + 2] = t.z; q[c * 4 + 3] = t.w;
+    }
+    A.m = -INFINITY;
+    A.l = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) A.o[c] = 0.0f;
+    constexpr int UK = 2;
+    for (int jb = first; jb < n_keys; jb += stride * 8 * UK) {
+        float4 kk[UK][4], vv[UK][4];
+        bool ok[UK];
+#pragma unroll
+        for (int u = 0; u < UK; ++u) {
+            const int j = jb + (u * 8 + sub) * stride;
+            ok[u] = j < n_keys;
+            if (ok[u]) {
+                const float4* kp = reinterpret_cast<const float4*>(kptr(j)) + l4 * 4;
+                const float4* vp = reinterpret_cast<const float4*>(vptr(j)) + l4 * 4;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { kk[u][c] = __ldcg(kp + c); vv[u][c] = __ldcg(vp + c); }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { kk[u][c] = make_float4(0.f, 0.f, 0.f, 0.f); vv[u][c] = kk[u][c]; }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UK; ++u) {
+            float s = 0.0f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                s = fmaf(q[c * 4], kk[u][c].x, s); s = fmaf(q[c * 4 + 1], kk[u][c].y, s);
+                s = fmaf(q[c * 4 + 2], kk[u][c].z, s); s = fmaf(q[c * 4 + 3], kk[u][c].w, s);
+            }
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            if (ok[u]) {
+                const float mn = fmaxf(A.m, s);
+                const float corr = expf(A.m - mn);
+                const float e = expf(s - mn);
+                A.l = A.l * corr + e;
+                A.m = mn;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    A.o[c * 4] = fmaf(e, vv[u][c].x, A.o[c * 4] * corr);
+                    A.o[c * 4 + 1] = fmaf(e, vv[u][c].y, A.o[c * 4 + 1] * corr);
+                    A.o[c * 4 + 2] = fmaf(e, vv[u][c].z, A.o[c * 4 + 2] * corr);
+                    A.o[c * 4 + 3] = fmaf(e, vv[u][c].w, A.o[c * 4 + 3] * corr);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 4; off < 32; off <<= 1) {   // merge the 8 key sub-groups
+        const float m2 = __shfl_xor_sync(0xffffffffu, A.m, off);
+        const float l2 = __shfl_xor_sync(0xffffffffu, A.l, off);
+        const float mn = fmaxf(A.m, m2);
+        const float c1 = A.m > -INFINITY ? expf(A.m - mn) : 0.0f;
+        const float c2 = m2 > -INFINITY ? expf(m2 - mn) : 0.0f;
+        A.l = A.l * c1 + l2 * c2;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const float o2 = __shfl_xor_sync(0xffffffffu, A.o[c], off);
+            A.o[c] = A.o[c] * c1 + o2 * c2;
+        }
+        A.m = mn;
+    }
+}
+
+// one (query row, head) unit handled by the 8 warps of a CTA (keys strided over warps); returns the merged
+// (M, L) and the unnormalised output in out[64] (shared memory), valid after the trailing __syncthreads().
+template <typename KF, typename VF>
+__device__ __forceinline__ void attn_cta(const float* q_smem, int n_keys, KF&& kptr, VF&& vptr, float* wm, float* wl,
+                                         float* wo, float* out, float* ML) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    AttnAcc A;
+    attn_warp(q_smem, n_keys, warp, NW, kptr, vptr, A);
+    if (lane < 4) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) wo[warp * 64 + lane * 16 + c] = A.o[c];
+    }
+    if (lane == 0) { wm[warp] = A.m; wl[warp] = A.l; }
+    __syncthreads();
+    if (tid < 64) {
+        float M = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) M = fmaxf(M, wm[w]);
+        float L = 0.0f, o = 0.0f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            const float m = wm[w];
+            const float sc = m > -INFINITY ? expf(m - M) : 0.0f;
+            L += sc * wl[w];
+            o += sc * wo[w * 64 + tid];
+        }
+        out[tid] = o;
+        if (tid == 0) { ML[0] = M; ML[1] = L; }
+    }
+    __syncthreads();
+}
+
+// ---- top candidates --------------------------------------------------------------------------------------
+template <int KC>
+struct Cand {
+    float v[KC];
+    int i[KC];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int k = 0; k < KC; ++k) { v[k] = -INFINITY; i[k] = INT_MAX; }
+    }
+    __device__ __forceinline__ void push(float val, int idx) {   // keep the KC best by (value desc, index asc)
+        if (!(val > v[KC - 1] || (val == v[KC - 1] && idx < i[KC - 1]))) return;
+        v[KC - 1] = val;
+        i[KC - 1] = idx;
+#pragma unroll
+        for (int k = KC - 1; k > 0; --k) {
+            const bool better = v[k] > v[k - 1] || (v[k] == v[k - 1] && i[k] < i[k - 1]);
+            if (better) {
+                const float tv = v[k]; v[k] = v[k - 1]; v[k - 1] = tv;
+                const int ti = i[k]; i[k] = i[k - 1]; i[k - 1] = ti;
+            }
+        }
+    }
+};
+
+// =====================================================================================================
+template <typename WT, int RC, int KC>
+__global__ void __launch_bounds__(NT, 1)
+dec3_kernel(const Dec3Args a) {
+    extern __shared__ __align__(16) float sm[];
+    const int d = a.d, H = a.H, L = a.L, V = a.V, R = a.R, t_max = a.t_max;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int gw = blockIdx.x * NW + warp, n_gw = gridDim.x * NW;
+    float* xs = sm;                         // [RC][4d] staged activations
+    float* qs = xs + RC * 4 * d;            // [64] query of the current attention unit
+    float* wm = qs + 64;                    // [NW]
+    float* wl = wm + NW;                    // [NW]
+    float* wo = wl + NW;                    // [NW][64]
+    float* ao = wo + NW * 64;               // [64]
+    float* ML = ao + 64;                    // [2]
+    float* red = ML + 2;                    // logits merge scratch: [NW][RC][2 + 2*KC]; also cross merge weights
+    unsigned int gen = ld_acquire(&a.bar[1]);
+    const float scale = a.qk_scale;
+    const int S = a.n_splits;
+
+    for (int step = 0; step < a.n_steps; ++step) {
+        const int p = a.pos0 + step;
+        const bool want_logits = p >= a.logits_from;
+        // ================= embed: x[r] = tok_emb[token] + pos_emb[p]  (mod.rs:141-146)
+        for (int r = blockIdx.x; r < R; r += gridDim.x) {
+            const int tok = a.use_cur_tok ? __ldcg(a.cur_tok + r) : __ldcg(a.tokens + (int64_t)r * t_max + p);
+            const float* e = a.tok_emb + (int64_t)tok * d;
+            const float* pe = a.pos_emb + (int64_t)p * d;
+            for (int c = tid; c < d; c += NT) a.x[(int64_t)r * d + c] = __fadd_rn(__ldg(e + c), __ldg(pe + c));
+        }
+        grid_sync(a.bar, gen);
+        for (int l = 0; l < L; ++l) {
+            const Dec3Layer& W = a.layers[l];
+            float* kcl = a.kc + (size_t)l * a.Rmax * t_max * d;
+            float* vcl = a.vc + (size_t)l * a.Rmax * t_max * d;
+            // ================= P1: q | k | v = LN(x) Wqkv + b   (mod.rs:429-431)
+            for (int r0 = 0; r0 < R; r0 += RC) {
+                stage_ln<RC>(a.x, r0, R, d, W.ln1_g, W.ln1_b, W.ln1_eps, a.eps_outside, xs);
+                __syncthreads();
+                gemv_phase<WT, RC>(reinterpret_cast<const WT*>(W.Wqkv), 3 * d, d, xs, gw, n_gw, [&](int n, const float (&acc)[RC]) {
+                    if (lane < RC && r0 + lane < R) {
+                        const int r = r0 + lane;
+                        float v = __fadd_rn(pick_row<RC>(acc, lane), __ldg(W.bqkv + n));
+                        if (n < 2 * d) v = __fmul_rn(v, scale);
+                        if (n < d) a.q[(int64_t)r * d + n] = v;
+                        else if (n < 2 * d) kcl[((int64_t)r * t_max + p) * d + (n - d)] = v;
+                        else vcl[((int64_t)r * t_max + p) * d + (n - 2 * d)] = v;
+                    }
+                });
+                __syncthreads();
+            }
+            grid_sync(a.bar, gen);
+            // ================= P2: self attention over positions 0..p of the row's ancestry (mask == causal)
+            for (int u = blockIdx.x; u < R * H; u += gridDim.x) {
+                const int r = u / H, h = u % H;
+                if (tid < 16) *reinterpret_cast<float4*>(qs + tid * 4) = __ldcg(reinterpret_cast<const float4*>(a.q + (int64_t)r * d + h * 64) + tid);
+                __syncthreads();
+                const int* anc = a.anc ? a.anc + (int64_t)r * t_max : nullptr;
+                const float* kb = kcl + h * 64;
+                const float* vb = vcl + h * 64;
+                auto kp = [&](int j) { return kb + ((int64_t)((anc && j < p) ? __ldcg(anc + j) : r) * t_max + j) * d; };
+                auto vp = [&](int j) { return vb + ((int64_t)((anc && j < p) ? __ldcg(anc + j) : r) * t_max + j) * d; };
+                attn_cta(qs, p + 1, kp, vp, wm, wl, wo, ao, ML);
+                if (tid < 64) a.att[(int64_t)r * d + h * 64 + tid] = __fdiv_rn(ao[tid], ML[1]);
+                __syncthreads();
+            }
+            grid_sync(a.bar, gen);
+            // ================= P3: x += att Wo + bo   (mod.rs:435, :346)
+            for (int r0 = 0; r0 < R; r0 += RC) {
+                stage_copy<RC>(a.att, r0, R, d, xs);
+                __syncthreads();
+                gemv_phase<WT, RC>(reinterpret_cast<const WT*>(W.Wo), d, d, xs, gw, n_gw, [&](int n, const float (&acc)[RC]) {
+                    if (lane < RC && r0 + lane < R) {
+                        float* xp = a.x + (int64_t)(r0 + lane) * d + n;
+                        *xp = __fadd_rn(__ldcg(xp), __fadd_rn(pick_row<RC>(acc, lane), __ldg(W.bo + n)));
+                    }
+                });
+                __syncthreads();
+            }
+            grid_sync(a.bar, gen);
+            // ================= P4: cross query = LN(x) Wq + b   (mod.rs:483)
+            for (int r0 = 0; r0 < R; r0 += RC) {
+                stage_ln<RC>(a.x, r0, R, d, W.ln2_g, W.ln2_b, W.ln2_eps, a.eps_outside, xs);
+                __syncthreads();
+                gemv_phase<WT, RC>(reinterpret_cast<const WT*>(W.Wcq), d, d, xs, gw, n_gw, [&](int n, const float (&acc)[RC]) {
+                    if (lane < RC && r0 + lane < R)
+                        a.q[(int64_t)(r0 + lane) * d + n] = __fmul_rn(__fadd_rn(pick_row<RC>(acc, lane), __ldg(W.bcq + n)), scale);
+                });
+                __syncthreads();
+            }
+            grid_sync(a.bar, gen);
+            // ================= P5: cross attention, split over the window's encoder positions (K/V projected once per window)
+            {
+                const float* ckvl = a.ckv + (size_t)l * a.Mcap * 2 * d;
+                for (int u = blockIdx.x; u < R * H * S; u += gridDim.x) {
+                    const int sp = u % S, h = (u / S) % H, r = u / (S * H);
+                    if (tid < 16) *reinterpret_cast<float4*>(qs + tid * 4) = __ldcg(reinterpret_cast<const float4*>(a.q + (int64_t)r * d + h * 64) + tid);
+                    __syncthreads();
+                    const int w = __ldcg(a.row_window + r);
+                    const int T = a.win_T[w];
+                    const int per = (T + S - 1) / S;
+                    const int kb0 = sp * per;
+                    const int nk = max(0, min(T, kb0 + per) - kb0);
+                    const float* kbase = ckvl + (a.win_row_off[w] + kb0) * (int64_t)(2 * d) + h * 64;
+                    const int64_t ld = 2 * (int64_t)d;
+                    auto kp = [&](int j) { return kbase + j * ld; };
+                    auto vp = [&](int j) { return kbase + j * ld + d; };
+                    attn_cta(qs, nk, kp, vp, wm, wl, wo, ao, ML);
+                    const int64_t o = ((int64_t)r * H + h) * S + sp;
+                    if (tid < 64) a.part_o[o * 64 + tid] = ao[tid];
+                    if (tid == 0) { a.part_m[o] = nk > 0 ? ML[0] : -INFINITY; a.part_l[o] = ML[1]; }
+                    __syncthreads();
+                }
+            }
+            grid_sync(a.bar, gen);
+            // ================= P6: x += merge(cross partials) Wo + bo   (mod.rs:489, :347)
+            for (int r0 = 0; r0 < R; r0 += RC) {
+                float* wn = red;   // [RC][H][S] normalised split weights
+                for (int i = tid; i < RC * H; i += NT) {
+                    const int rr = i / H, h = i % H, r = r0 + rr;
+                    if (r < R) {
+                        const int64_t o = ((int64_t)r * H + h) * S;
+                        float M = -INFINITY;
+                        for (int s = 0; s < S; ++s) M = fmaxf(M, __ldcg(a.part_m + o + s));
+                        float den = 0.0f;
+                        for (int s = 0; s < S; ++s) {
+                            const float m = __ldcg(a.part_m + o + s);
+                            const float e = m > -INFINITY ? expf(m - M) : 0.0f;
+                            wn[i * S + s] = e;
+                            den += e * __ldcg(a.part_l + o + s);
+                        }
+                        for (int s = 0; s < S; ++s) wn[i * S + s] = __fdiv_rn(wn[i * S + s], den);
+                    } else {
+                        for (int s = 0; s < S; ++s) wn[i * S + s] = 0.0f;
+                    }
+                }
+                __syncthreads();
+                for (int i = tid; i < RC * d / 4; i += NT) {   // 4 consecutive dims of one (row, head)
+                    const int rr = (i * 4) / d, c = (i * 4) % d, r = min(r0 + rr, R - 1);
+                    const int h = c / 64;
+                    const float4* po = reinterpret_cast<const float4*>(a.part_o + (((int64_t)r * H + h) * S) * 64 + (c & 63));
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+                    for (int s = 0; s < S; ++s) {
+                        const float4 v = __ldcg(po + s * 16);
+                        const float wgt = wn[(rr * H + h) * S + s];
+                        acc.x = fmaf(wgt, v.x, acc.x); acc.y = fmaf(wgt, v.y, acc.y);
+                        acc.z = fmaf(wgt, v.z, acc.z); acc.w = fmaf(wgt, v.w, acc.w);
+                    }
+                    *reinterpret_cast<float4*>(xs + rr * d + c) = acc;
+                }
+                __syncthreads();
+                gemv_phase<WT, RC>(reinterpret_cast<const WT*>(W.Wco), d, d, xs, gw, n_gw, [&](int n, const float (&acc)[RC]) {
+                    if (lane < RC && r0 + lane < R) {
+                        float* xp = a.x + (int64_t)(r0 + lane) * d + n;
+                        *xp = __fadd_rn(__ldcg(xp), __fadd_rn(pick_row<RC>(acc, lane), __ldg(W.bco + n)));
+                    }
+                });
+                __syncthreads();
+            }
+            grid_sync(a.bar, gen);
+            // ================= P7: hid = gelu(LN(x) W1 + b1)   (mod.rs:377-378)
+            for (int r0 = 0; r0 < R; r0 += RC) {
+                stage_ln<RC>(a.x, r0, R, d, W.ln3_g, W.ln3_b, W.ln3_eps, a.eps_outside, xs);
+                __syncthreads();
+                gemv_phase<WT, RC>(reinterpret_cast<const WT*>(W.W1), 4 * d, d, xs, gw, n_gw, [&](int n, const float (&acc)[RC]) {
+                    if (lane < RC && r0 + lane < R)
+                        a.hid[(int64_t)(r0 + lane) * 4 * d + n] = gelu_erf(__fadd_rn(pick_row<RC>(acc, lane), __ldg(W.b1 + n)));
+                });
+                __syncthreads();
+            }
+            grid_sync(a.bar, gen);
+            // ================= P8: x += hid W2 + b2   (mod.rs:379, :348)
+            for (int r0 = 0; r0 < R; r0 += RC) {
+                stage_copy<RC>(a.hid, r0, R, 4 * d, xs);
+                __syncthreads();
+                gemv_phase<WT, RC>(reinterpret_cast<const WT*>(W.W2), d, 4 * d, xs, gw, n_gw, [&](int n, const float (&acc)[RC]) {
+                    if (lane < RC && r0 + lane < R) {
+                        float* xp = a.x + (int64_t)(r0 + lane) * d + n;
+                        *xp = __fadd_rn(__ldcg(xp), __fadd_rn(pick_row<RC>(acc, lane), __ldg(W.b2 + n)));
+                    }
+                });
+                __syncthreads();
+            }
+            grid_sync(a.bar, gen);
+        }
+        if (want_logits) {
+            // ================= logits = LN(x) tok_emb^T (mod.rs:155-156) + mask + online softmax + candidates.
+            // 8 lanes per vocabulary row, 8 rows per warp step; lane (sub, l8) tracks batch row l8.
+            const bool use_mask = a.is_special != nullptr && (a.mask_mode == 1 || (a.mask_mode == 2 && p + 1 <= 5));
+            const WT* E = reinterpret_cast<const WT*>(a.E);
+            const int sub = lane >> 3, l8 = lane & 7;
+            for (int r0 = 0; r0 < R; r0 += RC) {
+                stage_ln<RC>(a.x, r0, R, d, a.lnf_g, a.lnf_b, a.lnf_eps, a.eps_outside, xs);
+                __syncthreads();
+                float m_run = -INFINITY, s_run = 0.0f;
+                Cand<KC> cand;
+                cand.init();
+                const int n_blk = (V + 7) / 8;
+                for (int blk = gw; blk < n_blk; blk += n_gw) {
+                    const int n0 = blk * 8;
+                    const WT* rows[2];
+                    int nn[2];
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        nn[g] = n0 + g * 4 + sub;
+                        rows[g] = E + (int64_t)min(nn[g], V - 1) * d;
+                    }
+                    float acc[2][RC];
+                    dot_groups<WT, RC, 2>(rows, xs, d, acc);
+                    if (l8 < RC && r0 + l8 < R) {
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) {
+                            if (nn[g] < V) {
+                                const float raw = pick_row<RC>(acc[g], l8);
+                                if (a.logits_out) a.logits_out[(int64_t)(r0 + l8) * V + nn[g]] = raw;
+                                const float v = (use_mask && a.is_special[nn[g]]) ? __fadd_rn(raw, -INFINITY) : raw;
+                                if (v > -INFINITY) {
+                                    if (v > m_run) { s_run = s_run * expf(m_run - v) + 1.0f; m_run = v; }
+                                    else s_run += expf(v - m_run);
+                                }
+                                cand.push(v, nn[g]);
+                            }
+                        }
+                    }
+                }
+                // merge: 4 sub-groups x 8 warps hold a state for every batch row -> one record per (CTA, row)
+                if (l8 < RC) {
+                    float* rec = red + ((warp * 4 + sub) * RC + l8) * (2 + 2 * KC);
+                    rec[0] = m_run;
+                    rec[1] = s_run;
+#pragma unroll
+                    for (int k = 0; k < KC; ++k) { rec[2 + k] = cand.v[k]; rec[2 + KC + k] = __int_as_float(cand.i[k]); }
+                }
+                __syncthreads();
+                if (tid < RC && r0 + tid < R) {
+                    float M = -INFINITY;
+                    for (int w = 0; w < NW * 4; ++w) M = fmaxf(M, red[(w * RC + tid) * (2 + 2 * KC)]);
+                    float Ssum = 0.0f;
+                    Cand<KC> best;
+                    best.init();
+                    for (int w = 0; w < NW * 4; ++w) {
+                        const float* rec = red + (w * RC + tid) * (2 + 2 * KC);
+                        if (rec[0] > -INFINITY) Ssum += rec[1] * expf(rec[0] - M);
+#pragma unroll
+                        for (int k = 0; k < KC; ++k) best.push(rec[2 + k], __float_as_int(rec[2 + KC + k]));
+                    }
+                    const int64_t o = (int64_t)blockIdx.x * R + r0 + tid;
+                    a.lg_m[o] = M;
+                    a.lg_s[o] = Ssum;
+#pragma unroll
+                    for (int k = 0; k < KC; ++k) { a.lg_v[o * KC + k] = best.v[k]; a.lg_i[o * KC + k] = best.i[k]; }
+                }
+                __syncthreads();
+            }
+            grid_sync(a.bar, gen);
+            // ================= finish: log_softmax of the candidates, k best (ties -> lower id), greedy bookkeeping
+            for (int r = blockIdx.x; r < R; r += gridDim.x) {
+                float* s_f = wm;   // [NW] scratch
+                int* s_i = reinterpret_cast<int*>(wl);
+                const int NP = gridDim.x;
+                float mx = -INFINITY;
+                for (int c = tid; c < NP; c += NT) mx = fmaxf(mx, __ldcg(a.lg_m + (int64_t)c * R + r));
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                if (lane == 0) s_f[warp] = mx;
+                __syncthreads();
+                mx = s_f[0];
+#pragma unroll
+                for (int w = 1; w < NW; ++w) mx = fmaxf(mx, s_f[w]);
+                __syncthreads();
+                float se = 0.0f;
+                for (int c = tid; c < NP; c += NT) {
+                    const float m = __ldcg(a.lg_m + (int64_t)c * R + r);
+                    if (m > -INFINITY) se += __ldcg(a.lg_s + (int64_t)c * R + r) * expf(m - mx);
+                }
+                se = warp_sum(se);
+                if (lane == 0) s_f[warp] = se;
+                __syncthreads();
+                se = 0.0f;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) se += s_f[w];
+                const float lse = logf(se);
+                __syncthreads();
+                float prev_v = INFINITY;
+                int prev_i = -1;
+                for (int kk = 0; kk < a.k; ++kk) {
+                    float bv = -INFINITY;
+                    int bi = INT_MAX;
+                    for (int c = tid; c < NP * KC; c += NT) {
+                        const int part = c / KC, k = c % KC;
+                        const int idx = __ldcg(a.lg_i + ((int64_t)part * R + r) * KC + k);
+                        if (idx == INT_MAX) continue;
+                        const float v = __fsub_rn(__fsub_rn(__ldcg(a.lg_v + ((int64_t)part * R + r) * KC + k), mx), lse);
+                        const bool after_prev = v < prev_v || (v == prev_v && idx > prev_i);
+                        if (after_prev && (v > bv || (v == bv && idx < bi))) { bv = v; bi = idx; }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                    }
+                    if (lane == 0) { s_f[warp] = bv; s_i[warp] = bi; }
+                    __syncthreads();
+                    bv = s_f[0];
+                    bi = s_i[0];
+#pragma unroll
+                    for (int w = 1; w < NW; ++w)
+                        if (s_f[w] > bv || (s_f[w] == bv && s_i[w] < bi)) { bv = s_f[w]; bi = s_i[w]; }
+                    __syncthreads();
+                    if (tid == 0) {
+                        a.topk_id[(int64_t)r * a.k + kk] = bi == INT_MAX ? -1 : bi;
+                        a.topk_lp[(int64_t)r * a.k + kk] = bv;
+                        if (kk == 0 && a.greedy && !__ldcg(a.finished + r)) {   // beam.rs:9-37 with beam_size 1
+                            a.tokens[(int64_t)r * t_max + p + 1] = bi;
+                            a.lengths[r] = p + 2;
+                            if (bi == a.eot) a.finished[r] = 1;
+                        }
+                    }
+                    prev_v = bv;
+                    prev_i = bi;
+                }
+            }
+            grid_sync(a.bar, gen);
+            if (a.greedy) {   // stop as soon as every search has produced EOT (beam.rs:22-27)
+                int live = 0;
+                for (int r = 0; r < R; ++r) live += __ldcg(a.finished + r) ? 0 : 1;
+                if (live == 0) {
+                    if (blockIdx.x == 0 && tid == 0) { *a.pos = p + 1; *a.n_unfinished = 0; *a.steps_done = step + 1; }
+                    return;
+                }
+            }
+        }
+    }
+    if (blockIdx.x == 0 && tid == 0) {
+        *a.pos = a.pos0 + a.n_steps;
+        int live = 0;
+        for (int r = 0; r < R; ++r) live += (a.greedy && __ldcg(a.finished + r)) ? 0 : 1;
+        *a.n_unfinished = live;
+        *a.steps_done = a.n_steps;
+    }
+}
+
+size_t dec3_smem_bytes(int d, int H, int S, int RC, int KC) {
+    size_t red = std::max((size_t)NW * 4 * RC * (2 + 2 * KC), (size_t)RC * H * S);
+    return sizeof(float) * ((size_t)RC * 4 * d + 64 + 2 * NW + NW * 64 + 64 + 2 + red + 8);
+}
+
+template <typename WT, int RC, int KC>
+void launch_t(const Dec3Args& a, int n_ctas, cudaStream_t st) {
+    const size_t smem = dec3_smem_bytes(a.d, a.H, a.n_splits, RC, KC);
+    auto k = dec3_kernel<WT, RC, KC>;
+    WB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    WB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, NT, smem));
+    if (per_sm < 1) fail(WB_ERR_UNSUPPORTED, "decoder megakernel does not fit on an SM");
+    void* args[] = {(void*)&a};
+    WB_CUDA(cudaLaunchCooperativeKernel((void*)k, dim3(n_ctas), dim3(NT), args, smem, st));
+    WB_LAUNCH_CHECK();
+}
+
+}  // namespace
+
+void launch_dec3(const Dec3Args& a, int n_ctas, bool w_half, cudaStream_t st) {
+    const bool big = a.R > 4;
+    const bool wide = a.k > 1;
+#define WB_D3(WT)                                                        \
+    do {                                                                 \
+        if (!big && !wide) launch_t<WT, 4, 2>(a, n_ctas, st);            \
+        else if (!big && wide) launch_t<WT, 4, 8>(a, n_ctas, st);        \
+        else if (big && !wide) launch_t<WT, 8, 2>(a, n_ctas, st);        \
+        else launch_t<WT, 8, 8>(a, n_ctas, st);                          \
+    } while (0)
+    if (w_half) WB_D3(__half);
+    else WB_D3(float);
+#undef WB_D3
+}
+
+}  // namespace wb

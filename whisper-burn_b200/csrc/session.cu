@@ -3,6 +3,7 @@
 //   (mod.rs:228-260) -> cross K/V (mod.rs:484-485, hoisted out of the step loop) -> decoder steps.
 // Windows of one call are batched: encoder rows of all windows are packed back to back.
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -55,9 +56,31 @@ Session::Session(Model* model, int64_t max_w, int64_t max_b, int64_t max_text_le
     {
         const char* e = getenv("WB200_DECODER");
         if (e && e[0] == '1') dec_version = 1;
+        if (e && e[0] == '2') dec_version = 2;
         cudaDeviceProp prop;
         WB_CUDA(cudaGetDeviceProperties(&prop, m->device));
+        n_sm = prop.multiProcessorCount;
         n_logit_ctas = 2 * prop.multiProcessorCount;
+        // persistent decoder: per-layer pointer table, barrier words, larger split-KV partial buffers
+        part_o.alloc((size_t)Rmax * H * 16 * 64); part_m.alloc((size_t)Rmax * H * 16); part_l.alloc((size_t)Rmax * H * 16);
+        datt.alloc((size_t)Rmax * d); steps_done.alloc(1); d3_bar.alloc(2);
+        WB_CUDA(cudaMemsetAsync(d3_bar.p, 0, 2 * sizeof(unsigned int), st));
+        {
+            const bool h16 = m->fp16_exact;
+            auto wp = [&](const LinearW& w) -> const void* { return h16 ? (const void*)w.w16 : (const void*)w.w32; };
+            std::vector<Dec3Layer> lay((size_t)L);
+            for (int l = 0; l < L; ++l) {
+                const DecBlockW& B = m->dec[(size_t)l];
+                Dec3Layer& y = lay[(size_t)l];
+                y.ln1_g = B.attn_ln.g; y.ln1_b = B.attn_ln.b; y.ln1_eps = B.attn_ln.eps;
+                y.ln2_g = B.cross_ln.g; y.ln2_b = B.cross_ln.b; y.ln2_eps = B.cross_ln.eps;
+                y.ln3_g = B.mlp_ln.g; y.ln3_b = B.mlp_ln.b; y.ln3_eps = B.mlp_ln.eps;
+                y.Wqkv = wp(B.qkv); y.Wo = wp(B.out); y.Wcq = wp(B.cq); y.Wco = wp(B.cout); y.W1 = wp(B.mlp1); y.W2 = wp(B.mlp2);
+                y.bqkv = B.qkv.b; y.bo = B.out.b; y.bcq = B.cq.b; y.bco = B.cout.b; y.b1 = B.mlp1.b; y.b2 = B.mlp2.b;
+            }
+            d3_layers.alloc((size_t)L);
+            WB_CUDA(cudaMemcpy(d3_layers.p, lay.data(), lay.size() * sizeof(Dec3Layer), cudaMemcpyHostToDevice));
+        }
         const size_t n_part = (size_t)std::max(H * n_splits, 4 * d / 32);
         ypart.alloc(n_part * Rmax * d);
         lg_m.alloc((size_t)n_logit_ctas * Rmax); lg_s.alloc((size_t)n_logit_ctas * Rmax);
@@ -257,7 +280,7 @@ void Session::set_special(const uint8_t* sp) {
     }
 }
 
-void Session::begin(const int64_t* prompt, int64_t prompt_len) {
+void Session::begin(const int64_t* prompt, int64_t prompt_len, bool prefill) {
     if (!encoded) fail(WB_ERR_STATE, "session: begin before encode");
     WB_REQUIRE(prompt_len >= 1 && prompt_len < t_max, "begin: prompt length out of range");
     const int V = m->dims.n_vocab;
@@ -283,7 +306,7 @@ void Session::begin(const int64_t* prompt, int64_t prompt_len) {
     anc_cur = 0;
     host_pos = 0;
     // feed prompt[0 .. prompt_len-1): no logits needed
-    for (int64_t i = 0; i + 1 < prompt_len; ++i) {
+    for (int64_t i = 0; prefill && i + 1 < prompt_len; ++i) {
         step_core(false, 0, 1, false, -1, nullptr);
         std::vector<int> nxt((size_t)R, (int)prompt[i + 1]);
         WB_CUDA(cudaMemcpyAsync(cur_tok.p, nxt.data(), nxt.size() * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -352,7 +375,38 @@ void Session::step_core_v2(bool with_logits, int mask_mode, int k, bool greedy, 
     ++host_pos;
 }
 
+// One cooperative launch of the persistent decoder: n_steps positions starting at pos0.
+void Session::launch_v3(int R_, int pos0, int n_steps, int logits_from, bool use_cur_tok, int mask_mode, int k,
+                        bool greedy, int eot) {
+    const wb_dims& D = m->dims;
+    const int d = D.n_text_state, H = D.n_text_head;
+    Dec3Args a;
+    a.R = R_; a.Rmax = Rmax; a.d = d; a.H = H; a.L = D.n_text_layer; a.V = D.n_vocab; a.t_max = t_max; a.Mcap = Mcap;
+    a.eps_outside = m->ln_eps_outside; a.qk_scale = (float)std::pow((double)d / (double)H, -0.25);
+    a.layers = d3_layers.p; a.tok_emb = m->tok_emb32; a.pos_emb = m->dec_pos;
+    a.E = m->fp16_exact ? (const void*)m->tok_emb16 : (const void*)m->tok_emb32;
+    a.lnf_g = m->dec_ln.g; a.lnf_b = m->dec_ln.b; a.lnf_eps = m->dec_ln.eps;
+    a.x = dx.p; a.q = dq.p; a.att = datt.p; a.hid = dhid.p; a.kc = kc.p; a.vc = vc.p; a.ckv = ckv.p;
+    a.row_window = row_window.p; a.win_row_off = d_win_row_off.p; a.win_T = d_win_T.p;
+    a.anc = anc_identity ? nullptr : (anc_cur == 0 ? anc0.p : anc1.p);
+    a.n_splits = std::max(1, std::min(16, n_sm / std::max(1, R_ * H)));
+    a.part_o = part_o.p; a.part_m = part_m.p; a.part_l = part_l.p;
+    a.tokens = tokens.p; a.cur_tok = cur_tok.p; a.use_cur_tok = use_cur_tok ? 1 : 0;
+    a.pos0 = pos0; a.n_steps = n_steps; a.logits_from = logits_from;
+    a.is_special = have_special ? is_special.p : nullptr; a.mask_mode = mask_mode;
+    a.k = k; a.greedy = greedy ? 1 : 0; a.eot = eot; a.lengths = lengths.p; a.finished = finished.p;
+    a.topk_id = topk_id.p; a.topk_lp = topk_lp.p; a.logits_out = full_logits ? logits.p : nullptr;
+    a.lg_m = lg_m.p; a.lg_s = lg_s.p; a.lg_v = lg_v.p; a.lg_i = lg_i.p;
+    a.pos = pos.p; a.n_unfinished = n_unfinished.p; a.steps_done = steps_done.p; a.bar = d3_bar.p;
+    launch_dec3(a, n_sm, m->fp16_exact, st);
+}
+
 void Session::step_core(bool with_logits, int mask_mode, int k, bool greedy, int eot, float* logprob_out) {
+    if (dec_version == 3 && k <= 7) {
+        launch_v3(R, host_pos, 1, with_logits ? 0 : INT_MAX, true, mask_mode, k, greedy, eot);
+        ++host_pos;
+        return;
+    }
     if (dec_version == 2 && k <= DEC2_KC - 1) {
         step_core_v2(with_logits, mask_mode, k, greedy, eot);
         return;
@@ -450,6 +504,20 @@ void Session::profile_decode(const int64_t* prompt, int64_t prompt_len, int n_st
         WB_CUDA(cudaEventCreate(&e));
         prof_ev.push_back(e);
     }
+    if (dec_version == 3) {
+        // the whole decode is ONE kernel: time the launch (prefill + n_steps greedy steps) and report per step
+        begin(prompt, prompt_len, false);
+        const int total = (int)prompt_len - 1 + n_steps;
+        WB_CUDA(cudaEventRecord(prof_ev[0], st));
+        launch_v3(R, 0, total, (int)prompt_len - 1, false, 2, 1, true, -1 /* never stop early */);
+        WB_CUDA(cudaEventRecord(prof_ev[1], st));
+        WB_CUDA(cudaStreamSynchronize(st));
+        float t = 0.f;
+        WB_CUDA(cudaEventElapsedTime(&t, prof_ev[0], prof_ev[1]));
+        *logits_ms = t / (float)total;
+        *step_ms = t / (float)total;
+        return;
+    }
     begin(prompt, prompt_len);
     prof = true;
     prof_n = 0;
@@ -515,6 +583,24 @@ void Session::step_beams(int64_t n_rows, const int32_t* window_of_row, const int
 void Session::greedy_decode(const int64_t* prompt, int64_t prompt_len, int max_depth, int64_t eot,
                             std::vector<std::vector<int64_t>>& out) {
     WB_REQUIRE(prompt_len + max_depth <= t_max, "greedy: prompt + max_depth exceeds the session's max_text_len");
+    if (dec_version == 3) {
+        // one cooperative launch: prompt prefill + every greedy step, early exit inside the kernel
+        begin(prompt, prompt_len, /*prefill=*/false);
+        const int n_steps = (int)prompt_len - 1 + max_depth;
+        if (max_depth > 0) launch_v3(R, 0, n_steps, (int)prompt_len - 1, false, 2, 1, true, (int)eot);
+        std::vector<int> tk((size_t)R * t_max), len((size_t)R);
+        int sd = 0;
+        WB_CUDA(cudaMemcpyAsync(tk.data(), tokens.p, tk.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+        WB_CUDA(cudaMemcpyAsync(len.data(), lengths.p, len.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (max_depth > 0) WB_CUDA(cudaMemcpyAsync(&sd, steps_done.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        WB_CUDA(cudaStreamSynchronize(st));
+        last_steps = max_depth > 0 ? sd - ((int)prompt_len - 1) : 0;
+        host_pos = (int)prompt_len - 1 + (int)last_steps;
+        out.assign((size_t)R, {});
+        for (int r = 0; r < R; ++r)
+            for (int i = 0; i < len[(size_t)r]; ++i) out[(size_t)r].push_back(tk[(size_t)r * t_max + i]);
+        return;
+    }
     begin(prompt, prompt_len);
     // beam_search with beam_size 1 (beam.rs:9-37): stop when the (only) beam ends in EOT or after max_depth steps
     int done_steps = 0;

@@ -59,7 +59,15 @@ struct Session {
     float last_ms[4] = {0, 0, 0, 0};
     int64_t last_steps = 0;
     // fused decoder step (decoder2.cu): partial buffers, tickets, switches
-    int dec_version = 2;         // WB200_DECODER=1 selects the unfused decoder.cu path (A/B testing)
+    int dec_version = 3;         // 3 = persistent cooperative kernel (decoder3.cu); WB200_DECODER=1|2 select the
+                                 // unfused (decoder.cu) / fused-per-layer (decoder2.cu) paths for A/B testing
+    int n_sm = 0;
+    DevBuf<Dec3Layer> d3_layers;
+    DevBuf<unsigned int> d3_bar;
+    DevBuf<int> steps_done;
+    DevBuf<float> datt;
+    void launch_v3(int R_, int pos0, int n_steps, int logits_from, bool use_cur_tok, int mask_mode, int k, bool greedy,
+                   int eot);
     bool full_logits = false;    // also write raw logits [R][V] (stateless forward_decoder)
     int n_logit_ctas = 0;
     DevBuf<float> ypart, lg_m, lg_s, lg_v;
@@ -87,7 +95,7 @@ struct Session {
     void run_cross_kv();
 
     void set_special(const uint8_t* is_special_host);
-    void begin(const int64_t* prompt, int64_t prompt_len);
+    void begin(const int64_t* prompt, int64_t prompt_len, bool prefill = true);
     // one decoder position for R rows; tokens come from cur_tok
     void step_core(bool with_logits, int mask_mode, int k, bool greedy, int eot, float* logprob_out);
     void step_beams(int64_t n_rows, const int32_t* window_of_row, const int32_t* parent_row, const int64_t* token,
