@@ -246,4 +246,4 @@ def test_launch_counter_counts_kernels(small):
     ffi.lib().wb_kernel_launch_count_reset()
     sess = transcribe.Session(wh, 1, 1, 16)
     sess.transcribe_windows([synth.waveform(16000, seed=1)], sp, is_special_of(sp), beam_size=1, max_depth=4)
-    assert ffi.lib().wb_kernel_launch_count() > 50
+    assert ffi.lib().wb_kernel_launch_count() > 20     # log-mel 2 + encoder ~27 + cross K/V + 1 persistent decoder launch

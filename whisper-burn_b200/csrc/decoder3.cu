@@ -80,47 +80,84 @@ __device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int& gen) 
 
 // ---- input staging ---------------------------------------------------------------------------------
 // LayerNorm (burn 0.9 form, see encoder.cu) of rows [r0, r0+RC) of src (L2) into xs[RC][d]; warp per row.
+// The row is fetched with ONE batch of independent 16-byte loads (d <= 1280 -> <= 10 per lane) and stays in
+// registers through mean / variance / normalisation: a single L2 round trip per stage.
+constexpr int LN_V4 = 10;
 template <int RC>
 __device__ __forceinline__ void stage_ln(const float* src, int r0, int R, int d, const float* __restrict__ g,
                                          const float* __restrict__ b, float eps, int eps_outside, float* xs) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nv = d / 4;
     for (int rr = warp; rr < RC; rr += NW) {
-        float* xr = xs + rr * d;
+        float4* xr = reinterpret_cast<float4*>(xs + rr * d);
         const int r = r0 + rr;
         if (r >= R) {
-            for (int c = lane; c < d; c += 32) xr[c] = 0.0f;
+            for (int c = lane; c < nv; c += 32) xr[c] = make_float4(0.f, 0.f, 0.f, 0.f);
             continue;
         }
-        const float* s = src + (int64_t)r * d;
-        float sum = 0.0f;
-        for (int c = lane; c < d; c += 32) {
-            const float v = __ldcg(s + c);
-            xr[c] = v;
-            sum += v;
+        const float4* s4 = reinterpret_cast<const float4*>(src + (int64_t)r * d);
+        float4 v[LN_V4];
+#pragma unroll
+        for (int i = 0; i < LN_V4; ++i) {
+            const int c = i * 32 + lane;
+            v[i] = c < nv ? __ldcg(s4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        float sum = 0.0f;
+#pragma unroll
+        for (int i = 0; i < LN_V4; ++i) sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
         sum = warp_sum(sum);
         const float mean = __fdiv_rn(sum, (float)d);
         float q = 0.0f;
-        for (int c = lane; c < d; c += 32) {
-            const float dv = __fsub_rn(xr[c], mean);
-            xr[c] = dv;
-            q = __fadd_rn(q, __fmul_rn(dv, dv));
+#pragma unroll
+        for (int i = 0; i < LN_V4; ++i) {
+            const int c = i * 32 + lane;
+            if (c < nv) {
+                v[i].x = __fsub_rn(v[i].x, mean); v[i].y = __fsub_rn(v[i].y, mean);
+                v[i].z = __fsub_rn(v[i].z, mean); v[i].w = __fsub_rn(v[i].w, mean);
+                q = __fadd_rn(q, __fmul_rn(v[i].x, v[i].x)); q = __fadd_rn(q, __fmul_rn(v[i].y, v[i].y));
+                q = __fadd_rn(q, __fmul_rn(v[i].z, v[i].z)); q = __fadd_rn(q, __fmul_rn(v[i].w, v[i].w));
+            }
         }
         q = warp_sum(q);
         const float var = __fdiv_rn(q, (float)d);
         const float den = eps_outside ? __fadd_rn(__fsqrt_rn(var), eps) : __fsqrt_rn(__fadd_rn(var, eps));
-        for (int c = lane; c < d; c += 32) xr[c] = __fadd_rn(__fmul_rn(__fdiv_rn(xr[c], den), __ldg(g + c)), __ldg(b + c));
+#pragma unroll
+        for (int i = 0; i < LN_V4; ++i) {
+            const int c = i * 32 + lane;
+            if (c < nv) {
+                const float4 g4 = __ldg(reinterpret_cast<const float4*>(g) + c);
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(b) + c);
+                float4 o;
+                o.x = __fadd_rn(__fmul_rn(__fdiv_rn(v[i].x, den), g4.x), b4.x);
+                o.y = __fadd_rn(__fmul_rn(__fdiv_rn(v[i].y, den), g4.y), b4.y);
+                o.z = __fadd_rn(__fmul_rn(__fdiv_rn(v[i].z, den), g4.z), b4.z);
+                o.w = __fadd_rn(__fmul_rn(__fdiv_rn(v[i].w, den), g4.w), b4.w);
+                xr[c] = o;
+            }
+        }
     }
 }
 
+// copies rows [r0, r0+RC) of src[R][K] (L2) into xs[RC][K]; 8 independent 16-byte loads per thread in flight
 template <int RC>
 __device__ __forceinline__ void stage_copy(const float* src, int r0, int R, int K, float* xs) {
     const int n4 = RC * K / 4;
-    for (int i = threadIdx.x; i < n4; i += NT) {
-        const int rr = (i * 4) / K, c = (i * 4) % K;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r0 + rr < R) v = __ldcg(reinterpret_cast<const float4*>(src + (int64_t)(r0 + rr) * K + c));
-        *reinterpret_cast<float4*>(xs + rr * K + c) = v;
+    for (int i0 = threadIdx.x; i0 < n4; i0 += NT * 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * NT;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < n4) {
+                const int rr = (i * 4) / K, c = (i * 4) % K;
+                if (r0 + rr < R) v[u] = __ldcg(reinterpret_cast<const float4*>(src + (int64_t)(r0 + rr) * K + c));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * NT;
+            if (i < n4) *reinterpret_cast<float4*>(xs + (int64_t)i * 4) = v[u];
+        }
     }
 }
 
@@ -234,7 +271,7 @@ __device__ __forceinline__ void dot_groups(const WT* (&wrow)[G], const float* xs
     for (int g = 0; g < G; ++g)
 #pragma unroll
         for (int rr = 0; rr < RC; ++rr) acc[g][rr] = 0.0f;
-#pragma unroll 3
+#pragma unroll 6
     for (int k0 = l * 8; k0 < K; k0 += 64) {
         float w[G][8];
 #pragma unroll
@@ -530,16 +567,24 @@ dec3_kernel(const Dec3Args a) {
                     const int rr = i / H, h = i % H, r = r0 + rr;
                     if (r < R) {
                         const int64_t o = ((int64_t)r * H + h) * S;
-                        float M = -INFINITY;
-                        for (int s = 0; s < S; ++s) M = fmaxf(M, __ldcg(a.part_m + o + s));
-                        float den = 0.0f;
-                        for (int s = 0; s < S; ++s) {
-                            const float m = __ldcg(a.part_m + o + s);
-                            const float e = m > -INFINITY ? expf(m - M) : 0.0f;
-                            wn[i * S + s] = e;
-                            den += e * __ldcg(a.part_l + o + s);
+                        float pm[16], pl[16];
+#pragma unroll
+                        for (int s = 0; s < 16; ++s) {
+                            pm[s] = s < S ? __ldcg(a.part_m + o + s) : -INFINITY;
+                            pl[s] = s < S ? __ldcg(a.part_l + o + s) : 0.0f;
                         }
-                        for (int s = 0; s < S; ++s) wn[i * S + s] = __fdiv_rn(wn[i * S + s], den);
+                        float M = -INFINITY;
+#pragma unroll
+                        for (int s = 0; s < 16; ++s) M = fmaxf(M, pm[s]);
+                        float den = 0.0f;
+#pragma unroll
+                        for (int s = 0; s < 16; ++s) {
+                            pm[s] = pm[s] > -INFINITY ? expf(pm[s] - M) : 0.0f;
+                            den += pm[s] * pl[s];
+                        }
+#pragma unroll
+                        for (int s = 0; s < 16; ++s)
+                            if (s < S) wn[i * S + s] = __fdiv_rn(pm[s], den);
                     } else {
                         for (int s = 0; s < S; ++s) wn[i * S + s] = 0.0f;
                     }
@@ -550,7 +595,7 @@ dec3_kernel(const Dec3Args a) {
                     const int h = c / 64;
                     const float4* po = reinterpret_cast<const float4*>(a.part_o + (((int64_t)r * H + h) * S) * 64 + (c & 63));
                     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
+#pragma unroll 8
                     for (int s = 0; s < S; ++s) {
                         const float4 v = __ldcg(po + s * 16);
                         const float wgt = wn[(rr * H + h) * S + s];
@@ -761,10 +806,14 @@ template <typename WT, int RC, int KC>
 void launch_t(const Dec3Args& a, int n_ctas, cudaStream_t st) {
     const size_t smem = dec3_smem_bytes(a.d, a.H, a.n_splits, RC, KC);
     auto k = dec3_kernel<WT, RC, KC>;
-    WB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    WB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, NT, smem));
-    if (per_sm < 1) fail(WB_ERR_UNSUPPORTED, "decoder megakernel does not fit on an SM");
+    static size_t configured = 0;   // per instantiation
+    if (configured != smem) {
+        WB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        WB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, NT, smem));
+        if (per_sm < 1) fail(WB_ERR_UNSUPPORTED, "decoder megakernel does not fit on an SM");
+        configured = smem;
+    }
     void* args[] = {(void*)&a};
     WB_CUDA(cudaLaunchCooperativeKernel((void*)k, dim3(n_ctas), dim3(NT), args, smem, st));
     WB_LAUNCH_CHECK();
