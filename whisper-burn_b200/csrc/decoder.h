@@ -222,6 +222,8 @@ struct Dec3Args {
     int* lg_i = nullptr;
     int *pos = nullptr, *n_unfinished = nullptr, *steps_done = nullptr;
     unsigned int* bar = nullptr;          // [2] arrival count, generation
+    unsigned long long* trace = nullptr;  // optional: stage / barrier timestamps of CTA 0 (ns)
+    int trace_cap = 0;
 };
 void launch_dec3(const Dec3Args& a, int n_ctas, bool w_half, cudaStream_t st);
 

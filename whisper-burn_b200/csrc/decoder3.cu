@@ -57,6 +57,17 @@ __device__ __forceinline__ unsigned int ld_acquire(const unsigned int* p) {
     return v;
 }
 
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// optional stage trace (CTA 0, thread 0): pairs of (stage end, barrier end) nanosecond stamps
+#define WB_TRACE()                                                                          \
+    do {                                                                                    \
+        if (a.trace && blockIdx.x == 0 && threadIdx.x == 0 && tr_n < a.trace_cap) a.trace[tr_n++] = gtime(); \
+    } while (0)
+
 // Grid barrier: bar[0] = arrival count, bar[1] = generation.  All CTAs are co-resident (cooperative launch).
 __device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int& gen) {
     __syncthreads();
@@ -462,6 +473,8 @@ dec3_kernel(const Dec3Args a) {
     float* ML = ao + 64;                    // [2]
     float* red = ML + 2;                    // logits merge scratch: [NW][RC][2 + 2*KC]; also cross merge weights
     unsigned int gen = ld_acquire(&a.bar[1]);
+    int tr_n = 0;
+    WB_TRACE();
     const float scale = a.qk_scale;
     const int S = a.n_splits;
 
@@ -475,7 +488,9 @@ dec3_kernel(const Dec3Args a) {
             const float* pe = a.pos_emb + (int64_t)p * d;
             for (int c = tid; c < d; c += NT) a.x[(int64_t)r * d + c] = __fadd_rn(__ldg(e + c), __ldg(pe + c));
         }
+        WB_TRACE();
         grid_sync(a.bar, gen);
+        WB_TRACE();
         for (int l = 0; l < L; ++l) {
             const Dec3Layer& W = a.layers[l];
             float* kcl = a.kc + (size_t)l * a.Rmax * t_max * d;
@@ -496,7 +511,9 @@ dec3_kernel(const Dec3Args a) {
                 });
                 __syncthreads();
             }
-            grid_sync(a.bar, gen);
+            WB_TRACE();
+        grid_sync(a.bar, gen);
+        WB_TRACE();
             // ================= P2: self attention over positions 0..p of the row's ancestry (mask == causal)
             for (int u = blockIdx.x; u < R * H; u += gridDim.x) {
                 const int r = u / H, h = u % H;
@@ -511,7 +528,9 @@ dec3_kernel(const Dec3Args a) {
                 if (tid < 64) a.att[(int64_t)r * d + h * 64 + tid] = __fdiv_rn(ao[tid], ML[1]);
                 __syncthreads();
             }
-            grid_sync(a.bar, gen);
+            WB_TRACE();
+        grid_sync(a.bar, gen);
+        WB_TRACE();
             // ================= P3: x += att Wo + bo   (mod.rs:435, :346)
             for (int r0 = 0; r0 < R; r0 += RC) {
                 stage_copy<RC>(a.att, r0, R, d, xs);
@@ -524,7 +543,9 @@ dec3_kernel(const Dec3Args a) {
                 });
                 __syncthreads();
             }
-            grid_sync(a.bar, gen);
+            WB_TRACE();
+        grid_sync(a.bar, gen);
+        WB_TRACE();
             // ================= P4: cross query = LN(x) Wq + b   (mod.rs:483)
             for (int r0 = 0; r0 < R; r0 += RC) {
                 stage_ln<RC>(a.x, r0, R, d, W.ln2_g, W.ln2_b, W.ln2_eps, a.eps_outside, xs);
@@ -535,7 +556,9 @@ dec3_kernel(const Dec3Args a) {
                 });
                 __syncthreads();
             }
-            grid_sync(a.bar, gen);
+            WB_TRACE();
+        grid_sync(a.bar, gen);
+        WB_TRACE();
             // ================= P5: cross attention, split over the window's encoder positions (K/V projected once per window)
             {
                 const float* ckvl = a.ckv + (size_t)l * a.Mcap * 2 * d;
@@ -559,7 +582,9 @@ dec3_kernel(const Dec3Args a) {
                     __syncthreads();
                 }
             }
-            grid_sync(a.bar, gen);
+            WB_TRACE();
+        grid_sync(a.bar, gen);
+        WB_TRACE();
             // ================= P6: x += merge(cross partials) Wo + bo   (mod.rs:489, :347)
             for (int r0 = 0; r0 < R; r0 += RC) {
                 float* wn = red;   // [RC][H][S] normalised split weights
@@ -613,7 +638,9 @@ dec3_kernel(const Dec3Args a) {
                 });
                 __syncthreads();
             }
-            grid_sync(a.bar, gen);
+            WB_TRACE();
+        grid_sync(a.bar, gen);
+        WB_TRACE();
             // ================= P7: hid = gelu(LN(x) W1 + b1)   (mod.rs:377-378)
             for (int r0 = 0; r0 < R; r0 += RC) {
                 stage_ln<RC>(a.x, r0, R, d, W.ln3_g, W.ln3_b, W.ln3_eps, a.eps_outside, xs);
@@ -624,7 +651,9 @@ dec3_kernel(const Dec3Args a) {
                 });
                 __syncthreads();
             }
-            grid_sync(a.bar, gen);
+            WB_TRACE();
+        grid_sync(a.bar, gen);
+        WB_TRACE();
             // ================= P8: x += hid W2 + b2   (mod.rs:379, :348)
             for (int r0 = 0; r0 < R; r0 += RC) {
                 stage_copy<RC>(a.hid, r0, R, 4 * d, xs);
@@ -637,7 +666,9 @@ dec3_kernel(const Dec3Args a) {
                 });
                 __syncthreads();
             }
-            grid_sync(a.bar, gen);
+            WB_TRACE();
+        grid_sync(a.bar, gen);
+        WB_TRACE();
         }
         if (want_logits) {
             // ================= logits = LN(x) tok_emb^T (mod.rs:155-156) + mask + online softmax + candidates.
@@ -708,7 +739,9 @@ dec3_kernel(const Dec3Args a) {
                 }
                 __syncthreads();
             }
-            grid_sync(a.bar, gen);
+            WB_TRACE();
+        grid_sync(a.bar, gen);
+        WB_TRACE();
             // ================= finish: log_softmax of the candidates, k best (ties -> lower id), greedy bookkeeping
             for (int r = blockIdx.x; r < R; r += gridDim.x) {
                 float* s_f = wm;   // [NW] scratch
@@ -777,7 +810,9 @@ dec3_kernel(const Dec3Args a) {
                     prev_i = bi;
                 }
             }
-            grid_sync(a.bar, gen);
+            WB_TRACE();
+        grid_sync(a.bar, gen);
+        WB_TRACE();
             if (a.greedy) {   // stop as soon as every search has produced EOT (beam.rs:22-27)
                 int live = 0;
                 for (int r = 0; r < R; ++r) live += __ldcg(a.finished + r) ? 0 : 1;

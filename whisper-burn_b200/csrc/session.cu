@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <climits>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -398,7 +399,23 @@ void Session::launch_v3(int R_, int pos0, int n_steps, int logits_from, bool use
     a.topk_id = topk_id.p; a.topk_lp = topk_lp.p; a.logits_out = full_logits ? logits.p : nullptr;
     a.lg_m = lg_m.p; a.lg_s = lg_s.p; a.lg_v = lg_v.p; a.lg_i = lg_i.p;
     a.pos = pos.p; a.n_unfinished = n_unfinished.p; a.steps_done = steps_done.p; a.bar = d3_bar.p;
+    if (getenv("WB200_TRACE")) {
+        d3_trace.ensure(1 << 16);
+        WB_CUDA(cudaMemsetAsync(d3_trace.p, 0, sizeof(unsigned long long) * (1 << 16), st));
+        a.trace = d3_trace.p;
+        a.trace_cap = 1 << 16;
+    }
     launch_dec3(a, n_sm, m->fp16_exact, st);
+    if (a.trace) {
+        std::vector<unsigned long long> h(1 << 16);
+        WB_CUDA(cudaStreamSynchronize(st));
+        WB_CUDA(cudaMemcpy(h.data(), d3_trace.p, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        FILE* f = fopen("gpurun_out/d3_trace.txt", "w");
+        if (f) {
+            for (size_t i = 0; i < h.size() && h[i]; ++i) fprintf(f, "%llu\n", h[i]);
+            fclose(f);
+        }
+    }
 }
 
 void Session::step_core(bool with_logits, int mask_mode, int k, bool greedy, int eot, float* logprob_out) {

@@ -66,6 +66,7 @@ struct Session {
     DevBuf<unsigned int> d3_bar;
     DevBuf<int> steps_done;
     DevBuf<float> datt;
+    DevBuf<unsigned long long> d3_trace;   // debug: WB200_TRACE=1
     void launch_v3(int R_, int pos0, int n_steps, int logits_from, bool use_cur_tok, int mask_mode, int k, bool greedy,
                    int eot);
     bool full_logits = false;    // also write raw logits [R][V] (stateless forward_decoder)
