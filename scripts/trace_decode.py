@@ -16,10 +16,10 @@ t = np.loadtxt("gpurun_out/d3_trace.txt", dtype=np.uint64).astype(np.int64)
 print("stamps", len(t), "total ms", (t[-1] - t[0]) / 1e6)
 # stamps: start, then per barrier (stage_end, barrier_end)
 L = dims.n_text_layer
-per_step = 2 * (1 + 8 * L + 2)
-names = ["embed"] + [f"L{l}.{n}" for l in range(L) for n in ("qkv", "self", "out", "cq", "cross", "cout", "mlp1", "mlp2")] + ["logits", "finish"]
+per_step = 2 * (8 * L + 2)
+names = [f"L{l}.{n}" for l in range(L) for n in ("qkv", "self", "out", "cq", "cross", "cout", "mlp1", "mlp2")] + ["logits", "finish"]
 body = t[1:]
-prefill = 3 * 2 * (1 + 8 * L)
+prefill = 3 * 2 * (8 * L)
 steps = body[prefill:]
 n = len(steps) // per_step
 steps = steps[:n * per_step].reshape(n, per_step // 2, 2)

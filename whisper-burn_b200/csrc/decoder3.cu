@@ -68,24 +68,20 @@ __device__ __forceinline__ unsigned long long gtime() {
         if (a.trace && blockIdx.x == 0 && threadIdx.x == 0 && tr_n < a.trace_cap) a.trace[tr_n++] = gtime(); \
     } while (0)
 
-// Grid barrier: bar[0] = arrival count, bar[1] = generation.  All CTAs are co-resident (cooperative launch).
+// Grid barrier on a monotonic counter (zeroed by the host before the launch): arrive with a one-way
+// red.release (no returned value to wait for), then poll until all CTAs of this round have arrived.
+// All CTAs are co-resident (cooperative launch).  `gen` counts the barriers this CTA has passed.
 __device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int& gen) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
-        if (atomicAdd(&bar[0], 1u) == gridDim.x - 1u) {
-            bar[0] = 0u;
-            __threadfence();
-            atomicAdd(&bar[1], 1u);
-        } else {
-            long long t0 = clock64();
-            while (ld_acquire(&bar[1]) == gen) {
-                if (clock64() - t0 > 4000000000LL) __trap();   // ~2 s: fail loudly instead of hanging the GPU
-            }
+        ++gen;
+        const unsigned int target = gen * gridDim.x;
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+        long long t0 = clock64();
+        while (ld_acquire(bar) < target) {
+            if (clock64() - t0 > 4000000000LL) __trap();   // ~2 s: fail loudly instead of hanging the GPU
         }
-        __threadfence();
     }
-    gen++;
     __syncthreads();
 }
 
@@ -146,6 +142,35 @@ __device__ __forceinline__ void stage_ln(const float* src, int r0, int R, int d,
                 xr[c] = o;
             }
         }
+    }
+}
+
+// same LayerNorm, source rows already in shared memory (src_s[rr][d])
+template <int RC>
+__device__ __forceinline__ void stage_ln_smem(const float* src_s, int r0, int R, int d, const float* __restrict__ g,
+                                              const float* __restrict__ b, float eps, int eps_outside, float* xs) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int rr = warp; rr < RC; rr += NW) {
+        float* xr = xs + rr * d;
+        if (r0 + rr >= R) {
+            for (int c = lane; c < d; c += 32) xr[c] = 0.0f;
+            continue;
+        }
+        const float* s = src_s + rr * d;
+        float sum = 0.0f;
+        for (int c = lane; c < d; c += 32) sum += s[c];
+        sum = warp_sum(sum);
+        const float mean = __fdiv_rn(sum, (float)d);
+        float q = 0.0f;
+        for (int c = lane; c < d; c += 32) {
+            const float dv = __fsub_rn(s[c], mean);
+            q = __fadd_rn(q, __fmul_rn(dv, dv));
+        }
+        q = warp_sum(q);
+        const float var = __fdiv_rn(q, (float)d);
+        const float den = eps_outside ? __fadd_rn(__fsqrt_rn(var), eps) : __fsqrt_rn(__fadd_rn(var, eps));
+        for (int c = lane; c < d; c += 32)
+            xr[c] = __fadd_rn(__fmul_rn(__fdiv_rn(__fsub_rn(s[c], mean), den), __ldg(g + c)), __ldg(b + c));
     }
 }
 
@@ -472,7 +497,7 @@ dec3_kernel(const Dec3Args a) {
     float* ao = wo + NW * 64;               // [64]
     float* ML = ao + 64;                    // [2]
     float* red = ML + 2;                    // logits merge scratch: [NW][RC][2 + 2*KC]; also cross merge weights
-    unsigned int gen = ld_acquire(&a.bar[1]);
+    unsigned int gen = 0;
     int tr_n = 0;
     WB_TRACE();
     const float scale = a.qk_scale;
@@ -481,23 +506,33 @@ dec3_kernel(const Dec3Args a) {
     for (int step = 0; step < a.n_steps; ++step) {
         const int p = a.pos0 + step;
         const bool want_logits = p >= a.logits_from;
-        // ================= embed: x[r] = tok_emb[token] + pos_emb[p]  (mod.rs:141-146)
-        for (int r = blockIdx.x; r < R; r += gridDim.x) {
-            const int tok = a.use_cur_tok ? __ldcg(a.cur_tok + r) : __ldcg(a.tokens + (int64_t)r * t_max + p);
-            const float* e = a.tok_emb + (int64_t)tok * d;
-            const float* pe = a.pos_emb + (int64_t)p * d;
-            for (int c = tid; c < d; c += NT) a.x[(int64_t)r * d + c] = __fadd_rn(__ldg(e + c), __ldg(pe + c));
-        }
-        WB_TRACE();
-        grid_sync(a.bar, gen);
-        WB_TRACE();
+        // embed: x[r] = tok_emb[token] + pos_emb[p] (mod.rs:141-146) is formed by EVERY CTA in shared memory for
+        // the first LayerNorm (no extra barrier); rows are published to a.x by the CTAs r % grid for the residual adds.
         for (int l = 0; l < L; ++l) {
             const Dec3Layer& W = a.layers[l];
             float* kcl = a.kc + (size_t)l * a.Rmax * t_max * d;
             float* vcl = a.vc + (size_t)l * a.Rmax * t_max * d;
             // ================= P1: q | k | v = LN(x) Wqkv + b   (mod.rs:429-431)
             for (int r0 = 0; r0 < R; r0 += RC) {
-                stage_ln<RC>(a.x, r0, R, d, W.ln1_g, W.ln1_b, W.ln1_eps, a.eps_outside, xs);
+                if (l == 0) {
+                    float* emb_s = xs + RC * d;   // scratch behind the LN rows (xs holds RC*4d floats)
+                    for (int rr = 0; rr < RC; ++rr) {
+                        const int r = r0 + rr;
+                        if (r >= R) break;
+                        const int tok = a.use_cur_tok ? __ldcg(a.cur_tok + r) : __ldcg(a.tokens + (int64_t)r * t_max + p);
+                        const float* e = a.tok_emb + (int64_t)tok * d;
+                        const float* pe = a.pos_emb + (int64_t)p * d;
+                        for (int c = tid; c < d; c += NT) {
+                            const float v = __fadd_rn(__ldg(e + c), __ldg(pe + c));
+                            emb_s[rr * d + c] = v;
+                            if (r % gridDim.x == blockIdx.x) a.x[(int64_t)r * d + c] = v;
+                        }
+                    }
+                    __syncthreads();
+                    stage_ln_smem<RC>(emb_s, r0, R, d, W.ln1_g, W.ln1_b, W.ln1_eps, a.eps_outside, xs);
+                } else {
+                    stage_ln<RC>(a.x, r0, R, d, W.ln1_g, W.ln1_b, W.ln1_eps, a.eps_outside, xs);
+                }
                 __syncthreads();
                 gemv_phase<WT, RC>(reinterpret_cast<const WT*>(W.Wqkv), 3 * d, d, xs, gw, n_gw, [&](int n, const float (&acc)[RC]) {
                     if (lane < RC && r0 + lane < R) {

@@ -405,6 +405,7 @@ void Session::launch_v3(int R_, int pos0, int n_steps, int logits_from, bool use
         a.trace = d3_trace.p;
         a.trace_cap = 1 << 16;
     }
+    WB_CUDA(cudaMemsetAsync(d3_bar.p, 0, 2 * sizeof(unsigned int), st));   // monotonic barrier counter starts at 0
     launch_dec3(a, n_sm, m->fp16_exact, st);
     if (a.trace) {
         std::vector<unsigned long long> h(1 << 16);
