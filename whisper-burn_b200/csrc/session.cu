@@ -44,6 +44,11 @@ Session::Session(Model* model, int64_t max_w, int64_t max_b, int64_t max_text_le
     x.alloc(Mcap * d); xn.alloc(Mcap * d); att.alloc(Mcap * d); qkv.alloc(Mcap * 3 * d); hid.alloc(Mcap * 4 * d);
     xa.alloc(Mcap * d);
     ckv.alloc((size_t)L * Mcap * 2 * d);
+    {
+        const char* e = getenv("WB200_GEMM");
+        use_tc = m->fp16_exact && !(e && std::strcmp(e, "simt") == 0);
+        if (use_tc) { lo_a.alloc(Mcap * 4 * d); lo_b.alloc(Mcap * d); xa_hi.alloc(Mcap * d); }
+    }
     kc.alloc((size_t)L * Rmax * t_max * d); vc.alloc((size_t)L * Rmax * t_max * d);
     dx.alloc((size_t)Rmax * d); dq.alloc((size_t)Rmax * d); dhid.alloc((size_t)Rmax * 4 * d);
     logits.alloc((size_t)Rmax * V);
@@ -211,6 +216,19 @@ void Session::load_encoder_output_host(const float* xa_host, int64_t n, int64_t 
 }
 
 // ---- encoder ------------------------------------------------------------------------------------
+// Plain (ungrouped) GEMM: tensor cores when the weights are TF32-exact; a_mut (== p.A) is overwritten by
+// its TF32 hi plane, lo_buf receives the lo plane.
+void Session::gemm(const GemmParams& p, float* a_mut, float* lo_buf) {
+    if (use_tc && p.groups == nullptr && p.lda == p.K && gemm_tc_supported(p)) {
+        launch_split_tf32(p.A, a_mut, lo_buf, (int64_t)p.max_rows * p.K, st);
+        GemmParams q = p;
+        q.A = a_mut;
+        launch_gemm_tc(q, lo_buf, 0, p.max_rows, st);
+    } else {
+        launch_gemm(p, st);
+    }
+}
+
 void Session::run_encoder() {
     const wb_dims& D = m->dims;
     const int d = D.n_audio_state;
@@ -237,22 +255,22 @@ void Session::run_encoder() {
         p = GemmParams{};
         p.A = xn.p; p.lda = d; p.B = B.qkv.w32; p.C = qkv.p; p.ldc = 3 * d; p.N = 3 * d; p.K = d;
         p.bias = B.qkv.b; p.scale = qk_scale; p.scale_cols = 2 * d; p.max_rows = M;
-        launch_gemm(p, st);
+        gemm(p, xn.p, lo_a.p);
         launch_encoder_attention(qkv.p, att.p, d_awin.p, n_windows, max_T, d, D.n_audio_head, st);
         p = GemmParams{};
         p.A = att.p; p.lda = d; p.B = B.out.w32; p.C = x.p; p.ldc = d; p.N = d; p.K = d;
         p.bias = B.out.b; p.residual = x.p; p.max_rows = M;
-        launch_gemm(p, st);
+        gemm(p, att.p, lo_a.p);
         // x = x + mlp(mlp_ln(x))     (mod.rs:301)
         launch_layernorm(x.p, xn.p, B.mlp_ln, M, d, m->ln_eps_outside, st);
         p = GemmParams{};
         p.A = xn.p; p.lda = d; p.B = B.mlp1.w32; p.C = hid.p; p.ldc = 4 * d; p.N = 4 * d; p.K = d;
         p.bias = B.mlp1.b; p.act = ACT_GELU; p.max_rows = M;
-        launch_gemm(p, st);
+        gemm(p, xn.p, lo_a.p);
         p = GemmParams{};
         p.A = hid.p; p.lda = 4 * d; p.B = B.mlp2.w32; p.C = x.p; p.ldc = d; p.N = d; p.K = 4 * d;
         p.bias = B.mlp2.b; p.residual = x.p; p.max_rows = M;
-        launch_gemm(p, st);
+        gemm(p, hid.p, lo_a.p);
     }
     launch_layernorm(x.p, xa.p, m->ln_post, M, d, m->ln_eps_outside, st);   // mod.rs:259
     run_cross_kv();
@@ -263,12 +281,22 @@ void Session::run_cross_kv() {
     const wb_dims& D = m->dims;
     const int d = D.n_text_state;
     const float qk_scale = (float)std::pow((double)d / (double)D.n_text_head, -0.25);
+    bool tc = false;
     for (int l = 0; l < D.n_text_layer; ++l) {
         const DecBlockW& B = m->dec[(size_t)l];
         GemmParams p;
         p.A = xa.p; p.lda = d; p.B = B.ckv.w32; p.C = ckv.p + (size_t)l * Mcap * 2 * d; p.ldc = 2 * d;
         p.N = 2 * d; p.K = d; p.bias = B.ckv.b; p.scale = qk_scale; p.scale_cols = d; p.max_rows = (int)M_tot;
-        launch_gemm(p, st);
+        if (use_tc && gemm_tc_supported(p)) {
+            if (!tc) {   // the encoder output itself stays intact (it is returned through the ABI)
+                launch_split_tf32(xa.p, xa_hi.p, lo_b.p, (int64_t)M_tot * d, st);
+                tc = true;
+            }
+            p.A = xa_hi.p;
+            launch_gemm_tc(p, lo_b.p, 0, (int)M_tot, st);
+        } else {
+            launch_gemm(p, st);
+        }
     }
 }
 

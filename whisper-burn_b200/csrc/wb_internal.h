@@ -168,6 +168,10 @@ struct GemmParams {
     int max_rows = 0;                 // max rows over groups
 };
 void launch_gemm(const GemmParams& p, cudaStream_t st);
+// tensor-core path (gemm_tc.cu): p.A is the TF32 hi plane, a_lo the lo plane of the same geometry
+bool gemm_tc_supported(const GemmParams& p);
+void launch_split_tf32(const float* src, float* hi, float* lo, int64_t n, cudaStream_t st);
+void launch_gemm_tc(const GemmParams& p, const float* a_lo, int64_t a_group_stride, int a_rows_total_per_group, cudaStream_t st);
 
 // ---- frontend (logmel.cu) ---------------------------------------------------------------------
 struct LogMelWindow {
