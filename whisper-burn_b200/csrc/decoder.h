@@ -224,7 +224,6 @@ struct Dec3Args {
     unsigned int* bar = nullptr;          // [2] arrival count, generation
     unsigned long long* trace = nullptr;  // optional: stage / barrier timestamps of CTA 0 (ns)
     int trace_cap = 0;
-    int xs_floats = 0;                    // size of the staged-activation region in shared memory (set by the launcher)
 };
 void launch_dec3(const Dec3Args& a, int n_ctas, bool w_half, cudaStream_t st);
 

@@ -490,7 +490,7 @@ dec3_kernel(const Dec3Args a) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int gw = blockIdx.x * NW + warp, n_gw = gridDim.x * NW;
     float* xs = sm;                         // [RC][4d] staged activations
-    float* qs = xs + a.xs_floats;           // [64] query of the current attention unit (xs region: max(RC*4d, RC*d + logits ring))
+    float* qs = xs + RC * 4 * d;            // [64] query of the current attention unit
     float* wm = qs + 64;                    // [NW]
     float* wl = wm + NW;                    // [NW]
     float* wo = wl + NW;                    // [NW][64]
@@ -719,76 +719,34 @@ dec3_kernel(const Dec3Args a) {
                 float m_run = -INFINITY, s_run = 0.0f;
                 Cand<KC> cand;
                 cand.init();
-                // Each warp streams its 4-row blocks of the embedding matrix through a private ring of NBUF
-                // shared-memory buffers with cp.async (16 B per lane per op, L2 evict-first: the matrix is read once
-                // per step and must not displace the layer weights / K/V that live in L2 across steps).
-                constexpr int NBUF = 4;
-                const int row_bytes = d * (int)sizeof(WT);
-                const int row_pitch = row_bytes + 16;                       // +16 B: the 4 rows land in different banks
-                uint8_t* ring = reinterpret_cast<uint8_t*>(xs + RC * d) + (size_t)warp * NBUF * 4 * row_pitch;
-                const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
-                uint64_t pol;
-                asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-                const int n_blk = (V + 3) / 4;
-                const int vec_per_row = row_bytes / 16;
-                auto issue = [&](int blk, int buf) {
-                    if (blk < n_blk) {
-                        for (int i = lane; i < 4 * vec_per_row; i += 32) {
-                            const int rw = i / vec_per_row, v = i % vec_per_row;
-                            const int n = min(blk * 4 + rw, V - 1);
-                            const char* src = reinterpret_cast<const char*>(E + (int64_t)n * d) + v * 16;
-                            const uint32_t dst = ring_s + (uint32_t)((buf * 4 + rw) * row_pitch + v * 16);
-                            asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(pol) : "memory");
-                        }
+                const int n_blk = (V + 7) / 8;
+                for (int blk = gw; blk < n_blk; blk += n_gw) {
+                    const int n0 = blk * 8;
+                    const WT* rows[2];
+                    int nn[2];
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        nn[g] = n0 + g * 4 + sub;
+                        rows[g] = E + (int64_t)min(nn[g], V - 1) * d;
                     }
-                    asm volatile("cp.async.commit_group;" ::: "memory");
-                };
+                    float acc[2][RC];
+                    dot_groups<WT, RC, 2>(rows, xs, d, acc);
+                    if (l8 < RC && r0 + l8 < R) {
 #pragma unroll
-                for (int j = 0; j < NBUF - 1; ++j) issue(gw + j * n_gw, j);
-                int it = 0;
-                for (int blk = gw; blk < n_blk; blk += n_gw, ++it) {
-                    issue(blk + (NBUF - 1) * n_gw, (it + NBUF - 1) % NBUF);
-                    asm volatile("cp.async.wait_group %0;" ::"n"(NBUF - 1) : "memory");
-                    __syncwarp();
-                    const uint8_t* wrow = ring + (size_t)((it % NBUF) * 4 + sub) * row_pitch;
-                    float acc1[RC];
-#pragma unroll
-                    for (int rr = 0; rr < RC; ++rr) acc1[rr] = 0.0f;
-                    for (int k0 = l8 * 8; k0 < d; k0 += 64) {
-                        float w[8];
-                        if constexpr (sizeof(WT) == 2) {
-                            cvt8(*reinterpret_cast<const uint4*>(wrow + k0 * 2), w);
-                        } else {
-                            const float4 a4 = *reinterpret_cast<const float4*>(wrow + k0 * 4);
-                            const float4 b4 = *reinterpret_cast<const float4*>(wrow + k0 * 4 + 16);
-                            w[0] = a4.x; w[1] = a4.y; w[2] = a4.z; w[3] = a4.w; w[4] = b4.x; w[5] = b4.y; w[6] = b4.z; w[7] = b4.w;
+                        for (int g = 0; g < 2; ++g) {
+                            if (nn[g] < V) {
+                                const float raw = pick_row<RC>(acc[g], l8);
+                                if (a.logits_out) a.logits_out[(int64_t)(r0 + l8) * V + nn[g]] = raw;
+                                const float v = (use_mask && a.is_special[nn[g]]) ? __fadd_rn(raw, -INFINITY) : raw;
+                                if (v > -INFINITY) {
+                                    if (v > m_run) { s_run = s_run * expf(m_run - v) + 1.0f; m_run = v; }
+                                    else s_run += expf(v - m_run);
+                                }
+                                cand.push(v, nn[g]);
+                            }
                         }
-#pragma unroll
-                        for (int rr = 0; rr < RC; ++rr) acc1[rr] = dot8_acc<RC>(w, xs + rr * d + k0, acc1[rr]);
-                    }
-#pragma unroll
-                    for (int rr = 0; rr < RC; ++rr) {
-                        float v = acc1[rr];
-                        v += __shfl_xor_sync(0xffffffffu, v, 4);
-                        v += __shfl_xor_sync(0xffffffffu, v, 2);
-                        v += __shfl_xor_sync(0xffffffffu, v, 1);
-                        acc1[rr] = v;
-                    }
-                    __syncwarp();   // everyone is done with this buffer before the next issue overwrites it
-                    const int n = blk * 4 + sub;
-                    if (l8 < RC && r0 + l8 < R && n < V) {
-                        const float raw = pick_row<RC>(acc1, l8);
-                        if (a.logits_out) a.logits_out[(int64_t)(r0 + l8) * V + n] = raw;
-                        const float v = (use_mask && a.is_special[n]) ? __fadd_rn(raw, -INFINITY) : raw;
-                        if (v > -INFINITY) {
-                            if (v > m_run) { s_run = s_run * expf(m_run - v) + 1.0f; m_run = v; }
-                            else s_run += expf(v - m_run);
-                        }
-                        cand.push(v, n);
                     }
                 }
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
-                __syncthreads();   // ring (behind xs) is reused by the merge scratch of other warps? no: keep order simple
                 // merge: 4 sub-groups x 8 warps hold a state for every batch row -> one record per (CTA, row)
                 if (l8 < RC) {
                     float* rec = red + ((warp * 4 + sub) * RC + l8) * (2 + 2 * KC);
@@ -911,17 +869,14 @@ dec3_kernel(const Dec3Args a) {
     }
 }
 
-size_t dec3_smem_bytes(int d, int H, int S, int RC, int KC, int wbytes) {
+size_t dec3_smem_bytes(int d, int H, int S, int RC, int KC) {
     size_t red = std::max((size_t)NW * 4 * RC * (2 + 2 * KC), (size_t)RC * H * S);
-    size_t xs_floats = (size_t)RC * 4 * d;
-    const size_t ring_floats = ((size_t)NW * 4 * 4 * ((size_t)d * wbytes + 16) + 3) / 4;   // logits stage: behind xs[RC][d]
-    xs_floats = std::max(xs_floats, (size_t)RC * d + ring_floats);
-    return sizeof(float) * (xs_floats + 64 + 2 * NW + NW * 64 + 64 + 2 + red + 8);
+    return sizeof(float) * ((size_t)RC * 4 * d + 64 + 2 * NW + NW * 64 + 64 + 2 + red + 8);
 }
 
 template <typename WT, int RC, int KC>
 void launch_t(const Dec3Args& a, int n_ctas, cudaStream_t st) {
-    const size_t smem = dec3_smem_bytes(a.d, a.H, a.n_splits, RC, KC, (int)sizeof(WT));
+    const size_t smem = dec3_smem_bytes(a.d, a.H, a.n_splits, RC, KC);
     auto k = dec3_kernel<WT, RC, KC>;
     static size_t configured = 0;   // per instantiation
     if (configured != smem) {
@@ -931,12 +886,7 @@ void launch_t(const Dec3Args& a, int n_ctas, cudaStream_t st) {
         if (per_sm < 1) fail(WB_ERR_UNSUPPORTED, "decoder megakernel does not fit on an SM");
         configured = smem;
     }
-    Dec3Args b = a;
-    {
-        const size_t ring_floats = ((size_t)NW * 4 * 4 * ((size_t)a.d * sizeof(WT) + 16) + 3) / 4;
-        b.xs_floats = (int)std::max((size_t)RC * 4 * a.d, (size_t)RC * a.d + ring_floats);
-    }
-    void* args[] = {(void*)&b};
+    void* args[] = {(void*)&a};
     WB_CUDA(cudaLaunchCooperativeKernel((void*)k, dim3(n_ctas), dim3(NT), args, smem, st));
     WB_LAUNCH_CHECK();
 }
