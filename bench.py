@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--chunks-per-gpu", type=int, default=1)
     ap.add_argument("--beam", type=int, default=1)
     ap.add_argument("--max-depth", type=int, default=100)
+    ap.add_argument("--kv", default="f32", choices=["f32", "f16"], help="K/V cache dtype (f32 = reference numerics)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-baseline-windows", type=int, default=0, help="windows of chunk 0 timed on the CPU (0 = all)")
     return ap.parse_args()
@@ -197,7 +198,8 @@ def run_ours(args):
     window_len = audio.max_waveform_samples(dims.n_audio_ctx - 10)        # transcribe.rs:32-34 (C ABI, host side)
     bounds = transcribe.window_bounds(CHUNK_SAMPLES, 16000, window_len)   # transcribe.rs:114-138
     n_win = len(bounds) * len(chunks)
-    sess = transcribe.Session(wh, max_windows=n_win, max_beams=max(args.beam, 1), max_text_len=4 + args.max_depth + 1)
+    sess = transcribe.Session(wh, max_windows=n_win, max_beams=max(args.beam, 1), max_text_len=4 + args.max_depth + 1,
+                              kv_dtype=ffi.WB_KV_F16 if args.kv == "f16" else ffi.WB_KV_F32)
 
     # ---- inputs resident in HBM (value) and in pinned host memory (e2e)
     flat = np.concatenate(chunks)
@@ -331,7 +333,7 @@ def run_ours(args):
                        "parallelism": f"dp{world} (windows sharded, weights replicated, one NCCL token all-gather)",
                        "l2": "flushed between timed iterations (256 MB write)", "timing": "wall clock around the synchronous C-ABI call, "
                        "torch.cuda.synchronize() both sides; device_ms = CUDA events on the library stream",
-                       "decode_steps_executed": steps_run, "windows_per_gpu": n_win},
+                       "decode_steps_executed": steps_run, "windows_per_gpu": n_win, "kv_cache": args.kv},
             "device_ms_per_step": ms_dev, "phase_ms": phase,
             "rtf": (ms_step / 1000.0) / audio_s,
             "e2e": {"value": e2e_val, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

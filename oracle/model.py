@@ -109,8 +109,9 @@ def attn_decoder_mask(n: int) -> torch.Tensor:
     return torch.triu(torch.full((n, n), float("-inf"), dtype=torch.float32), diagonal=1)
 
 
-def qkv_attention(q, k, v, mask, n_head: int) -> torch.Tensor:
-    """mod.rs:493-533."""
+def qkv_attention(q, k, v, mask, n_head: int, kv_f16: bool = False) -> torch.Tensor:
+    """mod.rs:493-533.  kv_f16 (not in the reference): the scaled keys and the values are rounded to fp16
+    at the point where the B200 path stores them in its fp16 K/V cache."""
     n_batch, n_qctx, n_state = q.shape
     n_ctx = k.shape[1]
     scale = _f32((n_state / n_head) ** -0.25)
@@ -118,6 +119,9 @@ def qkv_attention(q, k, v, mask, n_head: int) -> torch.Tensor:
     q = q.reshape(n_batch, n_qctx, n_head, n_hstate).transpose(1, 2) * scale
     k = k.reshape(n_batch, n_ctx, n_head, n_hstate).transpose(1, 2).transpose(2, 3) * scale
     v = v.reshape(n_batch, n_ctx, n_head, n_hstate).transpose(1, 2)
+    if kv_f16:
+        k = k.to(torch.float16).to(torch.float32)
+        v = v.to(torch.float16).to(torch.float32)
     qk = torch.matmul(q, k)
     if mask is not None:
         qk = qk + mask[0:n_qctx, 0:n_ctx]
@@ -126,7 +130,11 @@ def qkv_attention(q, k, v, mask, n_head: int) -> torch.Tensor:
 
 
 def _round_kv(t: torch.Tensor, opts: OracleOptions) -> torch.Tensor:
-    return t.to(torch.float16).to(torch.float32) if opts.kv_dtype == "f16" else t
+    return t   # rounding happens inside qkv_attention (after the key scaling), see kv_f16
+
+
+def _f16(opts: OracleOptions) -> bool:
+    return opts.kv_dtype == "f16"
 
 
 def self_attention(x, w, path, mask, n_head, opts=DEFAULT_OPTS):
@@ -134,7 +142,7 @@ def self_attention(x, w, path, mask, n_head, opts=DEFAULT_OPTS):
     q = linear(x, w, path + "/query")
     k = _round_kv(linear(x, w, path + "/key"), opts)
     v = _round_kv(linear(x, w, path + "/value"), opts)
-    return linear(qkv_attention(q, k, v, mask, n_head), w, path + "/out")
+    return linear(qkv_attention(q, k, v, mask, n_head, _f16(opts)), w, path + "/out")
 
 
 def cross_attention(x, xa, w, path, n_head, opts=DEFAULT_OPTS):
@@ -142,7 +150,7 @@ def cross_attention(x, xa, w, path, n_head, opts=DEFAULT_OPTS):
     q = linear(x, w, path + "/query")
     k = _round_kv(linear(xa, w, path + "/key"), opts)
     v = _round_kv(linear(xa, w, path + "/value"), opts)
-    return linear(qkv_attention(q, k, v, None, n_head), w, path + "/out")
+    return linear(qkv_attention(q, k, v, None, n_head, _f16(opts)), w, path + "/out")
 
 
 def mlp(x, w, path):
@@ -226,12 +234,12 @@ class CachedDecoder:
             vn = _round_kv(linear(h, w, p + "/attn/value"), opts)
             self.k[i] = kn if self.k[i] is None else torch.cat([self.k[i], kn], dim=1)
             self.v[i] = vn if self.v[i] is None else torch.cat([self.v[i], vn], dim=1)
-            x = x + linear(qkv_attention(q, self.k[i], self.v[i], None, dims.n_text_head), w, p + "/attn/out")
+            x = x + linear(qkv_attention(q, self.k[i], self.v[i], None, dims.n_text_head, _f16(opts)), w, p + "/attn/out")
             h = layer_norm(x, w, p + "/cross_attn_ln", opts)
             q = linear(h, w, p + "/cross_attn/query")
             ck, cv = self.cross[i]
             x = x + linear(qkv_attention(q, ck.expand(nb, -1, -1), cv.expand(nb, -1, -1), None,
-                                         dims.n_text_head), w, p + "/cross_attn/out")
+                                         dims.n_text_head, _f16(opts)), w, p + "/cross_attn/out")
             x = x + mlp(layer_norm(x, w, p + "/mlp_ln", opts), w, p + "/mlp")
         x = layer_norm(x, w, "decoder/ln", opts)
         self.t += 1

@@ -241,6 +241,22 @@ def test_greedy_equals_beam1_host_path_full_size(tiny):
     assert seq == greedy
 
 
+@pytest.mark.parametrize("beam_size,depth", [(1, 30), (5, 10)])
+def test_fp16_kv_cache_matches_oracle_f16_mode(small, beam_size, depth):
+    """WB_KV_F16 (the north star's persistent fp16 K/V cache): scaled keys and values are rounded to fp16 where
+    they enter the cache; the oracle restates exactly that rounding (OracleOptions.kv_dtype = "f16")."""
+    dims, _, w_t, sp, wh = small
+    chunk = synth.chunk_waveform(0)
+    waves = [chunk[:238559], chunk[:98882]]
+    sess = transcribe.Session(wh, max_windows=2, max_beams=5, max_text_len=4 + depth + 1, kv_dtype=ffi.WB_KV_F16)
+    got = sess.transcribe_windows(waves, sp, is_special_of(sp), beam_size=beam_size, max_depth=depth)
+    opts = o_model.OracleOptions(kv_dtype="f16")
+    for g, wv in zip(got, waves):
+        want = o_tr.mels_to_tokens(w_t, dims, sp, o_audio.prep_audio(torch.from_numpy(wv)[None]), beam_size=beam_size,
+                                   max_depth=depth, opts=opts)
+        assert g == want
+
+
 def test_launch_counter_counts_kernels(small):
     dims, _, _, sp, wh = small
     ffi.lib().wb_kernel_launch_count_reset()

@@ -198,8 +198,9 @@ struct Dec3Args {
     float lnf_eps = 1e-5f;
     // state
     float *x = nullptr, *q = nullptr, *att = nullptr, *hid = nullptr;
-    float *kc = nullptr, *vc = nullptr;   // [L][Rmax][t_max][d]
-    const float* ckv = nullptr;           // [L][Mcap][2d]
+    void *kc = nullptr, *vc = nullptr;    // [L][Rmax][t_max][d]  fp32 or fp16 (kv_half)
+    const void* ckv = nullptr;            // [L][Mcap][2d]
+    int kv_half = 0;
     const int* row_window = nullptr;
     const int64_t* win_row_off = nullptr;
     const int* win_T = nullptr;

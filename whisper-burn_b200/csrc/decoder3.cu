@@ -20,6 +20,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <cfloat>
 #include <climits>
 
@@ -368,15 +369,31 @@ __device__ __forceinline__ void attn_warp(const float* q_smem, int n_keys, int f
     for (int jb = first; jb < n_keys; jb += stride * 8 * UK) {
         float4 kk[UK][4], vv[UK][4];
         bool ok[UK];
+        using KT = typename std::remove_cv<typename std::remove_pointer<decltype(kptr(0))>::type>::type;
 #pragma unroll
         for (int u = 0; u < UK; ++u) {
             const int j = jb + (u * 8 + sub) * stride;
             ok[u] = j < n_keys;
             if (ok[u]) {
-                const float4* kp = reinterpret_cast<const float4*>(kptr(j)) + l4 * 4;
-                const float4* vp = reinterpret_cast<const float4*>(vptr(j)) + l4 * 4;
+                if constexpr (sizeof(KT) == 4) {
+                    const float4* kp = reinterpret_cast<const float4*>(kptr(j)) + l4 * 4;
+                    const float4* vp = reinterpret_cast<const float4*>(vptr(j)) + l4 * 4;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) { kk[u][c] = __ldcg(kp + c); vv[u][c] = __ldcg(vp + c); }
+                    for (int c = 0; c < 4; ++c) { kk[u][c] = __ldcg(kp + c); vv[u][c] = __ldcg(vp + c); }
+                } else {   // fp16 cache: 16 dims = 32 bytes = two 16-byte loads
+                    const uint4* kp = reinterpret_cast<const uint4*>(kptr(j)) + l4 * 2;
+                    const uint4* vp = reinterpret_cast<const uint4*>(vptr(j)) + l4 * 2;
+                    uint4 kr[2], vr[2];
+                    kr[0] = __ldcg(kp); kr[1] = __ldcg(kp + 1); vr[0] = __ldcg(vp); vr[1] = __ldcg(vp + 1);
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        float w[8];
+                        cvt8(kr[c], w);
+                        kk[u][2 * c] = make_float4(w[0], w[1], w[2], w[3]); kk[u][2 * c + 1] = make_float4(w[4], w[5], w[6], w[7]);
+                        cvt8(vr[c], w);
+                        vv[u][2 * c] = make_float4(w[0], w[1], w[2], w[3]); vv[u][2 * c + 1] = make_float4(w[4], w[5], w[6], w[7]);
+                    }
+                }
             } else {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) { kk[u][c] = make_float4(0.f, 0.f, 0.f, 0.f); vv[u][c] = kk[u][c]; }
@@ -482,7 +499,7 @@ struct Cand {
 };
 
 // =====================================================================================================
-template <typename WT, int RC, int KC>
+template <typename WT, int RC, int KC, typename KVT>
 __global__ void __launch_bounds__(NT, 1)
 dec3_kernel(const Dec3Args a) {
     extern __shared__ __align__(16) float sm[];
@@ -510,8 +527,8 @@ dec3_kernel(const Dec3Args a) {
         // the first LayerNorm (no extra barrier); rows are published to a.x by the CTAs r % grid for the residual adds.
         for (int l = 0; l < L; ++l) {
             const Dec3Layer& W = a.layers[l];
-            float* kcl = a.kc + (size_t)l * a.Rmax * t_max * d;
-            float* vcl = a.vc + (size_t)l * a.Rmax * t_max * d;
+            KVT* kcl = reinterpret_cast<KVT*>(a.kc) + (size_t)l * a.Rmax * t_max * d;
+            KVT* vcl = reinterpret_cast<KVT*>(a.vc) + (size_t)l * a.Rmax * t_max * d;
             // ================= P1: q | k | v = LN(x) Wqkv + b   (mod.rs:429-431)
             for (int r0 = 0; r0 < R; r0 += RC) {
                 if (l == 0) {
@@ -542,8 +559,8 @@ dec3_kernel(const Dec3Args a) {
                         float v = __fadd_rn(pick_row<RC>(acc, lane), __ldg(W.bqkv + n));
                         if (n < 2 * d) v = __fmul_rn(v, scale);
                         if (n < d) a.q[(int64_t)r * d + n] = v;
-                        else if (n < 2 * d) kcl[((int64_t)r * t_max + p) * d + (n - d)] = v;
-                        else vcl[((int64_t)r * t_max + p) * d + (n - 2 * d)] = v;
+                        else if (n < 2 * d) kcl[((int64_t)r * t_max + p) * d + (n - d)] = (KVT)v;     // fp16 cache: round-to-nearest
+                        else vcl[((int64_t)r * t_max + p) * d + (n - 2 * d)] = (KVT)v;
                     }
                 });
                 __syncthreads();
@@ -557,8 +574,8 @@ dec3_kernel(const Dec3Args a) {
                 if (tid < 16) *reinterpret_cast<float4*>(qs + tid * 4) = __ldcg(reinterpret_cast<const float4*>(a.q + (int64_t)r * d + h * 64) + tid);
                 __syncthreads();
                 const int* anc = a.anc ? a.anc + (int64_t)r * t_max : nullptr;
-                const float* kb = kcl + h * 64;
-                const float* vb = vcl + h * 64;
+                const KVT* kb = kcl + h * 64;
+                const KVT* vb = vcl + h * 64;
                 auto kp = [&](int j) { return kb + ((int64_t)((anc && j < p) ? __ldcg(anc + j) : r) * t_max + j) * d; };
                 auto vp = [&](int j) { return vb + ((int64_t)((anc && j < p) ? __ldcg(anc + j) : r) * t_max + j) * d; };
                 attn_cta(qs, p + 1, kp, vp, wm, wl, wo, ao, ML);
@@ -598,7 +615,7 @@ dec3_kernel(const Dec3Args a) {
         WB_TRACE();
             // ================= P5: cross attention, split over the window's encoder positions (K/V projected once per window)
             {
-                const float* ckvl = a.ckv + (size_t)l * a.Mcap * 2 * d;
+                const KVT* ckvl = reinterpret_cast<const KVT*>(a.ckv) + (size_t)l * a.Mcap * 2 * d;
                 for (int u = blockIdx.x; u < R * H * S; u += gridDim.x) {
                     const int sp = u % S, h = (u / S) % H, r = u / (S * H);
                     if (tid < 16) *reinterpret_cast<float4*>(qs + tid * 4) = __ldcg(reinterpret_cast<const float4*>(a.q + (int64_t)r * d + h * 64) + tid);
@@ -608,7 +625,7 @@ dec3_kernel(const Dec3Args a) {
                     const int per = (T + S - 1) / S;
                     const int kb0 = sp * per;
                     const int nk = max(0, min(T, kb0 + per) - kb0);
-                    const float* kbase = ckvl + (a.win_row_off[w] + kb0) * (int64_t)(2 * d) + h * 64;
+                    const KVT* kbase = ckvl + (a.win_row_off[w] + kb0) * (int64_t)(2 * d) + h * 64;
                     const int64_t ld = 2 * (int64_t)d;
                     auto kp = [&](int j) { return kbase + j * ld; };
                     auto vp = [&](int j) { return kbase + j * ld + d; };
@@ -874,10 +891,10 @@ size_t dec3_smem_bytes(int d, int H, int S, int RC, int KC) {
     return sizeof(float) * ((size_t)RC * 4 * d + 64 + 2 * NW + NW * 64 + 64 + 2 + red + 8);
 }
 
-template <typename WT, int RC, int KC>
+template <typename WT, int RC, int KC, typename KVT>
 void launch_t(const Dec3Args& a, int n_ctas, cudaStream_t st) {
     const size_t smem = dec3_smem_bytes(a.d, a.H, a.n_splits, RC, KC);
-    auto k = dec3_kernel<WT, RC, KC>;
+    auto k = dec3_kernel<WT, RC, KC, KVT>;
     static size_t configured = 0;   // per instantiation
     if (configured != smem) {
         WB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -898,10 +915,17 @@ void launch_dec3(const Dec3Args& a, int n_ctas, bool w_half, cudaStream_t st) {
     const bool wide = a.k > 1;
 #define WB_D3(WT)                                                        \
     do {                                                                 \
-        if (!big && !wide) launch_t<WT, 4, 2>(a, n_ctas, st);            \
-        else if (!big && wide) launch_t<WT, 4, 8>(a, n_ctas, st);        \
-        else if (big && !wide) launch_t<WT, 8, 2>(a, n_ctas, st);        \
-        else launch_t<WT, 8, 8>(a, n_ctas, st);                          \
+        if (a.kv_half) {                                                 \
+            if (!big && !wide) launch_t<WT, 4, 2, __half>(a, n_ctas, st);        \
+            else if (!big && wide) launch_t<WT, 4, 8, __half>(a, n_ctas, st);    \
+            else if (big && !wide) launch_t<WT, 8, 2, __half>(a, n_ctas, st);    \
+            else launch_t<WT, 8, 8, __half>(a, n_ctas, st);                      \
+        } else {                                                         \
+            if (!big && !wide) launch_t<WT, 4, 2, float>(a, n_ctas, st);         \
+            else if (!big && wide) launch_t<WT, 4, 8, float>(a, n_ctas, st);     \
+            else if (big && !wide) launch_t<WT, 8, 2, float>(a, n_ctas, st);     \
+            else launch_t<WT, 8, 8, float>(a, n_ctas, st);                       \
+        }                                                                \
     } while (0)
     if (w_half) WB_D3(__half);
     else WB_D3(float);

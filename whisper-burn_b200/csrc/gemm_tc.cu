@@ -97,6 +97,7 @@ __device__ __forceinline__ float gelu_erf(float x) {
 
 struct TcArgs {
     float* C;
+    __half* C16;
     const float* bias;
     const float* residual;
     const float* pos;
@@ -226,7 +227,12 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                         v[0] = __fadd_rn(r4.x, v[0]); v[1] = __fadd_rn(r4.y, v[1]);
                         v[2] = __fadd_rn(r4.z, v[2]); v[3] = __fadd_rn(r4.w, v[3]);
                     }
-                    *reinterpret_cast<float4*>(g.C + crow + n) = make_float4(v[0], v[1], v[2], v[3]);
+                    if (g.C16) {
+                        *reinterpret_cast<__half2*>(g.C16 + crow + n) = __floats2half2_rn(v[0], v[1]);
+                        *reinterpret_cast<__half2*>(g.C16 + crow + n + 2) = __floats2half2_rn(v[2], v[3]);
+                    } else {
+                        *reinterpret_cast<float4*>(g.C + crow + n) = make_float4(v[0], v[1], v[2], v[3]);
+                    }
                 }
             }
         }
@@ -329,7 +335,7 @@ void launch_gemm_tc(const GemmParams& p, const float* a_lo, int64_t a_group_stri
     const int BN = (p.N % 128 == 0 && (int64_t)(p.N / 128) * ((p.max_rows + TC_BM - 1) / TC_BM) * ng >= 96) ? 128 : 64;
     const CUtensorMap b = make_map(p.B, (uint64_t)p.K, (uint64_t)p.N, 1, (uint64_t)p.K, (uint64_t)p.K * p.N, TC_BK, (uint32_t)BN, 2);
     TcArgs a;
-    a.C = p.C; a.bias = p.bias; a.residual = p.residual; a.pos = p.pos; a.groups = p.groups;
+    a.C = p.C; a.C16 = p.C16; a.bias = p.bias; a.residual = p.residual; a.pos = p.pos; a.groups = p.groups;
     a.single = GemmGroup{0, 0, p.max_rows};
     a.ldc = p.ldc; a.N = p.N; a.K = p.K; a.act = p.act; a.scale = p.scale; a.scale_cols = p.scale_cols;
     a.a_rows_per_group = a_rows_total_per_group;

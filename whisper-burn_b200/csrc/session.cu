@@ -18,7 +18,7 @@ Session::Session(Model* model, int64_t max_w, int64_t max_b, int64_t max_text_le
     const wb_dims& D = m->dims;
     WB_REQUIRE(max_w >= 1 && max_b >= 1 && max_w * max_b <= 4096, "session: bad max_windows / max_beams");
     WB_REQUIRE(max_text_len >= 2 && max_text_len <= D.n_text_ctx, "session: max_text_len must be in [2, n_text_ctx]");
-    WB_REQUIRE(kv == WB_KV_F32, "session: only WB_KV_F32 is implemented in this build");
+    WB_REQUIRE(kv == WB_KV_F32 || kv == WB_KV_F16, "session: kv_dtype must be WB_KV_F32 or WB_KV_F16");
     WB_CUDA(cudaSetDevice(m->device));
     max_windows = (int)max_w;
     max_beams = (int)max_b;
@@ -43,13 +43,14 @@ Session::Session(Model* model, int64_t max_w, int64_t max_b, int64_t max_text_le
     h1.alloc((size_t)max_windows * TmS * d);
     x.alloc(Mcap * d); xn.alloc(Mcap * d); att.alloc(Mcap * d); qkv.alloc(Mcap * 3 * d); hid.alloc(Mcap * 4 * d);
     xa.alloc(Mcap * d);
-    ckv.alloc((size_t)L * Mcap * 2 * d);
+    if (kv == WB_KV_F16) ckv16.alloc((size_t)L * Mcap * 2 * d); else ckv.alloc((size_t)L * Mcap * 2 * d);
     {
         const char* e = getenv("WB200_GEMM");
         use_tc = m->fp16_exact && !(e && std::strcmp(e, "simt") == 0);
         if (use_tc) { lo_a.alloc(Mcap * 4 * d); lo_b.alloc(Mcap * d); xa_hi.alloc(Mcap * d); }
     }
-    kc.alloc((size_t)L * Rmax * t_max * d); vc.alloc((size_t)L * Rmax * t_max * d);
+    if (kv == WB_KV_F16) { kc16.alloc((size_t)L * Rmax * t_max * d); vc16.alloc((size_t)L * Rmax * t_max * d); }
+    else { kc.alloc((size_t)L * Rmax * t_max * d); vc.alloc((size_t)L * Rmax * t_max * d); }
     dx.alloc((size_t)Rmax * d); dq.alloc((size_t)Rmax * d); dhid.alloc((size_t)Rmax * 4 * d);
     logits.alloc((size_t)Rmax * V);
     part_o.alloc((size_t)Rmax * H * n_splits * 64); part_m.alloc((size_t)Rmax * H * n_splits);
@@ -63,6 +64,7 @@ Session::Session(Model* model, int64_t max_w, int64_t max_b, int64_t max_text_le
         const char* e = getenv("WB200_DECODER");
         if (e && e[0] == '1') dec_version = 1;
         if (e && e[0] == '2') dec_version = 2;
+        if (kv == WB_KV_F16) dec_version = 3;   // the fp16 cache exists in the persistent decoder only
         cudaDeviceProp prop;
         WB_CUDA(cudaGetDeviceProperties(&prop, m->device));
         n_sm = prop.multiProcessorCount;
@@ -285,7 +287,8 @@ void Session::run_cross_kv() {
     for (int l = 0; l < D.n_text_layer; ++l) {
         const DecBlockW& B = m->dec[(size_t)l];
         GemmParams p;
-        p.A = xa.p; p.lda = d; p.B = B.ckv.w32; p.C = ckv.p + (size_t)l * Mcap * 2 * d; p.ldc = 2 * d;
+        p.A = xa.p; p.lda = d; p.B = B.ckv.w32; p.ldc = 2 * d;
+        if (kv_dtype == WB_KV_F16) p.C16 = ckv16.p + (size_t)l * Mcap * 2 * d; else p.C = ckv.p + (size_t)l * Mcap * 2 * d;
         p.N = 2 * d; p.K = d; p.bias = B.ckv.b; p.scale = qk_scale; p.scale_cols = d; p.max_rows = (int)M_tot;
         if (use_tc && gemm_tc_supported(p)) {
             if (!tc) {   // the encoder output itself stays intact (it is returned through the ABI)
@@ -415,7 +418,9 @@ void Session::launch_v3(int R_, int pos0, int n_steps, int logits_from, bool use
     a.layers = d3_layers.p; a.tok_emb = m->tok_emb32; a.pos_emb = m->dec_pos;
     a.E = m->fp16_exact ? (const void*)m->tok_emb16 : (const void*)m->tok_emb32;
     a.lnf_g = m->dec_ln.g; a.lnf_b = m->dec_ln.b; a.lnf_eps = m->dec_ln.eps;
-    a.x = dx.p; a.q = dq.p; a.att = datt.p; a.hid = dhid.p; a.kc = kc.p; a.vc = vc.p; a.ckv = ckv.p;
+    a.x = dx.p; a.q = dq.p; a.att = datt.p; a.hid = dhid.p;
+    a.kv_half = kv_dtype == WB_KV_F16 ? 1 : 0;
+    if (a.kv_half) { a.kc = kc16.p; a.vc = vc16.p; a.ckv = ckv16.p; } else { a.kc = kc.p; a.vc = vc.p; a.ckv = ckv.p; }
     a.row_window = row_window.p; a.win_row_off = d_win_row_off.p; a.win_T = d_win_T.p;
     a.anc = anc_identity ? nullptr : (anc_cur == 0 ? anc0.p : anc1.p);
     a.n_splits = std::max(1, std::min(16, n_sm / std::max(1, R_ * H)));
@@ -448,6 +453,7 @@ void Session::launch_v3(int R_, int pos0, int n_steps, int logits_from, bool use
 }
 
 void Session::step_core(bool with_logits, int mask_mode, int k, bool greedy, int eot, float* logprob_out) {
+    if (kv_dtype == WB_KV_F16 && k > 7) fail(WB_ERR_UNSUPPORTED, "fp16 K/V cache supports k <= 7");
     if (dec_version == 3 && k <= 7) {
         launch_v3(R, host_pos, 1, with_logits ? 0 : INT_MAX, true, mask_mode, k, greedy, eot);
         ++host_pos;

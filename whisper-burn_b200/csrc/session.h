@@ -44,6 +44,7 @@ struct Session {
     DevBuf<float> ckv;     // [L][Mcap][2d]  cross keys (scaled) | values, projected once per window
     // ---- device: decode state
     DevBuf<float> kc, vc;  // [L][Rmax][t_max][d] self keys (scaled) / values
+    DevBuf<__half> kc16, vc16, ckv16;   // fp16 caches (WB_KV_F16)
     DevBuf<float> dx, dq, dhid, logits;
     DevBuf<float> part_o, part_m, part_l;
     DevBuf<int> tokens, lengths, cur_tok, finished, row_window, anc0, anc1, parent, pos, n_unfinished, topk_id;

@@ -155,6 +155,7 @@ struct GemmParams {
     int64_t lda = 0;
     const float* B = nullptr;      // [N][K]
     float* C = nullptr;
+    __half* C16 = nullptr;         // optional: store fp16-rounded results here instead of C (fp16 K/V cache)
     int64_t ldc = 0;
     int N = 0, K = 0;
     const float* bias = nullptr;   // [N] or null
