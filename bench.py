@@ -172,7 +172,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args):
@@ -342,13 +342,26 @@ def run_ours(args):
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "tokens_checksum": int(sum(sum(t) for t in toks) % (1 << 31)),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """Exactly one JSON line on the real stdout (native libraries such as NCCL print banners to fd 1)."""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)            # everything else that writes to fd 1 goes to stderr
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -97,6 +97,7 @@ __device__ __forceinline__ float gelu_erf(float x) {
 
 struct TcArgs {
     float* C;
+    float* C_lo;      // when set: C receives the TF32 hi plane of the result and C_lo the lo plane (feeds the next GEMM)
     __half* C16;
     const float* bias;
     const float* residual;
@@ -230,6 +231,17 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                     if (g.C16) {
                         *reinterpret_cast<__half2*>(g.C16 + crow + n) = __floats2half2_rn(v[0], v[1]);
                         *reinterpret_cast<__half2*>(g.C16 + crow + n + 2) = __floats2half2_rn(v[2], v[3]);
+                    } else if (g.C_lo) {
+                        float h[4], l[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint32_t t;
+                            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v[j]));
+                            h[j] = __uint_as_float(t);
+                            l[j] = __fsub_rn(v[j], h[j]);
+                        }
+                        *reinterpret_cast<float4*>(g.C + crow + n) = make_float4(h[0], h[1], h[2], h[3]);
+                        *reinterpret_cast<float4*>(g.C_lo + crow + n) = make_float4(l[0], l[1], l[2], l[3]);
                     } else {
                         *reinterpret_cast<float4*>(g.C + crow + n) = make_float4(v[0], v[1], v[2], v[3]);
                     }
@@ -289,7 +301,7 @@ CUtensorMap make_map(const float* base, uint64_t dim0, uint64_t dim1, uint64_t d
     const CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void*)base, dims, strides, box, estr,
                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) fail(WB_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+    if (r != CUDA_SUCCESS) fail(WB_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
     return m;
 }
 
@@ -335,7 +347,7 @@ void launch_gemm_tc(const GemmParams& p, const float* a_lo, int64_t a_group_stri
     const int BN = (p.N % 128 == 0 && (int64_t)(p.N / 128) * ((p.max_rows + TC_BM - 1) / TC_BM) * ng >= 96) ? 128 : 64;
     const CUtensorMap b = make_map(p.B, (uint64_t)p.K, (uint64_t)p.N, 1, (uint64_t)p.K, (uint64_t)p.K * p.N, TC_BK, (uint32_t)BN, 2);
     TcArgs a;
-    a.C = p.C; a.C16 = p.C16; a.bias = p.bias; a.residual = p.residual; a.pos = p.pos; a.groups = p.groups;
+    a.C = p.C; a.C_lo = p.C_lo; a.C16 = p.C16; a.bias = p.bias; a.residual = p.residual; a.pos = p.pos; a.groups = p.groups;
     a.single = GemmGroup{0, 0, p.max_rows};
     a.ldc = p.ldc; a.N = p.N; a.K = p.K; a.act = p.act; a.scale = p.scale; a.scale_cols = p.scale_cols;
     a.a_rows_per_group = a_rows_total_per_group;

@@ -47,7 +47,11 @@ Session::Session(Model* model, int64_t max_w, int64_t max_b, int64_t max_text_le
     {
         const char* e = getenv("WB200_GEMM");
         use_tc = m->fp16_exact && !(e && std::strcmp(e, "simt") == 0);
-        if (use_tc) { lo_a.alloc(Mcap * 4 * d); lo_b.alloc(Mcap * d); xa_hi.alloc(Mcap * d); }
+        if (use_tc) {
+            lo_a.alloc(Mcap * d); lo_b.alloc(Mcap * d); lo_b4.alloc(Mcap * 4 * d); xa_hi.alloc(Mcap * d);
+            mel_hi.alloc((size_t)max_windows * TmS * N_MELS); mel_lo.alloc((size_t)max_windows * TmS * N_MELS);
+            h1_lo.alloc((size_t)max_windows * TmS * d);
+        }
     }
     if (kv == WB_KV_F16) { kc16.alloc((size_t)L * Rmax * t_max * d); vc16.alloc((size_t)L * Rmax * t_max * d); }
     else { kc.alloc((size_t)L * Rmax * t_max * d); vc.alloc((size_t)L * Rmax * t_max * d); }
@@ -218,17 +222,12 @@ void Session::load_encoder_output_host(const float* xa_host, int64_t n, int64_t 
 }
 
 // ---- encoder ------------------------------------------------------------------------------------
-// Plain (ungrouped) GEMM: tensor cores when the weights are TF32-exact; a_mut (== p.A) is overwritten by
-// its TF32 hi plane, lo_buf receives the lo plane.
+// Plain (ungrouped) GEMM on the tensor cores when the weights are TF32-exact.  p.A must already be the
+// TF32 hi plane and a_lo the lo plane (written by the producing kernel); fp32 CUDA-core GEMM otherwise.
 void Session::gemm(const GemmParams& p, float* a_mut, float* lo_buf) {
-    if (use_tc && p.groups == nullptr && p.lda == p.K && gemm_tc_supported(p)) {
-        launch_split_tf32(p.A, a_mut, lo_buf, (int64_t)p.max_rows * p.K, st);
-        GemmParams q = p;
-        q.A = a_mut;
-        launch_gemm_tc(q, lo_buf, 0, p.max_rows, st);
-    } else {
-        launch_gemm(p, st);
-    }
+    (void)a_mut;
+    if (use_tc && p.groups == nullptr && p.lda == p.K && gemm_tc_supported(p)) launch_gemm_tc(p, lo_buf, 0, p.max_rows, st);
+    else launch_gemm(p, st);
 }
 
 void Session::run_encoder() {
@@ -236,45 +235,74 @@ void Session::run_encoder() {
     const int d = D.n_audio_state;
     const int M = (int)M_tot;
     const float qk_scale = (float)std::pow((double)d / (double)D.n_audio_head, -0.25);   // mod.rs:503
+    const bool tc = use_tc;
+    // lo planes (tensor-core path): lo_a = [M][4d] scratch shared by xn / att / hid; conv inputs have their own
+    float* lo = tc ? lo_a.p : nullptr;
     // halo rows of the conv1 output must read as zero padding
     WB_CUDA(cudaMemsetAsync(h1.p, 0, (size_t)n_windows * TmS * d * sizeof(float), st));
     GemmParams p;
-    // conv1 + GELU (mod.rs:243): K = 3*80 over three consecutive token-major mel rows
-    p = GemmParams{};
-    p.A = mel_rows.p; p.lda = N_MELS; p.B = m->conv1.w32; p.C = h1.p; p.ldc = d; p.N = d; p.K = 3 * N_MELS;
-    p.bias = m->conv1.b; p.act = ACT_GELU; p.groups = d_g1.p; p.n_groups = n_windows; p.max_rows = max_Tm;
-    launch_gemm(p, st);
-    // conv2 (stride 2) + GELU + transpose + positional embedding (mod.rs:244-252)
-    p = GemmParams{};
-    p.A = h1.p; p.lda = 2 * d; p.B = m->conv2.w32; p.C = x.p; p.ldc = d; p.N = d; p.K = 3 * d;
-    p.bias = m->conv2.b; p.act = ACT_GELU; p.pos = m->enc_pos; p.groups = d_g2.p; p.n_groups = n_windows;
-    p.max_rows = max_T;
-    launch_gemm(p, st);
+    // conv1 + GELU (mod.rs:243): K = 3*80 over three consecutive token-major mel rows; a conv output row is a
+    // dot product with ONE contiguous 240-vector, so the conv is a GEMM whose A rows overlap (lda = 80 < K)
+    bool conv_tc = tc && conv_tc_ok;
+    if (conv_tc) {
+        try {
+            launch_split_tf32(mel_rows.p, mel_hi.p, mel_lo.p, (int64_t)n_windows * TmS * N_MELS, st);
+            WB_CUDA(cudaMemsetAsync(h1_lo.p, 0, (size_t)n_windows * TmS * d * sizeof(float), st));
+            p = GemmParams{};
+            p.A = mel_hi.p; p.lda = N_MELS; p.B = m->conv1.w32; p.C = h1.p; p.C_lo = h1_lo.p; p.ldc = d; p.N = d; p.K = 3 * N_MELS;
+            p.bias = m->conv1.b; p.act = ACT_GELU; p.groups = d_g1.p; p.n_groups = n_windows; p.max_rows = max_Tm;
+            launch_gemm_tc(p, mel_lo.p, (int64_t)TmS * N_MELS, TmS - 2, st);
+            p = GemmParams{};
+            p.A = h1.p; p.lda = 2 * d; p.B = m->conv2.w32; p.C = x.p; p.ldc = d; p.N = d; p.K = 3 * d;
+            p.bias = m->conv2.b; p.act = ACT_GELU; p.pos = m->enc_pos; p.groups = d_g2.p; p.n_groups = n_windows;
+            p.max_rows = max_T;
+            launch_gemm_tc(p, h1_lo.p, (int64_t)TmS * d, Tcap, st);
+        } catch (const Error& e) {
+            if (e.code != WB_ERR_UNSUPPORTED) throw;
+            conv_tc_ok = false;   // the driver refused the overlapping-row tensor map: CUDA-core path from now on
+            conv_tc = false;
+        }
+    }
+    if (!conv_tc) {
+        p = GemmParams{};
+        p.A = mel_rows.p; p.lda = N_MELS; p.B = m->conv1.w32; p.C = h1.p; p.ldc = d; p.N = d; p.K = 3 * N_MELS;
+        p.bias = m->conv1.b; p.act = ACT_GELU; p.groups = d_g1.p; p.n_groups = n_windows; p.max_rows = max_Tm;
+        launch_gemm(p, st);
+        // conv2 (stride 2) + GELU + transpose + positional embedding (mod.rs:244-252)
+        p = GemmParams{};
+        p.A = h1.p; p.lda = 2 * d; p.B = m->conv2.w32; p.C = x.p; p.ldc = d; p.N = d; p.K = 3 * d;
+        p.bias = m->conv2.b; p.act = ACT_GELU; p.pos = m->enc_pos; p.groups = d_g2.p; p.n_groups = n_windows;
+        p.max_rows = max_T;
+        launch_gemm(p, st);
+    }
     for (int l = 0; l < D.n_audio_layer; ++l) {
         const EncBlockW& B = m->enc[(size_t)l];
-        // x = x + attn(attn_ln(x))   (mod.rs:300)
-        launch_layernorm(x.p, xn.p, B.attn_ln, M, d, m->ln_eps_outside, st);
+        // x = x + attn(attn_ln(x))   (mod.rs:300); LayerNorm writes the TF32 hi/lo planes the GEMM consumes
+        launch_layernorm(x.p, xn.p, lo, B.attn_ln, M, d, m->ln_eps_outside, st);
         p = GemmParams{};
         p.A = xn.p; p.lda = d; p.B = B.qkv.w32; p.C = qkv.p; p.ldc = 3 * d; p.N = 3 * d; p.K = d;
         p.bias = B.qkv.b; p.scale = qk_scale; p.scale_cols = 2 * d; p.max_rows = M;
-        gemm(p, xn.p, lo_a.p);
-        launch_encoder_attention(qkv.p, att.p, d_awin.p, n_windows, max_T, d, D.n_audio_head, st);
+        gemm(p, xn.p, lo);
+        launch_encoder_attention(qkv.p, att.p, lo, d_awin.p, n_windows, max_T, d, D.n_audio_head, st);
         p = GemmParams{};
         p.A = att.p; p.lda = d; p.B = B.out.w32; p.C = x.p; p.ldc = d; p.N = d; p.K = d;
         p.bias = B.out.b; p.residual = x.p; p.max_rows = M;
-        gemm(p, att.p, lo_a.p);
-        // x = x + mlp(mlp_ln(x))     (mod.rs:301)
-        launch_layernorm(x.p, xn.p, B.mlp_ln, M, d, m->ln_eps_outside, st);
+        gemm(p, att.p, lo);
+        // x = x + mlp(mlp_ln(x))     (mod.rs:301); the MLP1 epilogue (bias + GELU) emits hid as hi/lo planes
+        launch_layernorm(x.p, xn.p, lo, B.mlp_ln, M, d, m->ln_eps_outside, st);
         p = GemmParams{};
         p.A = xn.p; p.lda = d; p.B = B.mlp1.w32; p.C = hid.p; p.ldc = 4 * d; p.N = 4 * d; p.K = d;
         p.bias = B.mlp1.b; p.act = ACT_GELU; p.max_rows = M;
-        gemm(p, xn.p, lo_a.p);
+        const bool mlp_tc = tc && gemm_tc_supported(p);
+        if (mlp_tc) p.C_lo = lo_b4.p;
+        gemm(p, xn.p, lo);
         p = GemmParams{};
         p.A = hid.p; p.lda = 4 * d; p.B = B.mlp2.w32; p.C = x.p; p.ldc = d; p.N = d; p.K = 4 * d;
         p.bias = B.mlp2.b; p.residual = x.p; p.max_rows = M;
-        gemm(p, hid.p, lo_a.p);
+        if (mlp_tc) gemm(p, hid.p, lo_b4.p);
+        else launch_gemm(p, st);
     }
-    launch_layernorm(x.p, xa.p, m->ln_post, M, d, m->ln_eps_outside, st);   // mod.rs:259
+    launch_layernorm(x.p, xa.p, nullptr, m->ln_post, M, d, m->ln_eps_outside, st);   // mod.rs:259
     run_cross_kv();
     encoded = true;
 }

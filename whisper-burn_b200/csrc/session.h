@@ -38,7 +38,8 @@ struct Session {
     DevBuf<float> wave;
     DevBuf<int> max_slots;
     DevBuf<float> mel_rows, h1, x, xn, att, qkv, hid, xa;
-    DevBuf<float> lo_a, lo_b, xa_hi;   // TF32 lo planes of the GEMM inputs (tensor-core path)
+    DevBuf<float> lo_a, lo_b, lo_b4, xa_hi, mel_hi, mel_lo, h1_lo;   // TF32 planes of the GEMM inputs (tensor-core path)
+    bool conv_tc_ok = true;            // cleared if the driver rejects the overlapping-row tensor maps of the conv stems
     bool use_tc = true;                // WB200_GEMM=simt forces the fp32 CUDA-core GEMM
     void gemm(const GemmParams& p, float* a_mut, float* lo_buf);   // tensor-core when possible
     DevBuf<float> ckv;     // [L][Mcap][2d]  cross keys (scaled) | values, projected once per window

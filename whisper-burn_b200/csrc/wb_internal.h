@@ -156,6 +156,7 @@ struct GemmParams {
     const float* B = nullptr;      // [N][K]
     float* C = nullptr;
     __half* C16 = nullptr;         // optional: store fp16-rounded results here instead of C (fp16 K/V cache)
+    float* C_lo = nullptr;         // optional (tensor-core path): C gets the TF32 hi plane, C_lo the lo plane
     int64_t ldc = 0;
     int N = 0, K = 0;
     const float* bias = nullptr;   // [N] or null
@@ -191,14 +192,15 @@ void launch_rows_to_chan(const float* rows, float* chan, int n_frames, cudaStrea
 void launch_chan_to_rows(const float* chan, float* rows, int n_frames, int64_t chan_stride, cudaStream_t st);
 
 // ---- encoder pieces (encoder.cu) -----------------------------------------------------------------
-void launch_layernorm(const float* x, float* y, const LayerNormW& ln, int rows, int d, int eps_outside,
+// y_lo != null: y receives the TF32 hi plane of LayerNorm(x) and y_lo the lo plane (prologue of a tensor-core GEMM)
+void launch_layernorm(const float* x, float* y, float* y_lo, const LayerNormW& ln, int rows, int d, int eps_outside,
                       cudaStream_t st);
 struct AttnWindow {
     int64_t row_off;   // first packed row of the window
     int T;
 };
 // non-causal multi-head attention over packed rows; qkv [rows][3d] (q,k pre-scaled), out [rows][d]
-void launch_encoder_attention(const float* qkv, float* out, const AttnWindow* win_dev, int n_windows, int max_T,
+void launch_encoder_attention(const float* qkv, float* out, float* out_lo, const AttnWindow* win_dev, int n_windows, int max_T,
                               int d, int n_head, cudaStream_t st);
 
 }  // namespace wb
