@@ -1,0 +1,486 @@
+// Device helpers shared by the persistent decoders (decoder3.cu: grid-barrier version, decoder4.cu:
+// cluster / DSMEM version).  Internal; everything lives in an anonymous namespace of the including TU.
+#pragma once
+#include <algorithm>
+#include <type_traits>
+#include <cfloat>
+#include <climits>
+
+#include "decoder.h"
+#include "wb_internal.h"
+
+namespace wb {
+
+namespace {
+
+constexpr int NT = 256;
+constexpr int NW = 8;
+
+__device__ __forceinline__ float gelu_erf(float x) {
+    const float t = __fadd_rn(erff(__fdiv_rn(x, 1.41421356237309504880f)), 1.0f);
+    return __fdiv_rn(__fmul_rn(x, t), 2.0f);
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ void cvt8(const uint4& u, float (&w)[8]) {
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(h[i]);
+        w[2 * i] = f.x;
+        w[2 * i + 1] = f.y;
+    }
+}
+__device__ __forceinline__ unsigned int ld_acquire(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// optional stage trace (CTA 0, thread 0): pairs of (stage end, barrier end) nanosecond stamps
+#define WB_TRACE()                                                                          \
+    do {                                                                                    \
+        if (a.trace && blockIdx.x == 0 && threadIdx.x == 0 && tr_n < a.trace_cap) a.trace[tr_n++] = gtime(); \
+    } while (0)
+
+// Grid barrier on a monotonic counter (zeroed by the host before the launch): arrive with a one-way
+// red.release (no returned value to wait for), then poll until all CTAs of this round have arrived.
+// All CTAs are co-resident (cooperative launch).  `gen` counts the barriers this CTA has passed.
+__device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int& gen) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ++gen;
+        const unsigned int target = gen * gridDim.x;
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+        long long t0 = clock64();
+        while (ld_acquire(bar) < target) {
+            if (clock64() - t0 > 4000000000LL) __trap();   // ~2 s: fail loudly instead of hanging the GPU
+        }
+    }
+    __syncthreads();
+}
+
+// ---- input staging ---------------------------------------------------------------------------------
+// LayerNorm (burn 0.9 form, see encoder.cu) of rows [r0, r0+RC) of src (L2) into xs[RC][d]; warp per row.
+// The row is fetched with ONE batch of independent 16-byte loads (d <= 1280 -> <= 10 per lane) and stays in
+// registers through mean / variance / normalisation: a single L2 round trip per stage.
+constexpr int LN_V4 = 10;
+template <int RC>
+__device__ __forceinline__ void stage_ln(const float* src, int r0, int R, int d, const float* __restrict__ g,
+                                         const float* __restrict__ b, float eps, int eps_outside, float* xs) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nv = d / 4;
+    for (int rr = warp; rr < RC; rr += NW) {
+        float4* xr = reinterpret_cast<float4*>(xs + rr * d);
+        const int r = r0 + rr;
+        if (r >= R) {
+            for (int c = lane; c < nv; c += 32) xr[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            continue;
+        }
+        const float4* s4 = reinterpret_cast<const float4*>(src + (int64_t)r * d);
+        float4 v[LN_V4];
+#pragma unroll
+        for (int i = 0; i < LN_V4; ++i) {
+            const int c = i * 32 + lane;
+            v[i] = c < nv ? __ldcg(s4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float sum = 0.0f;
+#pragma unroll
+        for (int i = 0; i < LN_V4; ++i) sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        sum = warp_sum(sum);
+        const float mean = __fdiv_rn(sum, (float)d);
+        float q = 0.0f;
+#pragma unroll
+        for (int i = 0; i < LN_V4; ++i) {
+            const int c = i * 32 + lane;
+            if (c < nv) {
+                v[i].x = __fsub_rn(v[i].x, mean); v[i].y = __fsub_rn(v[i].y, mean);
+                v[i].z = __fsub_rn(v[i].z, mean); v[i].w = __fsub_rn(v[i].w, mean);
+                q = __fadd_rn(q, __fmul_rn(v[i].x, v[i].x)); q = __fadd_rn(q, __fmul_rn(v[i].y, v[i].y));
+                q = __fadd_rn(q, __fmul_rn(v[i].z, v[i].z)); q = __fadd_rn(q, __fmul_rn(v[i].w, v[i].w));
+            }
+        }
+        q = warp_sum(q);
+        const float var = __fdiv_rn(q, (float)d);
+        const float den = eps_outside ? __fadd_rn(__fsqrt_rn(var), eps) : __fsqrt_rn(__fadd_rn(var, eps));
+#pragma unroll
+        for (int i = 0; i < LN_V4; ++i) {
+            const int c = i * 32 + lane;
+            if (c < nv) {
+                const float4 g4 = __ldg(reinterpret_cast<const float4*>(g) + c);
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(b) + c);
+                float4 o;
+                o.x = __fadd_rn(__fmul_rn(__fdiv_rn(v[i].x, den), g4.x), b4.x);
+                o.y = __fadd_rn(__fmul_rn(__fdiv_rn(v[i].y, den), g4.y), b4.y);
+                o.z = __fadd_rn(__fmul_rn(__fdiv_rn(v[i].z, den), g4.z), b4.z);
+                o.w = __fadd_rn(__fmul_rn(__fdiv_rn(v[i].w, den), g4.w), b4.w);
+                xr[c] = o;
+            }
+        }
+    }
+}
+
+// same LayerNorm, source rows already in shared memory (src_s[rr][d])
+template <int RC>
+__device__ __forceinline__ void stage_ln_smem(const float* src_s, int r0, int R, int d, const float* __restrict__ g,
+                                              const float* __restrict__ b, float eps, int eps_outside, float* xs) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int rr = warp; rr < RC; rr += NW) {
+        float* xr = xs + rr * d;
+        if (r0 + rr >= R) {
+            for (int c = lane; c < d; c += 32) xr[c] = 0.0f;
+            continue;
+        }
+        const float* s = src_s + rr * d;
+        float sum = 0.0f;
+        for (int c = lane; c < d; c += 32) sum += s[c];
+        sum = warp_sum(sum);
+        const float mean = __fdiv_rn(sum, (float)d);
+        float q = 0.0f;
+        for (int c = lane; c < d; c += 32) {
+            const float dv = __fsub_rn(s[c], mean);
+            q = __fadd_rn(q, __fmul_rn(dv, dv));
+        }
+        q = warp_sum(q);
+        const float var = __fdiv_rn(q, (float)d);
+        const float den = eps_outside ? __fadd_rn(__fsqrt_rn(var), eps) : __fsqrt_rn(__fadd_rn(var, eps));
+        for (int c = lane; c < d; c += 32)
+            xr[c] = __fadd_rn(__fmul_rn(__fdiv_rn(__fsub_rn(s[c], mean), den), __ldg(g + c)), __ldg(b + c));
+    }
+}
+
+// copies rows [r0, r0+RC) of src[R][K] (L2) into xs[RC][K]; 8 independent 16-byte loads per thread in flight
+template <int RC>
+__device__ __forceinline__ void stage_copy(const float* src, int r0, int R, int K, float* xs) {
+    const int n4 = RC * K / 4;
+    for (int i0 = threadIdx.x; i0 < n4; i0 += NT * 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * NT;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < n4) {
+                const int rr = (i * 4) / K, c = (i * 4) % K;
+                if (r0 + rr < R) v[u] = __ldcg(reinterpret_cast<const float4*>(src + (int64_t)(r0 + rr) * K + c));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * NT;
+            if (i < n4) *reinterpret_cast<float4*>(xs + (int64_t)i * 4) = v[u];
+        }
+    }
+}
+
+// ---- weight-slice GEMV --------------------------------------------------------------------------------
+// Every warp of the grid owns output features n = gw, gw + n_warps, ...; two features are in flight.
+// emit(n, rr, value) is called by lane 0 semantics-free (all lanes hold the sums; lane rr handles row rr).
+template <int RC>
+__device__ __forceinline__ float dot8_acc(const float (&w)[8], const float* xs, float acc) {
+    const float4 x0 = *reinterpret_cast<const float4*>(xs);
+    const float4 x1 = *reinterpret_cast<const float4*>(xs + 4);
+    acc = fmaf(w[0], x0.x, acc); acc = fmaf(w[1], x0.y, acc); acc = fmaf(w[2], x0.z, acc); acc = fmaf(w[3], x0.w, acc);
+    acc = fmaf(w[4], x1.x, acc); acc = fmaf(w[5], x1.y, acc); acc = fmaf(w[6], x1.z, acc); acc = fmaf(w[7], x1.w, acc);
+    return acc;
+}
+
+// dots of G weight rows (K elements each, full warp per row, lane-strided 16-byte vectors) with the RC
+// staged rows; all G rows' loads are issued before any is consumed; results in all lanes.
+template <typename WT, int RC, int G>
+__device__ __forceinline__ void rows_dot(const WT* (&wrow)[G], int K, const float* xs, float (&acc)[G][RC]) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int rr = 0; rr < RC; ++rr) acc[g][rr] = 0.0f;
+    const int nv = K / 8;
+    constexpr int U = (sizeof(WT) == 2) ? (G == 1 ? 6 : 3) : (G == 1 ? 3 : 2);   // vectors per lane and row in flight
+    for (int v0 = 0; v0 < nv; v0 += 32 * U) {
+        if constexpr (sizeof(WT) == 2) {
+            uint4 raw[G][U];
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+#pragma unroll
+                for (int i = 0; i < U; ++i) {
+                    const int v = v0 + i * 32 + lane;
+                    raw[g][i] = v < nv ? __ldg(reinterpret_cast<const uint4*>(wrow[g]) + v) : make_uint4(0, 0, 0, 0);
+                }
+#pragma unroll
+            for (int i = 0; i < U; ++i) {
+                const int v = v0 + i * 32 + lane;
+                if (v < nv) {
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        float w[8];
+                        cvt8(raw[g][i], w);
+#pragma unroll
+                        for (int rr = 0; rr < RC; ++rr) acc[g][rr] = dot8_acc<RC>(w, xs + rr * K + v * 8, acc[g][rr]);
+                    }
+                }
+            }
+        } else {
+            float4 ra[G][U], rb[G][U];
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+#pragma unroll
+                for (int i = 0; i < U; ++i) {
+                    const int v = v0 + i * 32 + lane;
+                    if (v < nv) {
+                        ra[g][i] = __ldg(reinterpret_cast<const float4*>(wrow[g]) + 2 * v);
+                        rb[g][i] = __ldg(reinterpret_cast<const float4*>(wrow[g]) + 2 * v + 1);
+                    } else {
+                        ra[g][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        rb[g][i] = ra[g][i];
+                    }
+                }
+#pragma unroll
+            for (int i = 0; i < U; ++i) {
+                const int v = v0 + i * 32 + lane;
+                if (v < nv) {
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        const float w[8] = {ra[g][i].x, ra[g][i].y, ra[g][i].z, ra[g][i].w, rb[g][i].x, rb[g][i].y, rb[g][i].z, rb[g][i].w};
+#pragma unroll
+                        for (int rr = 0; rr < RC; ++rr) acc[g][rr] = dot8_acc<RC>(w, xs + rr * K + v * 8, acc[g][rr]);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int rr = 0; rr < RC; ++rr) acc[g][rr] = warp_sum(acc[g][rr]);
+}
+
+// Weight-slice GEMV phase: output features n = gw, gw + n_gw, ... two at a time; emit(n, acc[RC]) in all lanes.
+template <typename WT, int RC, typename Emit>
+__device__ __forceinline__ void gemv_phase(const WT* W, int N, int K, const float* xs, int gw, int n_gw, Emit&& emit) {
+    for (int n = gw; n < N; n += 2 * n_gw) {
+        const int n2 = n + n_gw;
+        if (n2 < N) {
+            const WT* rows[2] = {W + (int64_t)n * K, W + (int64_t)n2 * K};
+            float acc[2][RC];
+            rows_dot<WT, RC, 2>(rows, K, xs, acc);
+            emit(n, acc[0]);
+            emit(n2, acc[1]);
+        } else {
+            const WT* rows[1] = {W + (int64_t)n * K};
+            float acc[1][RC];
+            rows_dot<WT, RC, 1>(rows, K, xs, acc);
+            emit(n, acc[0]);
+        }
+    }
+}
+
+// 8 lanes per weight row: a warp instruction covers 4 consecutive rows, G such groups in flight; after the
+// call every lane of sub-group `sub` holds acc[g][rr] of row (g*4 + sub).  Used by the logits stage.
+template <typename WT, int RC, int G>
+__device__ __forceinline__ void dot_groups(const WT* (&wrow)[G], const float* xs, int K, float (&acc)[G][RC]) {
+    const int l = threadIdx.x & 7;
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int rr = 0; rr < RC; ++rr) acc[g][rr] = 0.0f;
+#pragma unroll 6
+    for (int k0 = l * 8; k0 < K; k0 += 64) {
+        float w[G][8];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            if constexpr (sizeof(WT) == 2) {
+                cvt8(__ldg(reinterpret_cast<const uint4*>(wrow[g] + k0)), w[g]);
+            } else {
+                const float4 a4 = __ldg(reinterpret_cast<const float4*>(wrow[g] + k0));
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(wrow[g] + k0) + 1);
+                w[g][0] = a4.x; w[g][1] = a4.y; w[g][2] = a4.z; w[g][3] = a4.w;
+                w[g][4] = b4.x; w[g][5] = b4.y; w[g][6] = b4.z; w[g][7] = b4.w;
+            }
+        }
+#pragma unroll
+        for (int rr = 0; rr < RC; ++rr)
+#pragma unroll
+            for (int g = 0; g < G; ++g) acc[g][rr] = dot8_acc<RC>(w[g], xs + rr * K + k0, acc[g][rr]);
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int rr = 0; rr < RC; ++rr) {
+            float v = acc[g][rr];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            acc[g][rr] = v;
+        }
+}
+
+template <int RC>
+__device__ __forceinline__ float pick_row(const float (&acc)[RC], int rr) {
+    float v = acc[0];
+#pragma unroll
+    for (int i = 1; i < RC; ++i) v = (rr == i) ? acc[i] : v;
+    return v;
+}
+
+// ---- attention of one query row over keys, one warp, 4 lanes per key, online softmax ------------------
+struct AttnAcc {
+    float m, l, o[16];
+};
+template <typename KF, typename VF>
+__device__ __forceinline__ void attn_warp(const float* q_smem, int n_keys, int first, int stride, KF&& kptr, VF&& vptr,
+                                          AttnAcc& A) {
+    const int lane = threadIdx.x & 31, sub = lane >> 2, l4 = lane & 3;
+    float q[16];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float4 t = *reinterpret_cast<const float4*>(q_smem + l4 * 16 + c * 4);
+        q[c * 4] = t.x; q[c * 4 + 1] = t.y; q[c * 4 + 2] = t.z; q[c * 4 + 3] = t.w;
+    }
+    A.m = -INFINITY;
+    A.l = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) A.o[c] = 0.0f;
+    constexpr int UK = 2;
+    for (int jb = first; jb < n_keys; jb += stride * 8 * UK) {
+        float4 kk[UK][4], vv[UK][4];
+        bool ok[UK];
+        using KT = typename std::remove_cv<typename std::remove_pointer<decltype(kptr(0))>::type>::type;
+#pragma unroll
+        for (int u = 0; u < UK; ++u) {
+            const int j = jb + (u * 8 + sub) * stride;
+            ok[u] = j < n_keys;
+            if (ok[u]) {
+                if constexpr (sizeof(KT) == 4) {
+                    const float4* kp = reinterpret_cast<const float4*>(kptr(j)) + l4 * 4;
+                    const float4* vp = reinterpret_cast<const float4*>(vptr(j)) + l4 * 4;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) { kk[u][c] = __ldcg(kp + c); vv[u][c] = __ldcg(vp + c); }
+                } else {   // fp16 cache: 16 dims = 32 bytes = two 16-byte loads
+                    const uint4* kp = reinterpret_cast<const uint4*>(kptr(j)) + l4 * 2;
+                    const uint4* vp = reinterpret_cast<const uint4*>(vptr(j)) + l4 * 2;
+                    uint4 kr[2], vr[2];
+                    kr[0] = __ldcg(kp); kr[1] = __ldcg(kp + 1); vr[0] = __ldcg(vp); vr[1] = __ldcg(vp + 1);
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        float w[8];
+                        cvt8(kr[c], w);
+                        kk[u][2 * c] = make_float4(w[0], w[1], w[2], w[3]); kk[u][2 * c + 1] = make_float4(w[4], w[5], w[6], w[7]);
+                        cvt8(vr[c], w);
+                        vv[u][2 * c] = make_float4(w[0], w[1], w[2], w[3]); vv[u][2 * c + 1] = make_float4(w[4], w[5], w[6], w[7]);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { kk[u][c] = make_float4(0.f, 0.f, 0.f, 0.f); vv[u][c] = kk[u][c]; }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UK; ++u) {
+            float s = 0.0f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                s = fmaf(q[c * 4], kk[u][c].x, s); s = fmaf(q[c * 4 + 1], kk[u][c].y, s);
+                s = fmaf(q[c * 4 + 2], kk[u][c].z, s); s = fmaf(q[c * 4 + 3], kk[u][c].w, s);
+            }
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            if (ok[u]) {
+                const float mn = fmaxf(A.m, s);
+                const float corr = expf(A.m - mn);
+                const float e = expf(s - mn);
+                A.l = A.l * corr + e;
+                A.m = mn;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    A.o[c * 4] = fmaf(e, vv[u][c].x, A.o[c * 4] * corr);
+                    A.o[c * 4 + 1] = fmaf(e, vv[u][c].y, A.o[c * 4 + 1] * corr);
+                    A.o[c * 4 + 2] = fmaf(e, vv[u][c].z, A.o[c * 4 + 2] * corr);
+                    A.o[c * 4 + 3] = fmaf(e, vv[u][c].w, A.o[c * 4 + 3] * corr);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 4; off < 32; off <<= 1) {   // merge the 8 key sub-groups
+        const float m2 = __shfl_xor_sync(0xffffffffu, A.m, off);
+        const float l2 = __shfl_xor_sync(0xffffffffu, A.l, off);
+        const float mn = fmaxf(A.m, m2);
+        const float c1 = A.m > -INFINITY ? expf(A.m - mn) : 0.0f;
+        const float c2 = m2 > -INFINITY ? expf(m2 - mn) : 0.0f;
+        A.l = A.l * c1 + l2 * c2;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const float o2 = __shfl_xor_sync(0xffffffffu, A.o[c], off);
+            A.o[c] = A.o[c] * c1 + o2 * c2;
+        }
+        A.m = mn;
+    }
+}
+
+// one (query row, head) unit handled by the 8 warps of a CTA (keys strided over warps); returns the merged
+// (M, L) and the unnormalised output in out[64] (shared memory), valid after the trailing __syncthreads().
+template <typename KF, typename VF>
+__device__ __forceinline__ void attn_cta(const float* q_smem, int n_keys, KF&& kptr, VF&& vptr, float* wm, float* wl,
+                                         float* wo, float* out, float* ML) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    AttnAcc A;
+    attn_warp(q_smem, n_keys, warp, NW, kptr, vptr, A);
+    if (lane < 4) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) wo[warp * 64 + lane * 16 + c] = A.o[c];
+    }
+    if (lane == 0) { wm[warp] = A.m; wl[warp] = A.l; }
+    __syncthreads();
+    if (tid < 64) {
+        float M = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) M = fmaxf(M, wm[w]);
+        float L = 0.0f, o = 0.0f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            const float m = wm[w];
+            const float sc = m > -INFINITY ? expf(m - M) : 0.0f;
+            L += sc * wl[w];
+            o += sc * wo[w * 64 + tid];
+        }
+        out[tid] = o;
+        if (tid == 0) { ML[0] = M; ML[1] = L; }
+    }
+    __syncthreads();
+}
+
+// ---- top candidates --------------------------------------------------------------------------------------
+template <int KC>
+struct Cand {
+    float v[KC];
+    int i[KC];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int k = 0; k < KC; ++k) { v[k] = -INFINITY; i[k] = INT_MAX; }
+    }
+    __device__ __forceinline__ void push(float val, int idx) {   // keep the KC best by (value desc, index asc)
+        if (!(val > v[KC - 1] || (val == v[KC - 1] && idx < i[KC - 1]))) return;
+        v[KC - 1] = val;
+        i[KC - 1] = idx;
+#pragma unroll
+        for (int k = KC - 1; k > 0; --k) {
+            const bool better = v[k] > v[k - 1] || (v[k] == v[k - 1] && i[k] < i[k - 1]);
+            if (better) {
+                const float tv = v[k]; v[k] = v[k - 1]; v[k - 1] = tv;
+                const int ti = i[k]; i[k] = i[k - 1]; i[k - 1] = ti;
+            }
+        }
+    }
+};
+
+
+}  // namespace
+
+}  // namespace wb

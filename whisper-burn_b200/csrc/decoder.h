@@ -227,6 +227,8 @@ struct Dec3Args {
     int trace_cap = 0;
 };
 void launch_dec3(const Dec3Args& a, int n_ctas, bool w_half, cudaStream_t st);
+// cluster / DSMEM version (decoder4.cu); returns false when the configuration is not covered
+bool launch_dec4(const Dec3Args& a, bool w_half, cudaStream_t st);
 
 void launch_dec2_self(const Dec2SelfArgs& a, int H, bool w_half, cudaStream_t st);
 void launch_dec2_cross(const Dec2CrossArgs& a, int H, int S, bool w_half, cudaStream_t st);

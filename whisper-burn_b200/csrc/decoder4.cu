@@ -1,0 +1,532 @@
+// Cluster / DSMEM persistent decoder for small batches (R <= 8 rows, d <= 512: tiny / base) on sm_100a.
+//
+// Same math and same single-launch structure as decoder3.cu (prefill + every greedy step in one kernel), but
+// the per-layer stage chain no longer crosses the chip: ONE 16-CTA thread-block cluster owns one batch row.
+//   * activations (q|k|v, attention output, out-projection deltas, MLP hidden) are exchanged by DSMEM
+//     broadcast -- the producing warp stores each value into the same shared-memory slot of all 16 CTAs --
+//     so every stage reads its input from LOCAL shared memory;
+//   * stages are separated by the hardware cluster barrier (barrier.cluster arrive.release / wait.acquire,
+//     ~0.2 us) instead of the 1.3 us grid barrier through L2 (decoder3.cu: 34 per step);
+//   * the weight rows a warp needs for the NEXT stage are loaded into registers BEFORE the barrier (they do
+//     not depend on activations), so after the barrier a stage is LayerNorm + FMAs on on-chip data;
+//   * every CTA keeps its own copy of the row's residual stream x and applies the broadcast deltas itself.
+// Only the vocabulary projection is chip-wide: x rows are published, a grid barrier, all 128 CTAs stream the
+// tied-embedding matrix (fused mask / online softmax / top candidates), a grid barrier, one CTA per row
+// finishes (log-softmax of the candidates, token, EOT), a grid barrier.  3 grid + 32 cluster barriers / step.
+// Reference math: see decoder3.cu.  Greedy path only (beam steps use decoder3.cu).
+#include <cooperative_groups.h>
+
+#include "dec_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace wb {
+
+namespace {
+
+constexpr int CS = 16;   // CTAs per cluster
+
+template <int NR, int VPL>
+struct RowRegs {
+    uint4 v[NR][VPL];
+};
+
+// rows row0, row0 + step, ... of W[.][K] (fp16) -> registers; lane-strided 16-byte vectors
+template <int NR, int VPL>
+__device__ __forceinline__ void load_rows(const __half* __restrict__ W, int K, int row0, int step, RowRegs<NR, VPL>& r) {
+    const int lane = threadIdx.x & 31, nv = K / 8;
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+        const uint4* p = reinterpret_cast<const uint4*>(W + (int64_t)(row0 + i * step) * K);
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+            const int v = j * 32 + lane;
+            r.v[i][j] = v < nv ? __ldg(p + v) : make_uint4(0, 0, 0, 0);
+        }
+    }
+}
+// acc[i] = <row i, xs> (all lanes)
+template <int NR, int VPL>
+__device__ __forceinline__ void dot_rows1(const RowRegs<NR, VPL>& r, const float* xs, int K, float (&acc)[NR]) {
+    const int lane = threadIdx.x & 31, nv = K / 8;
+#pragma unroll
+    for (int i = 0; i < NR; ++i) acc[i] = 0.0f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+        const int v = j * 32 + lane;
+        if (v < nv) {
+            const float4 x0 = *reinterpret_cast<const float4*>(xs + v * 8);
+            const float4 x1 = *reinterpret_cast<const float4*>(xs + v * 8 + 4);
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+                float w[8];
+                cvt8(r.v[i][j], w);
+                float a = acc[i];
+                a = fmaf(w[0], x0.x, a); a = fmaf(w[1], x0.y, a); a = fmaf(w[2], x0.z, a); a = fmaf(w[3], x0.w, a);
+                a = fmaf(w[4], x1.x, a); a = fmaf(w[5], x1.y, a); a = fmaf(w[6], x1.z, a); a = fmaf(w[7], x1.w, a);
+                acc[i] = a;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NR; ++i) acc[i] = warp_sum(acc[i]);
+}
+
+// store v into the same shared-memory slot of every CTA of the cluster (lane r -> rank r)
+__device__ __forceinline__ void bcast(cg::cluster_group& cl, float* local, float v) {
+    const int lane = threadIdx.x & 31;
+    if (lane < CS) *cl.map_shared_rank(local, lane) = v;
+}
+
+// LayerNorm of one row held in shared memory (burn 0.9 form), by warp 0; others wait at the caller's barrier
+__device__ __forceinline__ void ln_row(const float* x_s, float* out_s, int d, const float* __restrict__ g,
+                                       const float* __restrict__ b, float eps, int eps_outside) {
+    const int lane = threadIdx.x & 31;
+    if ((threadIdx.x >> 5) != 0) return;
+    float s = 0.0f;
+    for (int c = lane; c < d; c += 32) s += x_s[c];
+    s = warp_sum(s);
+    const float mean = __fdiv_rn(s, (float)d);
+    float q = 0.0f;
+    for (int c = lane; c < d; c += 32) {
+        const float dv = __fsub_rn(x_s[c], mean);
+        q = __fadd_rn(q, __fmul_rn(dv, dv));
+    }
+    q = warp_sum(q);
+    const float var = __fdiv_rn(q, (float)d);
+    const float den = eps_outside ? __fadd_rn(__fsqrt_rn(var), eps) : __fsqrt_rn(__fadd_rn(var, eps));
+    for (int c = lane; c < d; c += 32)
+        out_s[c] = __fadd_rn(__fmul_rn(__fdiv_rn(__fsub_rn(x_s[c], mean), den), __ldg(g + c)), __ldg(b + c));
+}
+
+template <int D, int RC, typename KVT>
+__global__ void __launch_bounds__(NT, 1)
+dec4_kernel(const Dec3Args a) {
+    extern __shared__ __align__(16) float sm[];
+    cg::cluster_group cl = cg::this_cluster();
+    constexpr int H = D / 64;
+    constexpr int VPL = (D / 8 + 31) / 32;        // vectors per lane for K = D
+    constexpr int VPL4 = (4 * D / 8 + 31) / 32;   // K = 4D
+    constexpr int NR_QKV = 3 * D / (CS * NW), NR_D = D / (CS * NW), NR_H = 4 * D / (CS * NW);
+    constexpr int KC = 2;
+    const int L = a.L, V = a.V, R = a.R, t_max = a.t_max;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int rank = (int)cl.block_rank();
+    const int row = blockIdx.x / CS;              // batch row of this cluster
+    const bool active = row < R;
+    const int gw = blockIdx.x * NW + warp, n_gw = gridDim.x * NW;
+
+    float* x_s = sm;                  // [D]   residual stream (own copy)
+    float* xn_s = x_s + D;            // [D]   LayerNorm output
+    float* qkv_s = xn_s + D;          // [3D]  q | k | v of the current position
+    float* att_s = qkv_s + 3 * D;     // [D]   attention output (self, then merged cross)
+    float* dl_s = att_s + D;          // [D]   out-projection / MLP2 output incl. bias ("delta" for x)
+    float* q2_s = dl_s + D;           // [D]   cross query
+    float* hid_s = q2_s + D;          // [4D]
+    float* part_s = hid_s + 4 * D;    // [CS][68] cross partials: M, L, -, -, o[64]
+    float* wm = part_s + CS * 68;     // [NW]
+    float* wl = wm + NW;              // [NW]
+    float* wo = wl + NW;              // [NW][64]
+    float* ao = wo + NW * 64;         // [64]
+    float* ML = ao + 64;              // [2]
+    float* xs = ML + 4;               // logits stage: [RC][D] LayerNorm rows, then merge scratch
+    float* red = xs + RC * D;         // [NW*4][RC][2 + 2*KC]
+    unsigned int gen = 0;
+    const float scale = a.qk_scale;
+
+    const __half* nullw = nullptr;
+    (void)nullw;
+    for (int step = 0; step < a.n_steps; ++step) {
+        const int p = a.pos0 + step;
+        const bool want_logits = p >= a.logits_from;
+        if (active) {
+            // ---- embed (mod.rs:141-146): every CTA of the cluster builds its own copy of x
+            const int tok = __ldcg(a.tokens + (int64_t)row * t_max + p);
+            for (int c = tid; c < D; c += NT) x_s[c] = __fadd_rn(__ldg(a.tok_emb + (int64_t)tok * D + c), __ldg(a.pos_emb + (int64_t)p * D + c));
+            RowRegs<NR_QKV, VPL> w_qkv;
+            load_rows<NR_QKV, VPL>(reinterpret_cast<const __half*>(a.layers[0].Wqkv), D, rank * (3 * D / CS) + warp, NW, w_qkv);
+            __syncthreads();
+            for (int l = 0; l < L; ++l) {
+                const Dec3Layer& W = a.layers[l];
+                KVT* kcl = reinterpret_cast<KVT*>(a.kc) + (size_t)l * a.Rmax * t_max * D;
+                KVT* vcl = reinterpret_cast<KVT*>(a.vc) + (size_t)l * a.Rmax * t_max * D;
+                // ================= S1: q | k | v = LN1(x) Wqkv + b
+                if (l > 0) {
+                    for (int c = tid; c < D; c += NT) x_s[c] = __fadd_rn(x_s[c], dl_s[c]);   // MLP2 of the previous layer
+                    __syncthreads();
+                }
+                ln_row(x_s, xn_s, D, W.ln1_g, W.ln1_b, W.ln1_eps, a.eps_outside);
+                __syncthreads();
+                {
+                    float acc[NR_QKV];
+                    dot_rows1<NR_QKV, VPL>(w_qkv, xn_s, D, acc);
+#pragma unroll
+                    for (int i = 0; i < NR_QKV; ++i) {
+                        const int n = rank * (3 * D / CS) + warp + i * NW;
+                        float v = __fadd_rn(acc[i], __ldg(W.bqkv + n));
+                        if (n < 2 * D) v = __fmul_rn(v, scale);
+                        bcast(cl, qkv_s + n, v);
+                        if (lane == 0 && n >= D) {
+                            if (n < 2 * D) kcl[((int64_t)row * t_max + p) * D + (n - D)] = (KVT)v;
+                            else vcl[((int64_t)row * t_max + p) * D + (n - 2 * D)] = (KVT)v;
+                        }
+                    }
+                }
+                RowRegs<NR_D, VPL> w_o;
+                load_rows<NR_D, VPL>(reinterpret_cast<const __half*>(W.Wo), D, rank * (D / CS) + warp, NW, w_o);
+                cl.sync();
+                // ================= S2: self attention, head = rank (ranks >= H idle)
+                if (rank < H) {
+                    const int h = rank;
+                    const KVT* kb = kcl + h * 64;
+                    const KVT* vb = vcl + h * 64;
+                    auto kp = [&](int j) { return kb + ((int64_t)row * t_max + j) * D; };
+                    auto vp = [&](int j) { return vb + ((int64_t)row * t_max + j) * D; };
+                    attn_cta(qkv_s + h * 64, p + 1, kp, vp, wm, wl, wo, ao, ML);
+                    if (tid < 64) {
+                        const float v = __fdiv_rn(ao[tid], ML[1]);
+#pragma unroll
+                        for (int r2 = 0; r2 < CS; ++r2) *cl.map_shared_rank(att_s + h * 64 + tid, r2) = v;
+                    }
+                }
+                cl.sync();
+                // ================= S3: delta = att Wo + bo
+                {
+                    float acc[NR_D];
+                    dot_rows1<NR_D, VPL>(w_o, att_s, D, acc);
+#pragma unroll
+                    for (int i = 0; i < NR_D; ++i) {
+                        const int n = rank * (D / CS) + warp + i * NW;
+                        bcast(cl, dl_s + n, __fadd_rn(acc[i], __ldg(W.bo + n)));
+                    }
+                }
+                RowRegs<NR_D, VPL> w_cq;
+                load_rows<NR_D, VPL>(reinterpret_cast<const __half*>(W.Wcq), D, rank * (D / CS) + warp, NW, w_cq);
+                cl.sync();
+                // ================= S4: x += delta; cross query = LN2(x) Wcq + b
+                for (int c = tid; c < D; c += NT) x_s[c] = __fadd_rn(x_s[c], dl_s[c]);
+                __syncthreads();
+                ln_row(x_s, xn_s, D, W.ln2_g, W.ln2_b, W.ln2_eps, a.eps_outside);
+                __syncthreads();
+                {
+                    float acc[NR_D];
+                    dot_rows1<NR_D, VPL>(w_cq, xn_s, D, acc);
+#pragma unroll
+                    for (int i = 0; i < NR_D; ++i) {
+                        const int n = rank * (D / CS) + warp + i * NW;
+                        bcast(cl, q2_s + n, __fmul_rn(__fadd_rn(acc[i], __ldg(W.bcq + n)), scale));
+                    }
+                }
+                RowRegs<NR_D, VPL> w_co;
+                load_rows<NR_D, VPL>(reinterpret_cast<const __half*>(W.Wco), D, rank * (D / CS) + warp, NW, w_co);
+                cl.sync();
+                // ================= S5: cross attention; head = rank % H, the CTAs of a head split the keys
+                {
+                    const int h = rank % H, ci = rank / H;
+                    const int nch = (CS - h + H - 1) / H;              // CTAs working on head h
+                    const int w = __ldcg(a.row_window + row);
+                    const int T = a.win_T[w];
+                    const KVT* ckvl = reinterpret_cast<const KVT*>(a.ckv) + (size_t)l * a.Mcap * 2 * D;
+                    const KVT* kbase = ckvl + a.win_row_off[w] * (int64_t)(2 * D) + h * 64;
+                    const int64_t ld = 2 * (int64_t)D;
+                    auto kp = [&](int j) { return kbase + j * ld; };
+                    auto vp = [&](int j) { return kbase + j * ld + D; };
+                    // keys j == ci*NW + warp (mod nch*NW)
+                    AttnAcc A;
+                    attn_warp(q2_s + h * 64, T, ci * NW + warp, nch * NW, kp, vp, A);
+                    if (lane < 4) {
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) wo[warp * 64 + lane * 16 + c] = A.o[c];
+                    }
+                    if (lane == 0) { wm[warp] = A.m; wl[warp] = A.l; }
+                    __syncthreads();
+                    if (tid < 64) {
+                        float M = -INFINITY;
+#pragma unroll
+                        for (int w2 = 0; w2 < NW; ++w2) M = fmaxf(M, wm[w2]);
+                        float Ls = 0.0f, o = 0.0f;
+#pragma unroll
+                        for (int w2 = 0; w2 < NW; ++w2) {
+                            const float m = wm[w2];
+                            const float sc = m > -INFINITY ? expf(m - M) : 0.0f;
+                            Ls += sc * wl[w2];
+                            o += sc * wo[w2 * 64 + tid];
+                        }
+#pragma unroll
+                        for (int r2 = 0; r2 < CS; ++r2) {
+                            float* dst = cl.map_shared_rank(part_s + rank * 68, r2);
+                            dst[4 + tid] = o;
+                            if (tid == 0) { dst[0] = M; dst[1] = Ls; }
+                        }
+                    }
+                }
+                cl.sync();
+                // ================= S6: merge the head partials, delta = cross Wco + bco
+                for (int c = tid; c < D; c += NT) {
+                    const int h = c / 64;
+                    float M = -INFINITY;
+                    for (int k = h; k < CS; k += H) M = fmaxf(M, part_s[k * 68]);
+                    float den = 0.0f, num = 0.0f;
+                    for (int k = h; k < CS; k += H) {
+                        const float m = part_s[k * 68];
+                        const float wgt = m > -INFINITY ? expf(m - M) : 0.0f;
+                        den += wgt * part_s[k * 68 + 1];
+                        num += wgt * part_s[k * 68 + 4 + (c & 63)];
+                    }
+                    att_s[c] = __fdiv_rn(num, den);
+                }
+                __syncthreads();
+                {
+                    float acc[NR_D];
+                    dot_rows1<NR_D, VPL>(w_co, att_s, D, acc);
+#pragma unroll
+                    for (int i = 0; i < NR_D; ++i) {
+                        const int n = rank * (D / CS) + warp + i * NW;
+                        bcast(cl, dl_s + n, __fadd_rn(acc[i], __ldg(W.bco + n)));
+                    }
+                }
+                RowRegs<NR_H, VPL> w_1;
+                load_rows<NR_H, VPL>(reinterpret_cast<const __half*>(W.W1), D, rank * (4 * D / CS) + warp, NW, w_1);
+                cl.sync();
+                // ================= S7: x += delta; hid = gelu(LN3(x) W1 + b1)
+                for (int c = tid; c < D; c += NT) x_s[c] = __fadd_rn(x_s[c], dl_s[c]);
+                __syncthreads();
+                ln_row(x_s, xn_s, D, W.ln3_g, W.ln3_b, W.ln3_eps, a.eps_outside);
+                __syncthreads();
+                {
+                    float acc[NR_H];
+                    dot_rows1<NR_H, VPL>(w_1, xn_s, D, acc);
+#pragma unroll
+                    for (int i = 0; i < NR_H; ++i) {
+                        const int n = rank * (4 * D / CS) + warp + i * NW;
+                        bcast(cl, hid_s + n, gelu_erf(__fadd_rn(acc[i], __ldg(W.b1 + n))));
+                    }
+                }
+                RowRegs<NR_D, VPL4> w_2;
+                load_rows<NR_D, VPL4>(reinterpret_cast<const __half*>(W.W2), 4 * D, rank * (D / CS) + warp, NW, w_2);
+                cl.sync();
+                // ================= S8: delta = hid W2 + b2
+                {
+                    float acc[NR_D];
+                    dot_rows1<NR_D, VPL4>(w_2, hid_s, 4 * D, acc);
+#pragma unroll
+                    for (int i = 0; i < NR_D; ++i) {
+                        const int n = rank * (D / CS) + warp + i * NW;
+                        bcast(cl, dl_s + n, __fadd_rn(acc[i], __ldg(W.b2 + n)));
+                    }
+                }
+                if (l + 1 < L)
+                    load_rows<NR_QKV, VPL>(reinterpret_cast<const __half*>(a.layers[l + 1].Wqkv), D, rank * (3 * D / CS) + warp, NW, w_qkv);
+                cl.sync();
+            }
+            // final residual add; rank 0 publishes the row for the vocabulary projection
+            if (want_logits && rank == 0)
+                for (int c = tid; c < D; c += NT) a.x[(int64_t)row * D + c] = __fadd_rn(x_s[c], dl_s[c]);
+        }
+        if (!want_logits) continue;   // prefill positions: clusters stay independent, no chip-wide step
+        grid_sync(a.bar, gen);
+        // ================= logits (all CTAs): LN(x) tok_emb^T + mask + online softmax + candidates
+        {
+            const bool use_mask = a.is_special != nullptr && (a.mask_mode == 1 || (a.mask_mode == 2 && p + 1 <= 5));
+            const __half* E = reinterpret_cast<const __half*>(a.E);
+            const int sub = lane >> 3, l8 = lane & 7;
+            stage_ln<RC>(a.x, 0, R, D, a.lnf_g, a.lnf_b, a.lnf_eps, a.eps_outside, xs);
+            __syncthreads();
+            float m_run = -INFINITY, s_run = 0.0f;
+            Cand<KC> cand;
+            cand.init();
+            const int n_blk = (V + 7) / 8;
+            for (int blk = gw; blk < n_blk; blk += n_gw) {
+                const int n0 = blk * 8;
+                const __half* rows[2];
+                int nn[2];
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    nn[g] = n0 + g * 4 + sub;
+                    rows[g] = E + (int64_t)min(nn[g], V - 1) * D;
+                }
+                float acc[2][RC];
+                dot_groups<__half, RC, 2>(rows, xs, D, acc);
+                if (l8 < RC && l8 < R) {
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        if (nn[g] < V) {
+                            const float raw = pick_row<RC>(acc[g], l8);
+                            const float v = (use_mask && a.is_special[nn[g]]) ? __fadd_rn(raw, -INFINITY) : raw;
+                            if (v > -INFINITY) {
+                                if (v > m_run) { s_run = s_run * expf(m_run - v) + 1.0f; m_run = v; }
+                                else s_run += expf(v - m_run);
+                            }
+                            cand.push(v, nn[g]);
+                        }
+                    }
+                }
+            }
+            if (l8 < RC) {
+                float* rec = red + ((warp * 4 + sub) * RC + l8) * (2 + 2 * KC);
+                rec[0] = m_run;
+                rec[1] = s_run;
+#pragma unroll
+                for (int k = 0; k < KC; ++k) { rec[2 + k] = cand.v[k]; rec[2 + KC + k] = __int_as_float(cand.i[k]); }
+            }
+            __syncthreads();
+            if (tid < RC && tid < R) {
+                float M = -INFINITY;
+                for (int w2 = 0; w2 < NW * 4; ++w2) M = fmaxf(M, red[(w2 * RC + tid) * (2 + 2 * KC)]);
+                float Ssum = 0.0f;
+                Cand<KC> best;
+                best.init();
+                for (int w2 = 0; w2 < NW * 4; ++w2) {
+                    const float* rec = red + (w2 * RC + tid) * (2 + 2 * KC);
+                    if (rec[0] > -INFINITY) Ssum += rec[1] * expf(rec[0] - M);
+#pragma unroll
+                    for (int k = 0; k < KC; ++k) best.push(rec[2 + k], __float_as_int(rec[2 + KC + k]));
+                }
+                const int64_t o = (int64_t)blockIdx.x * R + tid;
+                a.lg_m[o] = M;
+                a.lg_s[o] = Ssum;
+#pragma unroll
+                for (int k = 0; k < KC; ++k) { a.lg_v[o * KC + k] = best.v[k]; a.lg_i[o * KC + k] = best.i[k]; }
+            }
+        }
+        grid_sync(a.bar, gen);
+        // ================= finish: one CTA per row (greedy: beam.rs:9-37 with beam_size 1)
+        for (int r = blockIdx.x; r < R; r += gridDim.x) {
+            float* s_f = wm;
+            int* s_i = reinterpret_cast<int*>(wl);
+            const int NP = gridDim.x;
+            float mx = -INFINITY;
+            for (int c = tid; c < NP; c += NT) mx = fmaxf(mx, __ldcg(a.lg_m + (int64_t)c * R + r));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            if (lane == 0) s_f[warp] = mx;
+            __syncthreads();
+            mx = s_f[0];
+#pragma unroll
+            for (int w2 = 1; w2 < NW; ++w2) mx = fmaxf(mx, s_f[w2]);
+            __syncthreads();
+            float se = 0.0f;
+            for (int c = tid; c < NP; c += NT) {
+                const float m = __ldcg(a.lg_m + (int64_t)c * R + r);
+                if (m > -INFINITY) se += __ldcg(a.lg_s + (int64_t)c * R + r) * expf(m - mx);
+            }
+            se = warp_sum(se);
+            if (lane == 0) s_f[warp] = se;
+            __syncthreads();
+            se = 0.0f;
+#pragma unroll
+            for (int w2 = 0; w2 < NW; ++w2) se += s_f[w2];
+            const float lse = logf(se);
+            __syncthreads();
+            float bv = -INFINITY;
+            int bi = INT_MAX;
+            for (int c = tid; c < NP * KC; c += NT) {
+                const int part = c / KC, k = c % KC;
+                const int idx = __ldcg(a.lg_i + ((int64_t)part * R + r) * KC + k);
+                if (idx == INT_MAX) continue;
+                const float v = __fsub_rn(__fsub_rn(__ldcg(a.lg_v + ((int64_t)part * R + r) * KC + k), mx), lse);
+                if (v > bv || (v == bv && idx < bi)) { bv = v; bi = idx; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            if (lane == 0) { s_f[warp] = bv; s_i[warp] = bi; }
+            __syncthreads();
+            if (tid == 0) {
+                bv = s_f[0];
+                bi = s_i[0];
+                for (int w2 = 1; w2 < NW; ++w2)
+                    if (s_f[w2] > bv || (s_f[w2] == bv && s_i[w2] < bi)) { bv = s_f[w2]; bi = s_i[w2]; }
+                a.topk_id[r] = bi == INT_MAX ? -1 : bi;
+                a.topk_lp[r] = bv;
+                if (!__ldcg(a.finished + r)) {
+                    a.tokens[(int64_t)r * t_max + p + 1] = bi;
+                    a.lengths[r] = p + 2;
+                    if (bi == a.eot) a.finished[r] = 1;
+                }
+            }
+            __syncthreads();
+        }
+        grid_sync(a.bar, gen);
+        {
+            int live = 0;
+            for (int r = 0; r < R; ++r) live += __ldcg(a.finished + r) ? 0 : 1;
+            if (live == 0) {
+                if (blockIdx.x == 0 && tid == 0) { *a.pos = p + 1; *a.n_unfinished = 0; *a.steps_done = step + 1; }
+                return;
+            }
+        }
+    }
+    if (blockIdx.x == 0 && tid == 0) {
+        *a.pos = a.pos0 + a.n_steps;
+        int live = 0;
+        for (int r = 0; r < R; ++r) live += __ldcg(a.finished + r) ? 0 : 1;
+        *a.n_unfinished = live;
+        *a.steps_done = a.n_steps;
+    }
+}
+
+template <int D, int RC>
+size_t dec4_smem() {
+    return sizeof(float) * ((size_t)12 * D + CS * 68 + 2 * NW + NW * 64 + 64 + 4 + (size_t)RC * D + (size_t)NW * 4 * RC * 6 + 16);
+}
+
+template <int D, int RC, typename KVT>
+bool launch4_t(const Dec3Args& a, cudaStream_t st) {
+    auto k = dec4_kernel<D, RC, KVT>;
+    const size_t smem = dec4_smem<D, RC>();
+    static int state = 0;   // 0 unknown, 1 ok, -1 unsupported
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(8 * CS);
+    cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (state == 0) {
+        if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+            cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+            cudaGetLastError();
+            state = -1;
+            return false;
+        }
+        int n_clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&n_clusters, k, &cfg) != cudaSuccess || n_clusters < 8) {
+            cudaGetLastError();
+            state = -1;   // all 8 clusters must be co-resident for the grid barriers
+            return false;
+        }
+        state = 1;
+    }
+    if (state < 0) return false;
+    WB_CUDA(cudaLaunchKernelEx(&cfg, k, a));
+    WB_LAUNCH_CHECK();
+    return true;
+}
+
+}  // namespace
+
+// Returns false when this configuration is not covered (caller falls back to decoder3.cu).
+bool launch_dec4(const Dec3Args& a, bool w_half, cudaStream_t st) {
+    if (!w_half || a.R > 8 || a.R < 1 || a.k != 1 || !a.greedy || a.use_cur_tok || a.anc != nullptr || a.logits_out != nullptr) return false;
+    if (a.H * 64 != a.d || a.H > CS) return false;
+#define WB_D4(DD)                                                                                         \
+    do {                                                                                                  \
+        if (a.kv_half) return a.R <= 4 ? launch4_t<DD, 4, __half>(a, st) : launch4_t<DD, 8, __half>(a, st); \
+        return a.R <= 4 ? launch4_t<DD, 4, float>(a, st) : launch4_t<DD, 8, float>(a, st);                 \
+    } while (0)
+    if (a.d == 384) WB_D4(384);
+    if (a.d == 128) WB_D4(128);
+#undef WB_D4
+    return false;
+}
+
+}  // namespace wb

@@ -68,7 +68,8 @@ Session::Session(Model* model, int64_t max_w, int64_t max_b, int64_t max_text_le
         const char* e = getenv("WB200_DECODER");
         if (e && e[0] == '1') dec_version = 1;
         if (e && e[0] == '2') dec_version = 2;
-        if (kv == WB_KV_F16) dec_version = 3;   // the fp16 cache exists in the persistent decoder only
+        if (e && e[0] == '3') dec_version = 3;
+        if (kv == WB_KV_F16 && dec_version < 3) dec_version = 3;   // the fp16 cache exists in the persistent decoders only
         cudaDeviceProp prop;
         WB_CUDA(cudaGetDeviceProperties(&prop, m->device));
         n_sm = prop.multiProcessorCount;
@@ -467,6 +468,7 @@ void Session::launch_v3(int R_, int pos0, int n_steps, int logits_from, bool use
         a.trace_cap = 1 << 16;
     }
     WB_CUDA(cudaMemsetAsync(d3_bar.p, 0, 2 * sizeof(unsigned int), st));   // monotonic barrier counter starts at 0
+    if (dec_version == 4 && !a.trace && launch_dec4(a, m->fp16_exact, st)) return;
     launch_dec3(a, n_sm, m->fp16_exact, st);
     if (a.trace) {
         std::vector<unsigned long long> h(1 << 16);
@@ -482,7 +484,7 @@ void Session::launch_v3(int R_, int pos0, int n_steps, int logits_from, bool use
 
 void Session::step_core(bool with_logits, int mask_mode, int k, bool greedy, int eot, float* logprob_out) {
     if (kv_dtype == WB_KV_F16 && k > 7) fail(WB_ERR_UNSUPPORTED, "fp16 K/V cache supports k <= 7");
-    if (dec_version == 3 && k <= 7) {
+    if (dec_version >= 3 && k <= 7) {
         launch_v3(R, host_pos, 1, with_logits ? 0 : INT_MAX, true, mask_mode, k, greedy, eot);
         ++host_pos;
         return;
@@ -584,7 +586,7 @@ void Session::profile_decode(const int64_t* prompt, int64_t prompt_len, int n_st
         WB_CUDA(cudaEventCreate(&e));
         prof_ev.push_back(e);
     }
-    if (dec_version == 3) {
+    if (dec_version >= 3) {
         // the whole decode is ONE kernel: time the launch (prefill + n_steps greedy steps) and report per step
         begin(prompt, prompt_len, false);
         const int total = (int)prompt_len - 1 + n_steps;
@@ -663,7 +665,7 @@ void Session::step_beams(int64_t n_rows, const int32_t* window_of_row, const int
 void Session::greedy_decode(const int64_t* prompt, int64_t prompt_len, int max_depth, int64_t eot,
                             std::vector<std::vector<int64_t>>& out) {
     WB_REQUIRE(prompt_len + max_depth <= t_max, "greedy: prompt + max_depth exceeds the session's max_text_len");
-    if (dec_version == 3) {
+    if (dec_version >= 3) {
         // one cooperative launch: prompt prefill + every greedy step, early exit inside the kernel
         begin(prompt, prompt_len, /*prefill=*/false);
         const int n_steps = (int)prompt_len - 1 + max_depth;

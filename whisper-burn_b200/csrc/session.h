@@ -64,7 +64,8 @@ struct Session {
     float last_ms[4] = {0, 0, 0, 0};
     int64_t last_steps = 0;
     // fused decoder step (decoder2.cu): partial buffers, tickets, switches
-    int dec_version = 3;         // 3 = persistent cooperative kernel (decoder3.cu); WB200_DECODER=1|2 select the
+    int dec_version = 4;         // 4 = cluster/DSMEM persistent kernel (decoder4.cu) with fallback to 3 = grid-barrier
+                                 // persistent kernel (decoder3.cu); WB200_DECODER=1|2|3 select the older paths:
                                  // unfused (decoder.cu) / fused-per-layer (decoder2.cu) paths for A/B testing
     int n_sm = 0;
     DevBuf<Dec3Layer> d3_layers;
