@@ -16,6 +16,9 @@
 // Reference math: see decoder3.cu.  Greedy path only (beam steps use decoder3.cu).
 #include <cooperative_groups.h>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "dec_common.cuh"
 
 namespace cg = cooperative_groups;
@@ -478,9 +481,9 @@ template <int D, int RC, typename KVT>
 bool launch4_t(const Dec3Args& a, cudaStream_t st) {
     auto k = dec4_kernel<D, RC, KVT>;
     const size_t smem = dec4_smem<D, RC>();
-    static int state = 0;   // 0 unknown, 1 ok, -1 unsupported
+    static int state = 0;   // 0 unknown, >0 = number of co-resident clusters to launch, -1 unsupported
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(8 * CS);
+    cfg.gridDim = dim3((state > 0 ? state : 8) * CS);
     cfg.blockDim = dim3(NT);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
@@ -499,14 +502,17 @@ bool launch4_t(const Dec3Args& a, cudaStream_t st) {
             return false;
         }
         int n_clusters = 0;
-        if (cudaOccupancyMaxActiveClusters(&n_clusters, k, &cfg) != cudaSuccess || n_clusters < 8) {
+        const cudaError_t oe = cudaOccupancyMaxActiveClusters(&n_clusters, k, &cfg);
+        if (getenv("WB200_VERBOSE")) fprintf(stderr, "[wb] dec4<D=%d,RC=%d>: smem %zu B, max active clusters %d (%s)\n", D, RC, smem, n_clusters, cudaGetErrorString(oe));
+        if (oe != cudaSuccess || n_clusters < 1) {
             cudaGetLastError();
-            state = -1;   // all 8 clusters must be co-resident for the grid barriers
+            state = -1;
             return false;
         }
-        state = 1;
+        state = std::min(n_clusters, 8);   // every launched cluster must be co-resident (grid barriers); B200: 7 of size 16
+        cfg.gridDim = dim3(state * CS);
     }
-    if (state < 0) return false;
+    if (state < 0 || a.R > state) return false;
     WB_CUDA(cudaLaunchKernelEx(&cfg, k, a));
     WB_LAUNCH_CHECK();
     return true;
