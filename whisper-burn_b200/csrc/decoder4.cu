@@ -135,7 +135,9 @@ dec4_kernel(const Dec3Args a) {
     float* xs = ML + 4;               // logits stage: [RC][D] LayerNorm rows, then merge scratch
     float* red = xs + RC * D;         // [NW*4][RC][2 + 2*KC]
     unsigned int gen = 0;
+    int tr_n = 0;
     const float scale = a.qk_scale;
+    WB_TRACE();
 
     const __half* nullw = nullptr;
     (void)nullw;
@@ -178,6 +180,7 @@ dec4_kernel(const Dec3Args a) {
                 RowRegs<NR_D, VPL> w_o;
                 load_rows<NR_D, VPL>(reinterpret_cast<const __half*>(W.Wo), D, rank * (D / CS) + warp, NW, w_o);
                 cl.sync();
+                WB_TRACE();
                 // ================= S2: self attention, head = rank (ranks >= H idle)
                 if (rank < H) {
                     const int h = rank;
@@ -193,6 +196,7 @@ dec4_kernel(const Dec3Args a) {
                     }
                 }
                 cl.sync();
+                WB_TRACE();
                 // ================= S3: delta = att Wo + bo
                 {
                     float acc[NR_D];
@@ -206,6 +210,7 @@ dec4_kernel(const Dec3Args a) {
                 RowRegs<NR_D, VPL> w_cq;
                 load_rows<NR_D, VPL>(reinterpret_cast<const __half*>(W.Wcq), D, rank * (D / CS) + warp, NW, w_cq);
                 cl.sync();
+                WB_TRACE();
                 // ================= S4: x += delta; cross query = LN2(x) Wcq + b
                 for (int c = tid; c < D; c += NT) x_s[c] = __fadd_rn(x_s[c], dl_s[c]);
                 __syncthreads();
@@ -223,6 +228,7 @@ dec4_kernel(const Dec3Args a) {
                 RowRegs<NR_D, VPL> w_co;
                 load_rows<NR_D, VPL>(reinterpret_cast<const __half*>(W.Wco), D, rank * (D / CS) + warp, NW, w_co);
                 cl.sync();
+                WB_TRACE();
                 // ================= S5: cross attention; head = rank % H, the CTAs of a head split the keys
                 {
                     const int h = rank % H, ci = rank / H;
@@ -264,6 +270,7 @@ dec4_kernel(const Dec3Args a) {
                     }
                 }
                 cl.sync();
+                WB_TRACE();
                 // ================= S6: merge the head partials, delta = cross Wco + bco
                 for (int c = tid; c < D; c += NT) {
                     const int h = c / 64;
@@ -291,6 +298,7 @@ dec4_kernel(const Dec3Args a) {
                 RowRegs<NR_H, VPL> w_1;
                 load_rows<NR_H, VPL>(reinterpret_cast<const __half*>(W.W1), D, rank * (4 * D / CS) + warp, NW, w_1);
                 cl.sync();
+                WB_TRACE();
                 // ================= S7: x += delta; hid = gelu(LN3(x) W1 + b1)
                 for (int c = tid; c < D; c += NT) x_s[c] = __fadd_rn(x_s[c], dl_s[c]);
                 __syncthreads();
@@ -308,6 +316,7 @@ dec4_kernel(const Dec3Args a) {
                 RowRegs<NR_D, VPL4> w_2;
                 load_rows<NR_D, VPL4>(reinterpret_cast<const __half*>(W.W2), 4 * D, rank * (D / CS) + warp, NW, w_2);
                 cl.sync();
+                WB_TRACE();
                 // ================= S8: delta = hid W2 + b2
                 {
                     float acc[NR_D];
@@ -321,13 +330,16 @@ dec4_kernel(const Dec3Args a) {
                 if (l + 1 < L)
                     load_rows<NR_QKV, VPL>(reinterpret_cast<const __half*>(a.layers[l + 1].Wqkv), D, rank * (3 * D / CS) + warp, NW, w_qkv);
                 cl.sync();
+                WB_TRACE();
             }
             // final residual add; rank 0 publishes the row for the vocabulary projection
             if (want_logits && rank == 0)
                 for (int c = tid; c < D; c += NT) a.x[(int64_t)row * D + c] = __fadd_rn(x_s[c], dl_s[c]);
         }
         if (!want_logits) continue;   // prefill positions: clusters stay independent, no chip-wide step
+        WB_TRACE();
         grid_sync(a.bar, gen);
+        WB_TRACE();
         // ================= logits (all CTAs): LN(x) tok_emb^T + mask + online softmax + candidates
         {
             const bool use_mask = a.is_special != nullptr && (a.mask_mode == 1 || (a.mask_mode == 2 && p + 1 <= 5));
@@ -392,7 +404,9 @@ dec4_kernel(const Dec3Args a) {
                 for (int k = 0; k < KC; ++k) { a.lg_v[o * KC + k] = best.v[k]; a.lg_i[o * KC + k] = best.i[k]; }
             }
         }
+        WB_TRACE();
         grid_sync(a.bar, gen);
+        WB_TRACE();
         // ================= finish: one CTA per row (greedy: beam.rs:9-37 with beam_size 1)
         for (int r = blockIdx.x; r < R; r += gridDim.x) {
             float* s_f = wm;
@@ -453,7 +467,9 @@ dec4_kernel(const Dec3Args a) {
             }
             __syncthreads();
         }
+        WB_TRACE();
         grid_sync(a.bar, gen);
+        WB_TRACE();
         {
             int live = 0;
             for (int r = 0; r < R; ++r) live += __ldcg(a.finished + r) ? 0 : 1;

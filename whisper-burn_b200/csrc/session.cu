@@ -468,8 +468,7 @@ void Session::launch_v3(int R_, int pos0, int n_steps, int logits_from, bool use
         a.trace_cap = 1 << 16;
     }
     WB_CUDA(cudaMemsetAsync(d3_bar.p, 0, 2 * sizeof(unsigned int), st));   // monotonic barrier counter starts at 0
-    if (dec_version == 4 && !a.trace && launch_dec4(a, m->fp16_exact, st)) return;
-    launch_dec3(a, n_sm, m->fp16_exact, st);
+    if (!(dec_version == 4 && launch_dec4(a, m->fp16_exact, st))) launch_dec3(a, n_sm, m->fp16_exact, st);
     if (a.trace) {
         std::vector<unsigned long long> h(1 << 16);
         WB_CUDA(cudaStreamSynchronize(st));
