@@ -28,16 +28,49 @@ namespace wb {
 namespace {
 
 constexpr int CS = 16;   // CTAs per cluster
+constexpr int LG_NBUF = 3;                 // logits stage: ring slots per warp
+constexpr int LG_RB = 8;                   // vocabulary rows per slot
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LG_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LG_DONE;\n"
+        "bra LG_WAIT;\n"
+        "LG_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D bulk copy global -> shared (TMA engine, no tensor map), completion counted on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 
 template <int NR, int VPL>
 struct RowRegs {
     uint4 v[NR][VPL];
+    float bias[NR];   // fetched together with the rows, before the barrier
 };
 
 // rows row0, row0 + step, ... of W[.][K] (fp16) -> registers; lane-strided 16-byte vectors
 template <int NR, int VPL>
-__device__ __forceinline__ void load_rows(const __half* __restrict__ W, int K, int row0, int step, RowRegs<NR, VPL>& r) {
+__device__ __forceinline__ void load_rows(const __half* __restrict__ W, const float* __restrict__ bias, int K, int row0, int step,
+                                          RowRegs<NR, VPL>& r) {
     const int lane = threadIdx.x & 31, nv = K / 8;
+#pragma unroll
+    for (int i = 0; i < NR; ++i) r.bias[i] = __ldg(bias + row0 + i * step);
 #pragma unroll
     for (int i = 0; i < NR; ++i) {
         const uint4* p = reinterpret_cast<const uint4*>(W + (int64_t)(row0 + i * step) * K);
@@ -81,25 +114,62 @@ __device__ __forceinline__ void bcast(cg::cluster_group& cl, float* local, float
     if (lane < CS) *cl.map_shared_rank(local, lane) = v;
 }
 
-// LayerNorm of one row held in shared memory (burn 0.9 form), by warp 0; others wait at the caller's barrier
-__device__ __forceinline__ void ln_row(const float* x_s, float* out_s, int d, const float* __restrict__ g,
-                                       const float* __restrict__ b, float eps, int eps_outside) {
-    const int lane = threadIdx.x & 31;
-    if ((threadIdx.x >> 5) != 0) return;
+// LayerNorm of one row held in shared memory (burn 0.9 form) by the whole CTA: thread t owns elements t, t+NT.
+// If delta != null the row is first updated in place (x += delta).  gamma/beta are fetched before the
+// reductions so their latency is hidden.  red: [2*NW] floats of scratch.  Ends with a __syncthreads().
+template <int D>
+__device__ __forceinline__ void ln_block(float* x_s, const float* delta_s, float* out_s, const float* __restrict__ g,
+                                         const float* __restrict__ b, float eps, int eps_outside, float* red) {
+    constexpr int PT = (D + NT - 1) / NT;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float xv[PT], gv[PT], bv[PT];
+#pragma unroll
+    for (int i = 0; i < PT; ++i) {
+        const int c = tid + i * NT;
+        gv[i] = c < D ? __ldg(g + c) : 0.0f;
+        bv[i] = c < D ? __ldg(b + c) : 0.0f;
+    }
     float s = 0.0f;
-    for (int c = lane; c < d; c += 32) s += x_s[c];
+#pragma unroll
+    for (int i = 0; i < PT; ++i) {
+        const int c = tid + i * NT;
+        xv[i] = 0.0f;
+        if (c < D) {
+            xv[i] = delta_s ? __fadd_rn(x_s[c], delta_s[c]) : x_s[c];
+            if (delta_s) x_s[c] = xv[i];
+            s += xv[i];
+        }
+    }
     s = warp_sum(s);
-    const float mean = __fdiv_rn(s, (float)d);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    s = 0.0f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s += red[w];
+    const float mean = __fdiv_rn(s, (float)D);
     float q = 0.0f;
-    for (int c = lane; c < d; c += 32) {
-        const float dv = __fsub_rn(x_s[c], mean);
-        q = __fadd_rn(q, __fmul_rn(dv, dv));
+#pragma unroll
+    for (int i = 0; i < PT; ++i) {
+        const int c = tid + i * NT;
+        if (c < D) {
+            xv[i] = __fsub_rn(xv[i], mean);
+            q = __fadd_rn(q, __fmul_rn(xv[i], xv[i]));
+        }
     }
     q = warp_sum(q);
-    const float var = __fdiv_rn(q, (float)d);
+    if (lane == 0) red[NW + warp] = q;
+    __syncthreads();
+    q = 0.0f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) q += red[NW + w];
+    const float var = __fdiv_rn(q, (float)D);
     const float den = eps_outside ? __fadd_rn(__fsqrt_rn(var), eps) : __fsqrt_rn(__fadd_rn(var, eps));
-    for (int c = lane; c < d; c += 32)
-        out_s[c] = __fadd_rn(__fmul_rn(__fdiv_rn(__fsub_rn(x_s[c], mean), den), __ldg(g + c)), __ldg(b + c));
+#pragma unroll
+    for (int i = 0; i < PT; ++i) {
+        const int c = tid + i * NT;
+        if (c < D) out_s[c] = __fadd_rn(__fmul_rn(__fdiv_rn(xv[i], den), gv[i]), bv[i]);
+    }
+    __syncthreads();
 }
 
 template <int D, int RC, typename KVT>
@@ -134,6 +204,15 @@ dec4_kernel(const Dec3Args a) {
     float* ML = ao + 64;              // [2]
     float* xs = ML + 4;               // logits stage: [RC][D] LayerNorm rows, then merge scratch
     float* red = xs + RC * D;         // [NW*4][RC][2 + 2*KC]
+    constexpr int LG_PITCH = D * 2 + 16;                                   // bytes per staged vocabulary row (+16: bank spread)
+    uint8_t* ring = reinterpret_cast<uint8_t*>(red + NW * 4 * RC * 6);      // [NW][LG_NBUF][LG_RB][LG_PITCH]
+    uint64_t* lg_bar = reinterpret_cast<uint64_t*>(ring + (size_t)NW * LG_NBUF * LG_RB * LG_PITCH);   // [NW][LG_NBUF]
+    if (lane == 0) {
+        for (int j = 0; j < LG_NBUF; ++j) mbar_init(lg_bar + warp * LG_NBUF + j, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    unsigned int lg_count = 0;   // blocks this warp has pushed through its ring since kernel start (slot / parity bookkeeping)
     unsigned int gen = 0;
     int tr_n = 0;
     const float scale = a.qk_scale;
@@ -149,26 +228,21 @@ dec4_kernel(const Dec3Args a) {
             const int tok = __ldcg(a.tokens + (int64_t)row * t_max + p);
             for (int c = tid; c < D; c += NT) x_s[c] = __fadd_rn(__ldg(a.tok_emb + (int64_t)tok * D + c), __ldg(a.pos_emb + (int64_t)p * D + c));
             RowRegs<NR_QKV, VPL> w_qkv;
-            load_rows<NR_QKV, VPL>(reinterpret_cast<const __half*>(a.layers[0].Wqkv), D, rank * (3 * D / CS) + warp, NW, w_qkv);
+            load_rows<NR_QKV, VPL>(reinterpret_cast<const __half*>(a.layers[0].Wqkv), a.layers[0].bqkv, D, rank * (3 * D / CS) + warp, NW, w_qkv);
             __syncthreads();
             for (int l = 0; l < L; ++l) {
                 const Dec3Layer& W = a.layers[l];
                 KVT* kcl = reinterpret_cast<KVT*>(a.kc) + (size_t)l * a.Rmax * t_max * D;
                 KVT* vcl = reinterpret_cast<KVT*>(a.vc) + (size_t)l * a.Rmax * t_max * D;
                 // ================= S1: q | k | v = LN1(x) Wqkv + b
-                if (l > 0) {
-                    for (int c = tid; c < D; c += NT) x_s[c] = __fadd_rn(x_s[c], dl_s[c]);   // MLP2 of the previous layer
-                    __syncthreads();
-                }
-                ln_row(x_s, xn_s, D, W.ln1_g, W.ln1_b, W.ln1_eps, a.eps_outside);
-                __syncthreads();
+                ln_block<D>(x_s, l > 0 ? dl_s : nullptr, xn_s, W.ln1_g, W.ln1_b, W.ln1_eps, a.eps_outside, wm);   // l > 0: += MLP2 of the previous layer
                 {
                     float acc[NR_QKV];
                     dot_rows1<NR_QKV, VPL>(w_qkv, xn_s, D, acc);
 #pragma unroll
                     for (int i = 0; i < NR_QKV; ++i) {
                         const int n = rank * (3 * D / CS) + warp + i * NW;
-                        float v = __fadd_rn(acc[i], __ldg(W.bqkv + n));
+                        float v = __fadd_rn(acc[i], w_qkv.bias[i]);
                         if (n < 2 * D) v = __fmul_rn(v, scale);
                         bcast(cl, qkv_s + n, v);
                         if (lane == 0 && n >= D) {
@@ -178,7 +252,7 @@ dec4_kernel(const Dec3Args a) {
                     }
                 }
                 RowRegs<NR_D, VPL> w_o;
-                load_rows<NR_D, VPL>(reinterpret_cast<const __half*>(W.Wo), D, rank * (D / CS) + warp, NW, w_o);
+                load_rows<NR_D, VPL>(reinterpret_cast<const __half*>(W.Wo), W.bo, D, rank * (D / CS) + warp, NW, w_o);
                 cl.sync();
                 WB_TRACE();
                 // ================= S2: self attention, head = rank (ranks >= H idle)
@@ -204,29 +278,26 @@ dec4_kernel(const Dec3Args a) {
 #pragma unroll
                     for (int i = 0; i < NR_D; ++i) {
                         const int n = rank * (D / CS) + warp + i * NW;
-                        bcast(cl, dl_s + n, __fadd_rn(acc[i], __ldg(W.bo + n)));
+                        bcast(cl, dl_s + n, __fadd_rn(acc[i], w_o.bias[i]));
                     }
                 }
                 RowRegs<NR_D, VPL> w_cq;
-                load_rows<NR_D, VPL>(reinterpret_cast<const __half*>(W.Wcq), D, rank * (D / CS) + warp, NW, w_cq);
+                load_rows<NR_D, VPL>(reinterpret_cast<const __half*>(W.Wcq), W.bcq, D, rank * (D / CS) + warp, NW, w_cq);
                 cl.sync();
                 WB_TRACE();
                 // ================= S4: x += delta; cross query = LN2(x) Wcq + b
-                for (int c = tid; c < D; c += NT) x_s[c] = __fadd_rn(x_s[c], dl_s[c]);
-                __syncthreads();
-                ln_row(x_s, xn_s, D, W.ln2_g, W.ln2_b, W.ln2_eps, a.eps_outside);
-                __syncthreads();
+                ln_block<D>(x_s, dl_s, xn_s, W.ln2_g, W.ln2_b, W.ln2_eps, a.eps_outside, wm);
                 {
                     float acc[NR_D];
                     dot_rows1<NR_D, VPL>(w_cq, xn_s, D, acc);
 #pragma unroll
                     for (int i = 0; i < NR_D; ++i) {
                         const int n = rank * (D / CS) + warp + i * NW;
-                        bcast(cl, q2_s + n, __fmul_rn(__fadd_rn(acc[i], __ldg(W.bcq + n)), scale));
+                        bcast(cl, q2_s + n, __fmul_rn(__fadd_rn(acc[i], w_cq.bias[i]), scale));
                     }
                 }
                 RowRegs<NR_D, VPL> w_co;
-                load_rows<NR_D, VPL>(reinterpret_cast<const __half*>(W.Wco), D, rank * (D / CS) + warp, NW, w_co);
+                load_rows<NR_D, VPL>(reinterpret_cast<const __half*>(W.Wco), W.bco, D, rank * (D / CS) + warp, NW, w_co);
                 cl.sync();
                 WB_TRACE();
                 // ================= S5: cross attention; head = rank % H, the CTAs of a head split the keys
@@ -292,29 +363,26 @@ dec4_kernel(const Dec3Args a) {
 #pragma unroll
                     for (int i = 0; i < NR_D; ++i) {
                         const int n = rank * (D / CS) + warp + i * NW;
-                        bcast(cl, dl_s + n, __fadd_rn(acc[i], __ldg(W.bco + n)));
+                        bcast(cl, dl_s + n, __fadd_rn(acc[i], w_co.bias[i]));
                     }
                 }
                 RowRegs<NR_H, VPL> w_1;
-                load_rows<NR_H, VPL>(reinterpret_cast<const __half*>(W.W1), D, rank * (4 * D / CS) + warp, NW, w_1);
+                load_rows<NR_H, VPL>(reinterpret_cast<const __half*>(W.W1), W.b1, D, rank * (4 * D / CS) + warp, NW, w_1);
                 cl.sync();
                 WB_TRACE();
                 // ================= S7: x += delta; hid = gelu(LN3(x) W1 + b1)
-                for (int c = tid; c < D; c += NT) x_s[c] = __fadd_rn(x_s[c], dl_s[c]);
-                __syncthreads();
-                ln_row(x_s, xn_s, D, W.ln3_g, W.ln3_b, W.ln3_eps, a.eps_outside);
-                __syncthreads();
+                ln_block<D>(x_s, dl_s, xn_s, W.ln3_g, W.ln3_b, W.ln3_eps, a.eps_outside, wm);
                 {
                     float acc[NR_H];
                     dot_rows1<NR_H, VPL>(w_1, xn_s, D, acc);
 #pragma unroll
                     for (int i = 0; i < NR_H; ++i) {
                         const int n = rank * (4 * D / CS) + warp + i * NW;
-                        bcast(cl, hid_s + n, gelu_erf(__fadd_rn(acc[i], __ldg(W.b1 + n))));
+                        bcast(cl, hid_s + n, gelu_erf(__fadd_rn(acc[i], w_1.bias[i])));
                     }
                 }
                 RowRegs<NR_D, VPL4> w_2;
-                load_rows<NR_D, VPL4>(reinterpret_cast<const __half*>(W.W2), 4 * D, rank * (D / CS) + warp, NW, w_2);
+                load_rows<NR_D, VPL4>(reinterpret_cast<const __half*>(W.W2), W.b2, 4 * D, rank * (D / CS) + warp, NW, w_2);
                 cl.sync();
                 WB_TRACE();
                 // ================= S8: delta = hid W2 + b2
@@ -324,11 +392,11 @@ dec4_kernel(const Dec3Args a) {
 #pragma unroll
                     for (int i = 0; i < NR_D; ++i) {
                         const int n = rank * (D / CS) + warp + i * NW;
-                        bcast(cl, dl_s + n, __fadd_rn(acc[i], __ldg(W.b2 + n)));
+                        bcast(cl, dl_s + n, __fadd_rn(acc[i], w_2.bias[i]));
                     }
                 }
                 if (l + 1 < L)
-                    load_rows<NR_QKV, VPL>(reinterpret_cast<const __half*>(a.layers[l + 1].Wqkv), D, rank * (3 * D / CS) + warp, NW, w_qkv);
+                    load_rows<NR_QKV, VPL>(reinterpret_cast<const __half*>(a.layers[l + 1].Wqkv), a.layers[l + 1].bqkv, D, rank * (3 * D / CS) + warp, NW, w_qkv);
                 cl.sync();
                 WB_TRACE();
             }
@@ -350,33 +418,75 @@ dec4_kernel(const Dec3Args a) {
             float m_run = -INFINITY, s_run = 0.0f;
             Cand<KC> cand;
             cand.init();
-            const int n_blk = (V + 7) / 8;
-            for (int blk = gw; blk < n_blk; blk += n_gw) {
-                const int n0 = blk * 8;
-                const __half* rows[2];
-                int nn[2];
+            // Stream the embedding matrix through this warp's ring: 8-row blocks, one bulk copy (TMA engine)
+            // per row into a bank-spread slot, completion on the slot's mbarrier; 2 blocks always in flight.
+            const int n_blk = (V + LG_RB - 1) / LG_RB;
+            uint8_t* wring = ring + (size_t)warp * LG_NBUF * LG_RB * LG_PITCH;
+            uint64_t* wbar = lg_bar + warp * LG_NBUF;
+            auto issue = [&](int blk, unsigned int cnt) {
+                if (blk >= n_blk) return;
+                const int slot = cnt % LG_NBUF;
+                const int rows = min(LG_RB, V - blk * LG_RB);
+                if (lane == 0) mbar_expect_tx(wbar + slot, (uint32_t)rows * D * 2);
+                __syncwarp();
+                if (lane < rows) bulk_g2s(wring + (size_t)(slot * LG_RB + lane) * LG_PITCH, E + (int64_t)(blk * LG_RB + lane) * D, D * 2, wbar + slot);
+            };
+            unsigned int c_issue = lg_count, c_use = lg_count;
+            int blk_issue = gw;
 #pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    nn[g] = n0 + g * 4 + sub;
-                    rows[g] = E + (int64_t)min(nn[g], V - 1) * D;
-                }
+            for (int j = 0; j < LG_NBUF - 1; ++j) { issue(blk_issue, c_issue); blk_issue += n_gw; ++c_issue; }
+            for (int blk = gw; blk < n_blk; blk += n_gw) {
+                issue(blk_issue, c_issue);
+                blk_issue += n_gw;
+                ++c_issue;
+                const int slot = c_use % LG_NBUF;
+                mbar_wait(wbar + slot, (c_use / LG_NBUF) & 1);
+                const uint8_t* sl = wring + (size_t)slot * LG_RB * LG_PITCH;
                 float acc[2][RC];
-                dot_groups<__half, RC, 2>(rows, xs, D, acc);
+#pragma unroll
+                for (int g = 0; g < 2; ++g)
+#pragma unroll
+                    for (int rr = 0; rr < RC; ++rr) acc[g][rr] = 0.0f;
+#pragma unroll
+                for (int k0 = 0; k0 < D; k0 += 64) {
+                    const int kk = k0 + l8 * 8;
+                    float w[2][8];
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) cvt8(*reinterpret_cast<const uint4*>(sl + (size_t)(g * 4 + sub) * LG_PITCH + kk * 2), w[g]);
+#pragma unroll
+                    for (int rr = 0; rr < RC; ++rr)
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) acc[g][rr] = dot8_acc<RC>(w[g], xs + rr * D + kk, acc[g][rr]);
+                }
+#pragma unroll
+                for (int g = 0; g < 2; ++g)
+#pragma unroll
+                    for (int rr = 0; rr < RC; ++rr) {
+                        float v = acc[g][rr];
+                        v += __shfl_xor_sync(0xffffffffu, v, 4);
+                        v += __shfl_xor_sync(0xffffffffu, v, 2);
+                        v += __shfl_xor_sync(0xffffffffu, v, 1);
+                        acc[g][rr] = v;
+                    }
+                __syncwarp();   // slot fully read before it is refilled two iterations later
+                ++c_use;
                 if (l8 < RC && l8 < R) {
 #pragma unroll
                     for (int g = 0; g < 2; ++g) {
-                        if (nn[g] < V) {
+                        const int n = blk * LG_RB + g * 4 + sub;
+                        if (n < V) {
                             const float raw = pick_row<RC>(acc[g], l8);
-                            const float v = (use_mask && a.is_special[nn[g]]) ? __fadd_rn(raw, -INFINITY) : raw;
+                            const float v = (use_mask && a.is_special[n]) ? __fadd_rn(raw, -INFINITY) : raw;
                             if (v > -INFINITY) {
                                 if (v > m_run) { s_run = s_run * expf(m_run - v) + 1.0f; m_run = v; }
                                 else s_run += expf(v - m_run);
                             }
-                            cand.push(v, nn[g]);
+                            cand.push(v, n);
                         }
                     }
                 }
             }
+            lg_count = c_use;
             if (l8 < RC) {
                 float* rec = red + ((warp * 4 + sub) * RC + l8) * (2 + 2 * KC);
                 rec[0] = m_run;
@@ -490,7 +600,8 @@ dec4_kernel(const Dec3Args a) {
 
 template <int D, int RC>
 size_t dec4_smem() {
-    return sizeof(float) * ((size_t)12 * D + CS * 68 + 2 * NW + NW * 64 + 64 + 4 + (size_t)RC * D + (size_t)NW * 4 * RC * 6 + 16);
+    return sizeof(float) * ((size_t)12 * D + CS * 68 + 2 * NW + NW * 64 + 64 + 4 + (size_t)RC * D + (size_t)NW * 4 * RC * 6 + 16) +
+           (size_t)NW * LG_NBUF * LG_RB * (D * 2 + 16) + NW * LG_NBUF * 8 + 16;
 }
 
 template <int D, int RC, typename KVT>
