@@ -204,7 +204,7 @@ dec4_kernel(const Dec3Args a) {
     float* ML = ao + 64;              // [2]
     float* xs = ML + 4;               // logits stage: [RC][D] LayerNorm rows, then merge scratch
     float* red = xs + RC * D;         // [NW*4][RC][2 + 2*KC]
-    constexpr int LG_PITCH = D * 2 + 16;                                   // bytes per staged vocabulary row (+16: bank spread)
+    constexpr int LG_PITCH = D * 2;                                        // bytes per staged vocabulary row (rows contiguous: one bulk copy per block)
     uint8_t* ring = reinterpret_cast<uint8_t*>(red + NW * 4 * RC * 6);      // [NW][LG_NBUF][LG_RB][LG_PITCH]
     uint64_t* lg_bar = reinterpret_cast<uint64_t*>(ring + (size_t)NW * LG_NBUF * LG_RB * LG_PITCH);   // [NW][LG_NBUF]
     if (lane == 0) {
@@ -427,9 +427,10 @@ dec4_kernel(const Dec3Args a) {
                 if (blk >= n_blk) return;
                 const int slot = cnt % LG_NBUF;
                 const int rows = min(LG_RB, V - blk * LG_RB);
-                if (lane == 0) mbar_expect_tx(wbar + slot, (uint32_t)rows * D * 2);
-                __syncwarp();
-                if (lane < rows) bulk_g2s(wring + (size_t)(slot * LG_RB + lane) * LG_PITCH, E + (int64_t)(blk * LG_RB + lane) * D, D * 2, wbar + slot);
+                if (lane == 0) {
+                    mbar_expect_tx(wbar + slot, (uint32_t)rows * D * 2);
+                    bulk_g2s(wring + (size_t)slot * LG_RB * LG_PITCH, E + (int64_t)blk * LG_RB * D, (uint32_t)rows * D * 2, wbar + slot);
+                }
             };
             unsigned int c_issue = lg_count, c_use = lg_count;
             int blk_issue = gw;
@@ -449,7 +450,9 @@ dec4_kernel(const Dec3Args a) {
                     for (int rr = 0; rr < RC; ++rr) acc[g][rr] = 0.0f;
 #pragma unroll
                 for (int k0 = 0; k0 < D; k0 += 64) {
-                    const int kk = k0 + l8 * 8;
+                    // rows are D*2 bytes apart (a multiple of 128 B), so the four sub-groups would hit the same banks:
+                    // rotate the 16-byte chunk a lane takes within each 64-element group by 2*sub (sum is unchanged)
+                    const int kk = k0 + ((l8 + 2 * sub) & 7) * 8;
                     float w[2][8];
 #pragma unroll
                     for (int g = 0; g < 2; ++g) cvt8(*reinterpret_cast<const uint4*>(sl + (size_t)(g * 4 + sub) * LG_PITCH + kk * 2), w[g]);
@@ -601,7 +604,7 @@ dec4_kernel(const Dec3Args a) {
 template <int D, int RC>
 size_t dec4_smem() {
     return sizeof(float) * ((size_t)12 * D + CS * 68 + 2 * NW + NW * 64 + 64 + 4 + (size_t)RC * D + (size_t)NW * 4 * RC * 6 + 16) +
-           (size_t)NW * LG_NBUF * LG_RB * (D * 2 + 16) + NW * LG_NBUF * 8 + 16;
+           (size_t)NW * LG_NBUF * LG_RB * (D * 2) + NW * LG_NBUF * 8 + 16;
 }
 
 template <int D, int RC, typename KVT>
