@@ -263,10 +263,11 @@ dec4_kernel(const Dec3Args a) {
                     auto kp = [&](int j) { return kb + ((int64_t)row * t_max + j) * D; };
                     auto vp = [&](int j) { return vb + ((int64_t)row * t_max + j) * D; };
                     attn_cta(qkv_s + h * 64, p + 1, kp, vp, wm, wl, wo, ao, ML);
-                    if (tid < 64) {
-                        const float v = __fdiv_rn(ao[tid], ML[1]);
+                    {
+                        const int c = tid & 63, r0b = (tid >> 6) * 4;
+                        const float v = __fdiv_rn(ao[c], ML[1]);
 #pragma unroll
-                        for (int r2 = 0; r2 < CS; ++r2) *cl.map_shared_rank(att_s + h * 64 + tid, r2) = v;
+                        for (int r2 = 0; r2 < 4; ++r2) *cl.map_shared_rank(att_s + h * 64 + c, r0b + r2) = v;
                     }
                 }
                 cl.sync();
@@ -332,11 +333,17 @@ dec4_kernel(const Dec3Args a) {
                             Ls += sc * wl[w2];
                             o += sc * wo[w2 * 64 + tid];
                         }
+                        ao[tid] = o;
+                        if (tid == 0) { ML[0] = M; ML[1] = Ls; }
+                    }
+                    __syncthreads();
+                    {
+                        const int c = tid & 63, r0b = (tid >> 6) * 4;
 #pragma unroll
-                        for (int r2 = 0; r2 < CS; ++r2) {
-                            float* dst = cl.map_shared_rank(part_s + rank * 68, r2);
-                            dst[4 + tid] = o;
-                            if (tid == 0) { dst[0] = M; dst[1] = Ls; }
+                        for (int r2 = 0; r2 < 4; ++r2) {
+                            float* dst = cl.map_shared_rank(part_s + rank * 68, r0b + r2);
+                            dst[4 + c] = ao[c];
+                            if (c == 0) { dst[0] = ML[0]; dst[1] = ML[1]; }
                         }
                     }
                 }
@@ -415,6 +422,7 @@ dec4_kernel(const Dec3Args a) {
             const int sub = lane >> 3, l8 = lane & 7;
             stage_ln<RC>(a.x, 0, R, D, a.lnf_g, a.lnf_b, a.lnf_eps, a.eps_outside, xs);
             __syncthreads();
+            WB_TRACE();
             float m_run = -INFINITY, s_run = 0.0f;
             Cand<KC> cand;
             cand.init();
@@ -490,8 +498,27 @@ dec4_kernel(const Dec3Args a) {
                 }
             }
             lg_count = c_use;
-            if (l8 < RC) {
-                float* rec = red + ((warp * 4 + sub) * RC + l8) * (2 + 2 * KC);
+            WB_TRACE();
+            // merge the 4 sub-group states of every batch row inside the warp (lanes l8, l8+8, l8+16, l8+24) ...
+#pragma unroll
+            for (int off = 8; off < 32; off <<= 1) {
+                const float m2 = __shfl_xor_sync(0xffffffffu, m_run, off);
+                const float s2 = __shfl_xor_sync(0xffffffffu, s_run, off);
+                float cv[KC];
+                int ci[KC];
+#pragma unroll
+                for (int k = 0; k < KC; ++k) { cv[k] = __shfl_xor_sync(0xffffffffu, cand.v[k], off); ci[k] = __shfl_xor_sync(0xffffffffu, cand.i[k], off); }
+                const float mn = fmaxf(m_run, m2);
+                const float e1 = m_run > -INFINITY ? expf(m_run - mn) : 0.0f;
+                const float e2 = m2 > -INFINITY ? expf(m2 - mn) : 0.0f;
+                s_run = s_run * e1 + s2 * e2;
+                m_run = mn;
+#pragma unroll
+                for (int k = 0; k < KC; ++k) cand.push(cv[k], ci[k]);
+            }
+            // ... then the 8 warps through shared memory: one record per (warp, row)
+            if (sub == 0 && l8 < RC) {
+                float* rec = red + (warp * RC + l8) * (2 + 2 * KC);
                 rec[0] = m_run;
                 rec[1] = s_run;
 #pragma unroll
@@ -500,11 +527,11 @@ dec4_kernel(const Dec3Args a) {
             __syncthreads();
             if (tid < RC && tid < R) {
                 float M = -INFINITY;
-                for (int w2 = 0; w2 < NW * 4; ++w2) M = fmaxf(M, red[(w2 * RC + tid) * (2 + 2 * KC)]);
+                for (int w2 = 0; w2 < NW; ++w2) M = fmaxf(M, red[(w2 * RC + tid) * (2 + 2 * KC)]);
                 float Ssum = 0.0f;
                 Cand<KC> best;
                 best.init();
-                for (int w2 = 0; w2 < NW * 4; ++w2) {
+                for (int w2 = 0; w2 < NW; ++w2) {
                     const float* rec = red + (w2 * RC + tid) * (2 + 2 * KC);
                     if (rec[0] > -INFINITY) Ssum += rec[1] * expf(rec[0] - M);
 #pragma unroll
