@@ -88,6 +88,11 @@ int wb_model_create(const wb_dims* dims, int device, wb_model** out);
  * (dump.py:141-145), Conv1d weights [out, in, k], embeddings [rows, d], LayerNorm eps is a
  * 1-element tensor.  Data is copied. */
 int wb_model_set_tensor(wb_model* m, const char* path, const float* data, const int64_t* shape, int ndim);
+/* model::load::load_whisper (src/model/load.rs:295-310): builds a finalized model from the npy tree that
+ * python/dump.py writes (one f32 .npy per tensor, payload = [dims..., values...], scalars as [1.0, value]);
+ * the dimensions come from the tree itself.  wb_npy_tree_probe only reads the dimensions (host only). */
+int wb_npy_tree_probe(const char* dir, wb_dims* dims_out);
+int wb_model_load_npy_tree(const char* dir, int device, int ln_eps_outside, wb_model** out);
 /* burn's nn::LayerNorm is third-party and un-vendored: burn 0.9 (the reference's pin, Cargo.lock:242-244)
  * normalises by (sqrt(var) + eps); later burn releases by sqrt(var + eps).  outside != 0 selects the
  * former (default).  Must be called before wb_model_finalize. */

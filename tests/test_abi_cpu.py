@@ -77,3 +77,19 @@ def test_contract_violations_are_invalid_arg():
     with pytest.raises(ffi.WbError) as e:
         audio.prep_audio(np.zeros((1, 399), np.float32))
     assert e.value.code == ffi.WB_ERR_INVALID_ARG
+
+
+def test_npy_tree_probe_reads_reference_format(tmp_path):
+    """The reference's model-file format (python/dump.py:120-213 / src/model/load.rs:19-53): dims come from the tree."""
+    from whisper_burn_b200 import npytree, synth
+    dims, w_np = synth.make_weights("test-a", seed=1)
+    npytree.save_npy_tree(tmp_path, dims, w_np)
+    got = npytree.probe(tmp_path)
+    assert got == dims
+    raw = np.load(tmp_path / "encoder/conv1/weight.npy")
+    assert raw.dtype == np.float32 and list(raw[:3]) == [dims.n_audio_state, 80, 3]      # [dims..., values...]
+    assert list(np.load(tmp_path / "encoder/ln_post/eps.npy")) == [1.0, np.float32(1e-5)]   # scalars as [1.0, value]
+    (tmp_path / "encoder/n_mels.npy").unlink()
+    with pytest.raises(ffi.WbError) as e:
+        npytree.probe(tmp_path)
+    assert e.value.code == ffi.WB_ERR_STATE and "n_mels" in e.value.msg

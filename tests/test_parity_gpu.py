@@ -257,6 +257,21 @@ def test_fp16_kv_cache_matches_oracle_f16_mode(small, beam_size, depth):
         assert g == want
 
 
+def test_npy_tree_round_trip(small, tmp_path):
+    """wb_model_load_npy_tree (load::load_whisper, src/model/load.rs:295-310) == tensors set one by one."""
+    from whisper_burn_b200 import npytree
+    dims, w_np, _, sp, wh = small
+    npytree.save_npy_tree(tmp_path, dims, w_np)
+    wh2 = model.Whisper.from_npy_tree(tmp_path)
+    assert wh2.config == dims and wh2.weights_fp16_exact
+    mel = np.random.default_rng(3).standard_normal((1, 80, 200)).astype(np.float32) * 0.5
+    assert np.array_equal(wh.forward_encoder(mel), wh2.forward_encoder(mel))
+    wave = synth.waveform(40000, seed=2)
+    a = transcribe.Session(wh, 1, 1, 24).transcribe_windows([wave], sp, is_special_of(sp), beam_size=1, max_depth=16)
+    b = transcribe.Session(wh2, 1, 1, 24).transcribe_windows([wave], sp, is_special_of(sp), beam_size=1, max_depth=16)
+    assert a == b
+
+
 def test_launch_counter_counts_kernels(small):
     dims, _, _, sp, wh = small
     ffi.lib().wb_kernel_launch_count_reset()

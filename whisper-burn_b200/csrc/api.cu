@@ -182,6 +182,29 @@ int wb_model_set_tensor(wb_model* m, const char* path, const float* data, const 
     });
 }
 
+int wb_npy_tree_probe(const char* dir, wb_dims* dims_out) {
+    return guarded([&] {
+        WB_REQUIRE(dir && dims_out, "npy_tree_probe: null pointer");
+        wb::npy_tree_probe(dir, *dims_out);
+    });
+}
+
+int wb_model_load_npy_tree(const char* dir, int device, int ln_eps_outside, wb_model** out) {
+    return guarded([&] {
+        WB_REQUIRE(dir && out, "model_load_npy_tree: null pointer");
+        wb_dims dims{};
+        wb::npy_tree_probe(dir, dims);
+        require_device(device);
+        std::unique_ptr<wb_model> m(new wb_model());
+        m->impl.dims = dims;
+        m->impl.device = device;
+        m->impl.ln_eps_outside = ln_eps_outside ? 1 : 0;
+        wb::npy_tree_load(m->impl, dir);
+        wb::model_finalize(m->impl);
+        *out = m.release();
+    });
+}
+
 int wb_model_set_layernorm_eps_mode(wb_model* m, int outside) {
     return guarded([&] {
         WB_REQUIRE(m != nullptr, "null model");

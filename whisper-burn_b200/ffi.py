@@ -48,6 +48,8 @@ SYMBOLS = {
     "wb_prep_audio_dev": (C.c_int, [C.c_int, _P, C.c_int64, C.c_int64, _P, _I64]),
     "wb_model_create": (C.c_int, [C.POINTER(Dims), C.c_int, C.POINTER(_P)]),
     "wb_model_set_tensor": (C.c_int, [_P, C.c_char_p, _F, _I64, C.c_int]),
+    "wb_npy_tree_probe": (C.c_int, [C.c_char_p, C.POINTER(Dims)]),
+    "wb_model_load_npy_tree": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(_P)]),
     "wb_model_set_layernorm_eps_mode": (C.c_int, [_P, C.c_int]),
     "wb_model_finalize": (C.c_int, [_P]),
     "wb_model_destroy": (None, [_P]),

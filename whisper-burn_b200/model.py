@@ -49,6 +49,17 @@ class Whisper:
             self._h = None
             raise
 
+    @classmethod
+    def from_npy_tree(cls, directory, device: int = 0, ln_eps_outside: bool = True) -> "Whisper":
+        """model::load::load_whisper (load.rs:295-310): the npy tree python/dump.py writes."""
+        dims = ffi.Dims()
+        ffi.check(ffi.lib().wb_npy_tree_probe(str(directory).encode(), C.byref(dims)))
+        self = cls.__new__(cls)
+        self.config = WhisperConfig(*[getattr(dims, f) for f, _ in ffi.Dims._fields_])
+        self._h = C.c_void_p()
+        ffi.check(ffi.lib().wb_model_load_npy_tree(str(directory).encode(), device, 1 if ln_eps_outside else 0, C.byref(self._h)))
+        return self
+
     def close(self):
         if getattr(self, "_h", None):
             ffi.lib().wb_model_destroy(self._h)
