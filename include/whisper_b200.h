@@ -161,6 +161,12 @@ int wb_transcribe_windows_dev(wb_session* s, const float* wave_dev, const int64_
 int wb_waveform_to_tokens(wb_session* s, const float* waveform, int64_t n_samples, int64_t sample_rate,
                           int beam_size, int max_depth, const wb_special_ids* ids, const uint8_t* is_special,
                           int64_t* tokens_out, int64_t capacity, int64_t* n_tokens_out);
+/* The same for n_waveforms independent waveforms at once (the unit BASELINE.json shards over GPUs: "8x30 s chunks
+ * batched"): the windows of all waveforms are decoded in one batch, each waveform's windows are merged in order.
+ * tokens_out is [n_waveforms][capacity], n_tokens_out [n_waveforms]. */
+int wb_waveforms_to_tokens(wb_session* s, const float* const* waveforms, const int64_t* n_samples, int64_t n_waveforms,
+                           int64_t sample_rate, int beam_size, int max_depth, const wb_special_ids* ids,
+                           const uint8_t* is_special, int64_t* tokens_out, int64_t capacity, int64_t* n_tokens_out);
 /* transcribe.rs:114-138: number of windows and their [start, end) bounds */
 int64_t wb_window_count(int64_t n_samples, int64_t sample_rate, int64_t window_len);
 int wb_window_bounds(int64_t n_samples, int64_t sample_rate, int64_t window_len, int64_t* starts, int64_t* ends);

@@ -272,6 +272,15 @@ def test_npy_tree_round_trip(small, tmp_path):
     assert a == b
 
 
+def test_batched_waveforms_equal_one_by_one(small):
+    """wb_waveforms_to_tokens (all windows in one batch) == wb_waveform_to_tokens per waveform (transcribe.rs:23-74)."""
+    dims, _, _, sp, wh = small
+    waves = [synth.waveform(60000 + 9000 * i, seed=20 + i) for i in range(3)]
+    sess = transcribe.Session(wh, 4, 1, 24)
+    one = [sess.waveform_to_tokens(w, sp, is_special_of(sp), 16000, 1, 12) for w in waves]
+    assert sess.waveforms_to_tokens(waves, sp, is_special_of(sp), 16000, 1, 12) == one
+
+
 def test_launch_counter_counts_kernels(small):
     dims, _, _, sp, wh = small
     ffi.lib().wb_kernel_launch_count_reset()

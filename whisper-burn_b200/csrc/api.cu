@@ -407,42 +407,69 @@ int wb_window_bounds(int64_t n_samples, int64_t sample_rate, int64_t window_len,
     });
 }
 
+// windows of ALL waveforms are decoded together in batches of the session's capacity (they are independent,
+// SURVEY.md F9), then each waveform's windows are merged in order exactly like the reference's sequential
+// loop (transcribe.rs:42-71)
+static void waveforms_to_tokens(wb::Session& S, const float* const* waveforms, const int64_t* n_samples, int64_t n_waveforms,
+                                int64_t sample_rate, int beam_size, int max_depth, const wb_special_ids& ids,
+                                const uint8_t* is_special, std::vector<std::vector<int64_t>>& out) {
+    const int64_t window_len = wb_max_waveform_samples(S.m->dims.n_audio_ctx - wb::MEL_PADDING);   // transcribe.rs:32-34
+    std::vector<const float*> ptrs;
+    std::vector<int64_t> lens;
+    std::vector<int> owner;
+    for (int64_t w = 0; w < n_waveforms; ++w)
+        for (const auto& b : wb::window_bounds(n_samples[w], sample_rate, window_len)) {
+            ptrs.push_back(waveforms[w] + b.first);
+            lens.push_back(b.second - b.first);
+            owner.push_back((int)w);
+        }
+    out.assign((size_t)n_waveforms, {});
+    for (size_t b0 = 0; b0 < ptrs.size(); b0 += (size_t)S.max_windows) {
+        const size_t nb = std::min(ptrs.size() - b0, (size_t)S.max_windows);
+        S.encode_waveforms_host(ptrs.data() + b0, lens.data() + b0, (int64_t)nb);
+        std::vector<std::vector<int64_t>> toks;
+        wb::transcribe_windows(S, beam_size, max_depth, ids, is_special, toks);
+        for (size_t i = 0; i < nb; ++i) {
+            std::vector<int64_t>& tokens = out[(size_t)owner[b0 + i]];
+            const auto& nt = toks[i];
+            int64_t pi = 0, ci = 0;
+            if (wb::find_chunk_overlap(tokens.data(), (int64_t)tokens.size(), nt.data(), (int64_t)nt.size(), 40, 3, &pi, &ci)) {
+                tokens.resize((size_t)pi);                                    // transcribe.rs:59-60
+                tokens.insert(tokens.end(), nt.begin() + ci, nt.end());
+            } else {
+                tokens.insert(tokens.end(), nt.begin(), nt.end());
+            }
+        }
+    }
+    collect_timings(S);
+}
+
 int wb_waveform_to_tokens(wb_session* s, const float* waveform, int64_t n_samples, int64_t sample_rate, int beam_size,
                           int max_depth, const wb_special_ids* ids, const uint8_t* is_special, int64_t* tokens_out,
                           int64_t capacity, int64_t* n_tokens_out) {
     return guarded([&] {
         WB_REQUIRE(s && waveform && ids && is_special && tokens_out && n_tokens_out, "waveform_to_tokens: null pointer");
-        wb::Session& S = *s->impl;
-        const int64_t window_len = wb_max_waveform_samples(S.m->dims.n_audio_ctx - wb::MEL_PADDING);   // transcribe.rs:32-34
-        const auto bounds = wb::window_bounds(n_samples, sample_rate, window_len);
-        std::vector<int64_t> tokens;
-        // windows are independent: decode them in batches of the session's capacity,
-        // then merge in order exactly like the reference's sequential loop (transcribe.rs:42-71)
-        for (size_t b0 = 0; b0 < bounds.size(); b0 += (size_t)S.max_windows) {
-            const size_t nb = std::min(bounds.size() - b0, (size_t)S.max_windows);
-            std::vector<const float*> ptrs(nb);
-            std::vector<int64_t> lens(nb);
-            for (size_t i = 0; i < nb; ++i) {
-                ptrs[i] = waveform + bounds[b0 + i].first;
-                lens[i] = bounds[b0 + i].second - bounds[b0 + i].first;
-            }
-            S.encode_waveforms_host(ptrs.data(), lens.data(), (int64_t)nb);
-            std::vector<std::vector<int64_t>> toks;
-            wb::transcribe_windows(S, beam_size, max_depth, *ids, is_special, toks);
-            for (const auto& nt : toks) {
-                int64_t pi = 0, ci = 0;
-                if (wb::find_chunk_overlap(tokens.data(), (int64_t)tokens.size(), nt.data(), (int64_t)nt.size(), 40, 3, &pi, &ci)) {
-                    tokens.resize((size_t)pi);                                    // transcribe.rs:59-60
-                    tokens.insert(tokens.end(), nt.begin() + ci, nt.end());
-                } else {
-                    tokens.insert(tokens.end(), nt.begin(), nt.end());
-                }
-            }
+        std::vector<std::vector<int64_t>> out;
+        waveforms_to_tokens(*s->impl, &waveform, &n_samples, 1, sample_rate, beam_size, max_depth, *ids, is_special, out);
+        WB_REQUIRE((int64_t)out[0].size() <= capacity, "tokens_out capacity too small");
+        std::memcpy(tokens_out, out[0].data(), out[0].size() * sizeof(int64_t));
+        *n_tokens_out = (int64_t)out[0].size();
+    });
+}
+
+int wb_waveforms_to_tokens(wb_session* s, const float* const* waveforms, const int64_t* n_samples, int64_t n_waveforms,
+                           int64_t sample_rate, int beam_size, int max_depth, const wb_special_ids* ids,
+                           const uint8_t* is_special, int64_t* tokens_out, int64_t capacity, int64_t* n_tokens_out) {
+    return guarded([&] {
+        WB_REQUIRE(s && waveforms && n_samples && ids && is_special && tokens_out && n_tokens_out, "waveforms_to_tokens: null pointer");
+        WB_REQUIRE(n_waveforms >= 1, "waveforms_to_tokens: n_waveforms must be >= 1");
+        std::vector<std::vector<int64_t>> out;
+        waveforms_to_tokens(*s->impl, waveforms, n_samples, n_waveforms, sample_rate, beam_size, max_depth, *ids, is_special, out);
+        for (int64_t w = 0; w < n_waveforms; ++w) {
+            WB_REQUIRE((int64_t)out[(size_t)w].size() <= capacity, "tokens_out capacity (per waveform) too small");
+            std::memcpy(tokens_out + w * capacity, out[(size_t)w].data(), out[(size_t)w].size() * sizeof(int64_t));
+            n_tokens_out[w] = (int64_t)out[(size_t)w].size();
         }
-        collect_timings(S);
-        WB_REQUIRE((int64_t)tokens.size() <= capacity, "tokens_out capacity too small");
-        std::memcpy(tokens_out, tokens.data(), tokens.size() * sizeof(int64_t));
-        *n_tokens_out = (int64_t)tokens.size();
     });
 }
 

@@ -119,6 +119,21 @@ class Session:
                                                  C.byref(ids), ffi.u8ptr(sp), ffi.i64ptr(out), cap, C.byref(n)))
         return [int(t) for t in out[:n.value]]
 
+    def waveforms_to_tokens(self, waveforms: Sequence[np.ndarray], special, is_special: np.ndarray, sample_rate: int = 16000,
+                            beam_size: int = 5, max_depth: int = 100) -> List[List[int]]:
+        """Batched waveform_to_tokens: all windows of all waveforms decoded together (wb_waveforms_to_tokens)."""
+        ws = [np.ascontiguousarray(w, dtype=np.float32) for w in waveforms]
+        cap = (max(len(w) for w in ws) // 1000 + 2) * (4 + max_depth + 1) + 16
+        out = np.zeros((len(ws), cap), dtype=np.int64)
+        n = np.zeros(len(ws), dtype=np.int64)
+        ptrs = (C.c_void_p * len(ws))(*[w.ctypes.data for w in ws])
+        lens = np.array([len(w) for w in ws], dtype=np.int64)
+        ids = ffi.SpecialIds(special.sot, special.lang, special.transcribe, special.notimestamps, special.eot)
+        sp = np.ascontiguousarray(is_special, dtype=np.uint8)
+        ffi.check(ffi.lib().wb_waveforms_to_tokens(self._h, ptrs, ffi.i64ptr(lens), len(ws), sample_rate, beam_size, max_depth,
+                                                  C.byref(ids), ffi.u8ptr(sp), ffi.i64ptr(out), cap, ffi.i64ptr(n)))
+        return [[int(t) for t in out[i, :n[i]]] for i in range(len(ws))]
+
     def last_timings_ms(self):
         buf = np.zeros(4, dtype=np.float32)
         ffi.check(ffi.lib().wb_session_last_timings(self._h, ffi.fptr(buf)))
