@@ -180,6 +180,9 @@ int wb_find_chunk_overlap(const int64_t* prev, int64_t n_prev, const int64_t* cu
 int64_t wb_beam_get_top_elements(const double* scores, int64_t n, int64_t num, int64_t* idx_out);
 
 /* ---- measurement ----------------------------------------------------------------------------- */
+/* Diagnostics: which persistent decoder kernel the last decode launch used: 4 = cluster/DSMEM (decoder4.cu), 5 = batched
+ * tensor-core (decoder5.cu), 3 = grid-barrier FMA fallback (decoder3.cu), 0 = none yet. */
+int wb_session_last_decoder(const wb_session* s);
 /* kernels launched by this library on this thread's sessions since the last reset */
 int64_t wb_kernel_launch_count(void);
 void wb_kernel_launch_count_reset(void);

@@ -41,6 +41,13 @@ def tiny():
     return dims, w_np, w_t, synth.special_tokens(dims), model.Whisper(dims, w_np)
 
 
+@pytest.fixture(scope="module")
+def wide():
+    """d = 256: the configuration class the batched tensor-core decoder (decoder5.cu) covers (small.en / medium / large)."""
+    dims, w_np, w_t = synth.make_weights("test-c", seed=0)
+    return dims, w_np, w_t, synth.special_tokens(dims), model.Whisper(dims, w_np)
+
+
 # ---------------------------------------------------------------- log-mel (audio.rs)
 @pytest.mark.parametrize("n,kind", [(400, "noise"), (401, "mix"), (559, "mix"), (16000, "chirp"), (16000, "mix"),
                                     (4000, "click"), (98882, "mix"), (238559, "mix"), (480000, "mix")])
@@ -217,6 +224,7 @@ def test_tiny_en_chunk_greedy_golden(tiny):
     sess = transcribe.Session(wh, max_windows=3, max_beams=5, max_text_len=105)
     waves = [chunk[s:e] for s, e in te["bounds"]]
     got = sess.transcribe_windows(waves, sp, is_special_of(sp), beam_size=1, max_depth=100)
+    assert sess.last_decoder() == 4
     assert got == te["windows"], f"min oracle margin {te['min_margin']}"
     merged = sess.waveform_to_tokens(chunk, sp, is_special_of(sp), beam_size=1, max_depth=100)
     assert merged == te["merged"]
@@ -279,6 +287,42 @@ def test_batched_waveforms_equal_one_by_one(small):
     sess = transcribe.Session(wh, 4, 1, 24)
     one = [sess.waveform_to_tokens(w, sp, is_special_of(sp), 16000, 1, 12) for w in waves]
     assert sess.waveforms_to_tokens(waves, sp, is_special_of(sp), 16000, 1, 12) == one
+
+
+@pytest.mark.parametrize("kv", ["f32", "f16"])
+def test_batched_tensor_core_decoder_greedy_vs_oracle(wide, kv):
+    """decoder5.cu (mma.sync swap-AB, hi/lo fp16 split of the activations): 10 windows decoded in one batch,
+    token ids identical to the oracle's per-window greedy search (transcribe.rs:148-383)."""
+    dims, _, w_t, sp, wh = wide
+    waves = [synth.waveform(30000 + 7000 * i, seed=40 + i) for i in range(10)]
+    sess = transcribe.Session(wh, max_windows=10, max_beams=1, max_text_len=4 + 14 + 1,
+                              kv_dtype=ffi.WB_KV_F16 if kv == "f16" else ffi.WB_KV_F32)
+    got = sess.transcribe_windows(waves, sp, is_special_of(sp), beam_size=1, max_depth=14)
+    assert sess.last_decoder() == 5
+    opts = o_model.OracleOptions(kv_dtype=kv)
+    for g, wv in zip(got, waves):
+        want = o_tr.mels_to_tokens(w_t, dims, sp, o_audio.prep_audio(torch.from_numpy(wv)[None]), beam_size=1, max_depth=14, opts=opts)
+        assert g == want
+    # batching invariance across decoders: one window alone takes the same path with a single n-tile
+    solo = transcribe.Session(wh, max_windows=1, max_beams=1, max_text_len=4 + 14 + 1, kv_dtype=ffi.WB_KV_F16 if kv == "f16" else ffi.WB_KV_F32)
+    assert solo.transcribe_windows(waves[3:4], sp, is_special_of(sp), beam_size=1, max_depth=14)[0] == got[3]
+
+
+def test_batched_tensor_core_decoder_beams_and_logits(wide):
+    dims, _, w_t, sp, wh = wide
+    waves = [synth.waveform(42000 + 9000 * i, seed=60 + i) for i in range(3)]
+    sess = transcribe.Session(wh, max_windows=3, max_beams=5, max_text_len=4 + 8 + 1)
+    got = sess.transcribe_windows(waves, sp, is_special_of(sp), beam_size=5, max_depth=8)      # 15 rows, ancestry table
+    assert sess.last_decoder() == 5
+    for g, wv in zip(got, waves):
+        assert g == o_tr.mels_to_tokens(w_t, dims, sp, o_audio.prep_audio(torch.from_numpy(wv)[None]), beam_size=5, max_depth=8)
+    # stateless forward_decoder (full logits) against the oracle's decoder (mod.rs:131-157)
+    sess.encode_waveforms(waves[:1])
+    enc = sess.get_encoder_output(0)[None]
+    toks = np.asarray([sp.prompt() + [17, 300, 5]], np.int64)
+    lg = wh.forward_decoder(toks, enc)
+    ref = o_model.forward_decoder(w_t, dims, torch.from_numpy(toks), torch.from_numpy(enc)).numpy()
+    assert rel_to_scale(lg, ref) < 2e-5
 
 
 def test_launch_counter_counts_kernels(small):

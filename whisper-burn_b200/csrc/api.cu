@@ -492,6 +492,8 @@ int64_t wb_beam_get_top_elements(const double* scores, int64_t n, int64_t num, i
     return (int64_t)top.size();
 }
 
+int wb_session_last_decoder(const wb_session* s) { return s ? s->impl->last_decoder : -1; }
+
 int64_t wb_kernel_launch_count(void) { return wb::g_launch_count; }
 void wb_kernel_launch_count_reset(void) { wb::g_launch_count = 0; }
 

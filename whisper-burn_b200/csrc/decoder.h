@@ -198,6 +198,9 @@ struct Dec3Args {
     float lnf_eps = 1e-5f;
     // state
     float *x = nullptr, *q = nullptr, *att = nullptr, *hid = nullptr;
+    float *x2 = nullptr, *ypart = nullptr;   // decoder5.cu: second residual buffer (ping-pong), MLP2 partial sums [4][R][d]
+    float* lgbuf = nullptr;                 // decoder5.cu: [R][V] logits scratch (== logits_out when that is requested)
+    int lg_slices = 1;                      // decoder5.cu: vocabulary slices per row in the softmax / candidate stage
     void *kc = nullptr, *vc = nullptr;    // [L][Rmax][t_max][d]  fp32 or fp16 (kv_half)
     const void* ckv = nullptr;            // [L][Mcap][2d]
     int kv_half = 0;
@@ -229,6 +232,8 @@ struct Dec3Args {
 void launch_dec3(const Dec3Args& a, int n_ctas, bool w_half, cudaStream_t st);
 // cluster / DSMEM version (decoder4.cu); returns false when the configuration is not covered
 bool launch_dec4(const Dec3Args& a, bool w_half, cudaStream_t st);
+// batched tensor-core version (decoder5.cu); returns false when the configuration is not covered
+bool launch_dec5(const Dec3Args& a, int n_ctas, bool w_half, cudaStream_t st);
 
 void launch_dec2_self(const Dec2SelfArgs& a, int H, bool w_half, cudaStream_t st);
 void launch_dec2_cross(const Dec2CrossArgs& a, int H, int S, bool w_half, cudaStream_t st);

@@ -55,7 +55,7 @@ Session::Session(Model* model, int64_t max_w, int64_t max_b, int64_t max_text_le
     }
     if (kv == WB_KV_F16) { kc16.alloc((size_t)L * Rmax * t_max * d); vc16.alloc((size_t)L * Rmax * t_max * d); }
     else { kc.alloc((size_t)L * Rmax * t_max * d); vc.alloc((size_t)L * Rmax * t_max * d); }
-    dx.alloc((size_t)Rmax * d); dq.alloc((size_t)Rmax * d); dhid.alloc((size_t)Rmax * 4 * d);
+    dx.alloc((size_t)Rmax * d); dx2.alloc((size_t)Rmax * d); dq.alloc((size_t)Rmax * d); dhid.alloc((size_t)Rmax * 4 * d);
     logits.alloc((size_t)Rmax * V);
     part_o.alloc((size_t)Rmax * H * n_splits * 64); part_m.alloc((size_t)Rmax * H * n_splits);
     part_l.alloc((size_t)Rmax * H * n_splits);
@@ -448,6 +448,8 @@ void Session::launch_v3(int R_, int pos0, int n_steps, int logits_from, bool use
     a.E = m->fp16_exact ? (const void*)m->tok_emb16 : (const void*)m->tok_emb32;
     a.lnf_g = m->dec_ln.g; a.lnf_b = m->dec_ln.b; a.lnf_eps = m->dec_ln.eps;
     a.x = dx.p; a.q = dq.p; a.att = datt.p; a.hid = dhid.p;
+    a.x2 = dx2.p; a.ypart = ypart.p; a.lgbuf = logits.p;
+    a.lg_slices = std::max(1, std::min(16, n_sm / std::max(1, R_)));
     a.kv_half = kv_dtype == WB_KV_F16 ? 1 : 0;
     if (a.kv_half) { a.kc = kc16.p; a.vc = vc16.p; a.ckv = ckv16.p; } else { a.kc = kc.p; a.vc = vc.p; a.ckv = ckv.p; }
     a.row_window = row_window.p; a.win_row_off = d_win_row_off.p; a.win_T = d_win_T.p;
@@ -468,7 +470,12 @@ void Session::launch_v3(int R_, int pos0, int n_steps, int logits_from, bool use
         a.trace_cap = 1 << 16;
     }
     WB_CUDA(cudaMemsetAsync(d3_bar.p, 0, 2 * sizeof(unsigned int), st));   // monotonic barrier counter starts at 0
-    if (!(dec_version == 4 && launch_dec4(a, m->fp16_exact, st))) launch_dec3(a, n_sm, m->fp16_exact, st);
+    last_decoder = 3;
+    if (dec_version == 4) {
+        if (launch_dec4(a, m->fp16_exact, st)) last_decoder = 4;
+        else if (launch_dec5(a, n_sm, m->fp16_exact, st)) last_decoder = 5;
+    }
+    if (last_decoder == 3) launch_dec3(a, n_sm, m->fp16_exact, st);
     if (a.trace) {
         std::vector<unsigned long long> h(1 << 16);
         WB_CUDA(cudaStreamSynchronize(st));

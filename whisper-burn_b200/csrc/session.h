@@ -46,7 +46,7 @@ struct Session {
     // ---- device: decode state
     DevBuf<float> kc, vc;  // [L][Rmax][t_max][d] self keys (scaled) / values
     DevBuf<__half> kc16, vc16, ckv16;   // fp16 caches (WB_KV_F16)
-    DevBuf<float> dx, dq, dhid, logits;
+    DevBuf<float> dx, dx2, dq, dhid, logits;
     DevBuf<float> part_o, part_m, part_l;
     DevBuf<int> tokens, lengths, cur_tok, finished, row_window, anc0, anc1, parent, pos, n_unfinished, topk_id;
     DevBuf<float> topk_lp;
@@ -64,7 +64,8 @@ struct Session {
     float last_ms[4] = {0, 0, 0, 0};
     int64_t last_steps = 0;
     // fused decoder step (decoder2.cu): partial buffers, tickets, switches
-    int dec_version = 4;         // 4 = cluster/DSMEM persistent kernel (decoder4.cu) with fallback to 3 = grid-barrier
+    int last_decoder = 0;        // which persistent decoder the last launch used (3, 4 or 5); 0 = none yet / per-op path
+    int dec_version = 4;         // 4 = cluster/DSMEM kernel (decoder4.cu, small batches) / batched tensor-core kernel (decoder5.cu), fallback 3 = grid-barrier
                                  // persistent kernel (decoder3.cu); WB200_DECODER=1|2|3 select the older paths:
                                  // unfused (decoder.cu) / fused-per-layer (decoder2.cu) paths for A/B testing
     int n_sm = 0;

@@ -134,6 +134,9 @@ class Session:
                                                   C.byref(ids), ffi.u8ptr(sp), ffi.i64ptr(out), cap, ffi.i64ptr(n)))
         return [[int(t) for t in out[i, :n[i]]] for i in range(len(ws))]
 
+    def last_decoder(self) -> int:
+        return int(ffi.lib().wb_session_last_decoder(self._h))
+
     def last_timings_ms(self):
         buf = np.zeros(4, dtype=np.float32)
         ffi.check(ffi.lib().wb_session_last_timings(self._h, ffi.fptr(buf)))
