@@ -24,11 +24,12 @@ print("decoder", sess.last_decoder(), "rows", len(waves))
 t = np.loadtxt("gpurun_out/d3_trace.txt", dtype=np.uint64).astype(np.int64)
 print("stamps", len(t), "total ms", (t[-1] - t[0]) / 1e6)
 L = dims.n_text_layer
-tail = ["logits", "softmax", "finish"] if sess.last_decoder() == 5 else ["logits", "finish"]
-per_step = 2 * (8 * L + len(tail))
-names = [f"L{l}.{n}" for l in range(L) for n in ("qkv", "self", "out", "cq", "cross", "cout", "mlp1", "mlp2")] + tail
+kinds = ["ln1", "qkv", "self", "out", "ln2", "cq", "cross", "cout", "ln3", "mlp1", "mlp2"]
+tail = ["lnf", "logits", "softmax", "finish"]
+NK = len(kinds)
+per_step = 2 * (NK * L + len(tail))
 body = t[1:]
-prefill = 3 * 2 * (8 * L)
+prefill = 3 * 2 * (NK * L)
 steps = body[prefill:]
 n = len(steps) // per_step
 steps = steps[:n * per_step].reshape(n, per_step // 2, 2)
@@ -36,11 +37,9 @@ prev_end = np.concatenate([[body[prefill - 1]], steps[:-1, -1, 1]])
 stage = steps[:, :, 0] - np.concatenate([prev_end[:, None], steps[:, :-1, 1]], axis=1)
 barr = steps[:, :, 1] - steps[:, :, 0]
 print(f"steps {n}; mean step us {(steps[:, -1, 1] - prev_end).mean() / 1e3:.1f}")
-ns = len(names)
-kinds = ["qkv", "self", "out", "cq", "cross", "cout", "mlp1", "mlp2"]
 for k, nm in enumerate(kinds):
-    idx = [l * 8 + k for l in range(L)]
+    idx = [l * NK + k for l in range(L)]
     print(f"{nm:8s} stage {stage[:, idx].mean() / 1e3:7.2f} us   barrier(wait) {barr[:, idx].mean() / 1e3:7.2f} us   (mean over layers)")
 for i, nm in enumerate(tail):
-    print(f"{nm:8s} stage {stage[:, 8 * L + i].mean() / 1e3:7.2f} us   barrier(wait) {barr[:, 8 * L + i].mean() / 1e3:7.2f} us")
+    print(f"{nm:8s} stage {stage[:, NK * L + i].mean() / 1e3:7.2f} us   barrier(wait) {barr[:, NK * L + i].mean() / 1e3:7.2f} us")
 print("sum stage", stage.mean(0).sum() / 1e3, "sum barrier", barr.mean(0).sum() / 1e3)

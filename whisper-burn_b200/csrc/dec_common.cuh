@@ -424,6 +424,104 @@ __device__ __forceinline__ void attn_warp(const float* q_smem, int n_keys, int f
     }
 }
 
+// Ring variant for long key ranges (cross attention over up to 1500 encoder positions): K/V go global -> shared
+// memory with cp.async into a per-warp ring (lane-private slots, no registers held while in flight), NSTG-1 batches
+// of 8 keys in flight per warp, so the loop runs at memory throughput instead of one memory latency per batch.
+// ring: this warp's NSTG * 8 * NV2 * 32 uint4 (NV2 = 16-byte vectors of K plus V per lane and key: 8 fp32 / 4 fp16).
+template <int NSTG, typename KF, typename VF>
+__device__ __forceinline__ void attn_warp_ring(const float* q_smem, int n_keys, int first, int stride, KF&& kptr, VF&& vptr,
+                                               uint4* ring, AttnAcc& A) {
+    using KT = typename std::remove_cv<typename std::remove_pointer<decltype(kptr(0))>::type>::type;
+    constexpr int NV = sizeof(KT) == 4 ? 4 : 2;   // 16-byte vectors per lane and tensor (16 dims)
+    const int lane = threadIdx.x & 31, sub = lane >> 2, l4 = lane & 3;
+    float q[16];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float4 t = *reinterpret_cast<const float4*>(q_smem + l4 * 16 + c * 4);
+        q[c * 4] = t.x; q[c * 4 + 1] = t.y; q[c * 4 + 2] = t.z; q[c * 4 + 3] = t.w;
+    }
+    A.m = -INFINITY;
+    A.l = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) A.o[c] = 0.0f;
+    const int span = stride * 8;
+    const int n_it = n_keys > first ? (n_keys - first + span - 1) / span : 0;
+    auto issue = [&](int it) {
+        const int j = first + (it * 8 + sub) * stride;
+        if (it < n_it && j < n_keys) {
+            uint4* dst = ring + (it % NSTG) * (2 * NV * 32) + lane;   // vector c of this lane at [c][lane]: conflict-free
+            const uint4* kp = reinterpret_cast<const uint4*>(kptr(j)) + l4 * NV;
+            const uint4* vp = reinterpret_cast<const uint4*>(vptr(j)) + l4 * NV;
+#pragma unroll
+            for (int c = 0; c < NV; ++c) {
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + c * 32)), "l"(kp + c) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + (NV + c) * 32)), "l"(vp + c) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");   // always: keeps the group count uniform
+    };
+#pragma unroll
+    for (int s = 0; s < NSTG - 1; ++s) issue(s);
+#pragma unroll 1
+    for (int it = 0; it < n_it; ++it) {
+        issue(it + NSTG - 1);
+        asm volatile("cp.async.wait_group %0;" ::"n"(NSTG - 1) : "memory");
+        const int j = first + (it * 8 + sub) * stride;
+        if (j < n_keys) {
+            const uint4* src = ring + (it % NSTG) * (2 * NV * 32) + lane;
+            float kf[16], vf[16];
+            if constexpr (sizeof(KT) == 4) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const uint4 kk = src[c * 32], vv = src[(4 + c) * 32];
+                    kf[c * 4] = __uint_as_float(kk.x); kf[c * 4 + 1] = __uint_as_float(kk.y); kf[c * 4 + 2] = __uint_as_float(kk.z); kf[c * 4 + 3] = __uint_as_float(kk.w);
+                    vf[c * 4] = __uint_as_float(vv.x); vf[c * 4 + 1] = __uint_as_float(vv.y); vf[c * 4 + 2] = __uint_as_float(vv.z); vf[c * 4 + 3] = __uint_as_float(vv.w);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    float w[8];
+                    cvt8(src[c * 32], w);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) kf[c * 8 + e] = w[e];
+                    cvt8(src[(2 + c) * 32], w);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) vf[c * 8 + e] = w[e];
+                }
+            }
+            float s = 0.0f;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) s = fmaf(q[c], kf[c], s);
+            s += __shfl_xor_sync(0xfu << (lane & 28), s, 1);
+            s += __shfl_xor_sync(0xfu << (lane & 28), s, 2);
+            const float mn = fmaxf(A.m, s);
+            const float corr = expf(A.m - mn);
+            const float e = expf(s - mn);
+            A.l = A.l * corr + e;
+            A.m = mn;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) A.o[c] = fmaf(e, vf[c], A.o[c] * corr);
+        }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
+#pragma unroll
+    for (int off = 4; off < 32; off <<= 1) {   // merge the 8 key sub-groups
+        const float m2 = __shfl_xor_sync(0xffffffffu, A.m, off);
+        const float l2 = __shfl_xor_sync(0xffffffffu, A.l, off);
+        const float mn = fmaxf(A.m, m2);
+        const float c1 = A.m > -INFINITY ? expf(A.m - mn) : 0.0f;
+        const float c2 = m2 > -INFINITY ? expf(m2 - mn) : 0.0f;
+        A.l = A.l * c1 + l2 * c2;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const float o2 = __shfl_xor_sync(0xffffffffu, A.o[c], off);
+            A.o[c] = A.o[c] * c1 + o2 * c2;
+        }
+        A.m = mn;
+    }
+}
+
 // one (query row, head) unit handled by the 8 warps of a CTA (keys strided over warps); returns the merged
 // (M, L) and the unnormalised output in out[64] (shared memory), valid after the trailing __syncthreads().
 template <typename KF, typename VF>

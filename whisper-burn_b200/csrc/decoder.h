@@ -185,6 +185,20 @@ struct Dec3Layer {
     const void *Wqkv, *Wo, *Wcq, *Wco, *W1, *W2;     // [N][K] fp16 or fp32
     const float *bqkv, *bo, *bcq, *bco, *b1, *b2;
 };
+// decoder5.cu stage descriptors, built on the host: entry [l * 16 + slot] for the stage slots of layer l (LN1, QKV, SELF, OUT, LN2,
+// CQ, CROSS, COUT, LN3, MLP1, MLP2 = 0..10), entries [L * 16 + 11] / [L * 16 + 12] for the final LayerNorm and the logits.
+enum { D5_KIND_LN = 0, D5_KIND_ATTN, D5_KIND_GEMM };
+enum { D5_ST_LN_EMB = 0, D5_ST_LN_FOLD, D5_ST_LN_FOLD_NOPUB, D5_ST_LN_X, D5_ST_PLANES, D5_ST_CROSS };
+enum { D5_EM_QKV = 0, D5_EM_RESID, D5_EM_CQ, D5_EM_HID, D5_EM_PART, D5_EM_LOGITS };
+struct Dec5Desc {
+    int kind = D5_KIND_ATTN;
+    const void* W = nullptr;       // [N][n_slabs * d] fp16
+    const float* bias = nullptr;
+    int N = 0, n_slabs = 1, stage = 0, emit = 0;
+    const float *g = nullptr, *b = nullptr;   // LayerNorm parameters (D5_KIND_LN)
+    float eps = 0.0f;
+    int src = 0;                   // input planes of a linear stage: 1 = attention output, 2 = MLP hidden, 3 = LayerNorm output
+};
 struct Dec3Args {
     int R = 0, Rmax = 0, d = 0, H = 0, L = 0, V = 0, t_max = 0;
     int64_t Mcap = 0;
@@ -199,6 +213,8 @@ struct Dec3Args {
     // state
     float *x = nullptr, *q = nullptr, *att = nullptr, *hid = nullptr;
     float *x2 = nullptr, *ypart = nullptr;   // decoder5.cu: second residual buffer (ping-pong), MLP2 partial sums [4][R][d]
+    const Dec5Desc* d5 = nullptr;           // decoder5.cu: device array [L * 8 + 1]
+    void *att_pl = nullptr, *hid_pl = nullptr;   // decoder5.cu: fragment-order fp16 hi/lo planes of the attention output / MLP hidden layer
     float* lgbuf = nullptr;                 // decoder5.cu: [R][V] logits scratch (== logits_out when that is requested)
     int lg_slices = 1;                      // decoder5.cu: vocabulary slices per row in the softmax / candidate stage
     void *kc = nullptr, *vc = nullptr;    // [L][Rmax][t_max][d]  fp32 or fp16 (kv_half)
@@ -234,6 +250,7 @@ void launch_dec3(const Dec3Args& a, int n_ctas, bool w_half, cudaStream_t st);
 bool launch_dec4(const Dec3Args& a, bool w_half, cudaStream_t st);
 // batched tensor-core version (decoder5.cu); returns false when the configuration is not covered
 bool launch_dec5(const Dec3Args& a, int n_ctas, bool w_half, cudaStream_t st);
+size_t dec5_plane_uint4(int d);   // uint4 elements of one global activation plane
 
 void launch_dec2_self(const Dec2SelfArgs& a, int H, bool w_half, cudaStream_t st);
 void launch_dec2_cross(const Dec2CrossArgs& a, int H, int S, bool w_half, cudaStream_t st);

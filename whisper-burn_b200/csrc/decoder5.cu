@@ -1,4 +1,4 @@
-// Batched persistent decoder on the tensor cores (9..32 rows per launch: small.en / medium / large batches and beams).
+// Batched persistent decoder on the tensor cores (up to 32 rows per launch: small.en / medium / large batches and beams).
 //
 // Same single-launch structure, stage list and reference math as decoder3.cu (TextDecoder::forward
 // src/model/mod.rs:131-157, blocks :345-350, attention :428-533, MLP :376-382, search closure
@@ -7,16 +7,23 @@
 //   * a warp owns a 16-feature tile of W[N][K] (fp16, exact) and multiplies it with ALL rows of the batch:
 //     mma.sync.m16n8k16 with M = 16 output features, N = 8 batch rows per n-tile (up to 4 n-tiles), K = 16;
 //   * the fp32 activations are split into fp16 hi + fp16 (lo * 2^11) planes (22 mantissa bits; products with
-//     the fp16 weights are exact, accumulation is fp32) and staged in shared memory in FRAGMENT ORDER, so a B
-//     fragment is one conflict-free 16-byte shared load; the A fragments come straight from global memory
-//     as 16-byte loads (a K permutation inside each 32-column chunk makes 8 consecutive halves of a weight
-//     row the a0..a3 registers of two MMAs), prefetched BEFORE the grid barrier that precedes the stage;
+//     the fp16 weights are exact, accumulation is fp32) held in FRAGMENT ORDER, so a B fragment is one
+//     conflict-free 16-byte shared load.  Attention outputs and the MLP hidden layer are WRITTEN in that layout
+//     by their producers (global planes), so staging them is a plain cp.async copy; LayerNorm inputs are
+//     normalised from fp32 x by every CTA (warp per row, rows software-pipelined);
+//   * the A fragments come straight from global memory as 16-byte loads (a K permutation inside each
+//     32-column chunk makes 8 consecutive halves of a weight row the a0..a3 registers of two MMAs) and are
+//     prefetched BEFORE the grid barrier that precedes the stage: weights do not depend on activations;
 //   * the 8 warps of a CTA split K; partial tiles are reduced through shared memory in a fixed order;
 //   * MLP2 (K = 4d) is split over CTAs into 4 slabs of d: the partial sums are folded into x by the next
-//     consumer of x (deterministic order), so every stage is ONE dependent round trip behind its barrier;
+//     consumer of x (fixed order; the residual stream ping-pongs between two buffers so a folded row can
+//     never be folded twice);
 //   * logits: E[V][d] is streamed once through the same MMA path into an L2-resident [R][V] buffer; a second
 //     stage turns it into per-slice (max, sum-exp, top candidates) records, the finish stage is decoder3's.
-// Requirements: fp16-exact weights, d % 256 == 0, R <= 32.  Everything else falls back to decoder3.cu.
+// Code size matters: the layer loop must stay inside the instruction cache, so every building block (staging,
+// MMA tile, emit, attention) exists ONCE and the stages are driven by small descriptors (the first version
+// inlined six copies and ran 3x slower than its memory traffic explains).
+// Requirements: fp16-exact weights, d % 256 == 0, d <= 1280, R <= 32.  Everything else falls back to decoder3.cu.
 #include <cooperative_groups.h>
 #include <cuda_fp16.h>
 
@@ -26,15 +33,29 @@ namespace wb {
 
 namespace {
 
-constexpr int RED_LD = 20;   // padded feature stride of the cross-warp reduction buffer (conflict-free fragment stores)
-constexpr int MAXCH = 5;     // 32-column chunks per warp and slab: slab = d <= 1280 -> d / 256 <= 5
-constexpr int GC = 4;        // logits: chunks per prefetch group
+constexpr int RED_LD = 20;    // padded feature stride of the cross-warp reduction buffer (conflict-free fragment stores)
+constexpr int MAXCH = 5;      // 32-column chunks per warp and slab: slab = d <= 1280 -> d / 256 <= 5
+constexpr int GC = 4;         // logits: chunks per prefetch group
+constexpr int PL_ROWS = 32;   // rows of the global activation planes
+constexpr int RING_W = 16384; // attention: bytes of the per-warp K/V ring (aliases the activation planes, which are dead during attention)
+constexpr int DEC5_KC = 8;    // top candidates kept per (row, slice) record
+
+enum { ST_LN_EMB = D5_ST_LN_EMB, ST_LN_FOLD = D5_ST_LN_FOLD, ST_LN_FOLD_NOPUB = D5_ST_LN_FOLD_NOPUB, ST_LN_X = D5_ST_LN_X,
+       ST_PLANES = D5_ST_PLANES, ST_CROSS = D5_ST_CROSS };
+enum { EM_QKV = D5_EM_QKV, EM_RESID = D5_EM_RESID, EM_CQ = D5_EM_CQ, EM_HID = D5_EM_HID, EM_PART = D5_EM_PART, EM_LOGITS = D5_EM_LOGITS };
+
+using GemmDesc = Dec5Desc;   // host-built stage descriptors (decoder.h): no switch in the kernel, so the compiler cannot clone the stage body per case
 
 __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void bar_named(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 __device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 
@@ -48,195 +69,56 @@ __device__ __forceinline__ void split4(const float4 v, uint2& hi, uint2& lo) {
     lo = make_uint2(h2_bits(l01), h2_bits(l23));
 }
 
-// Fragment-order planes: element (row, col) of the staged [8*NT8][KS] activation slab lives in the uint4
-//   ((row / 8) * nchunks + col / 32) * 32 + (row % 8) * 4 + (col % 32) / 8,   halves (col % 8)
+// Fragment-order planes: element (row, col) of an activation matrix [rows][K] lives in the uint4
+//   ((row / 8) * (K / 32) + col / 32) * 32 + (row % 8) * 4 + (col % 32) / 8,   half (col % 8)
 // i.e. lane (g = row % 8, t) of the MMA finds the 8 halves x[row][chunk*32 + t*8 .. +8) in ONE 16-byte word.
+__device__ __forceinline__ int plane_idx(int nchunks, int row, int col) {
+    return ((row >> 3) * nchunks + (col >> 5)) * 32 + (row & 7) * 4 + ((col & 31) >> 3);
+}
 __device__ __forceinline__ void store_frag(uint4* xhi, uint4* xlo, int nchunks, int row, int col, const float4 v) {
     uint2 hi, lo;
     split4(v, hi, lo);
-    const int idx = ((row >> 3) * nchunks + (col >> 5)) * 32 + (row & 7) * 4 + ((col & 31) >> 3);
-    const int half = (col & 7) >> 2;
+    const int idx = plane_idx(nchunks, row, col), half = (col & 7) >> 2;
     reinterpret_cast<uint2*>(xhi + idx)[half] = hi;
     reinterpret_cast<uint2*>(xlo + idx)[half] = lo;
 }
-
-// LayerNorm (burn 0.9 form, dec_common.cuh stage_ln) of all 8*NT8 rows into the planes; warp per row, the row
-// stays in registers.  load(r, c4) returns the float4 at columns 4*c4.. of row r; rows >= R are zero.
-template <int NT8, typename LoadF>
-__device__ __forceinline__ void stage_ln_frag(LoadF&& load, int R, int d, const float* __restrict__ g, const float* __restrict__ b,
-                                              float eps, int eps_outside, uint4* xhi, uint4* xlo) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nv = d / 4, nchunks = d / 32;
-    for (int r = warp; r < NT8 * 8; r += NW) {
-        if (r >= R) {
-            for (int c = lane; c < nv; c += 32) store_frag(xhi, xlo, nchunks, r, c * 4, make_float4(0.f, 0.f, 0.f, 0.f));
-            continue;
-        }
-        float4 v[LN_V4];
-#pragma unroll
-        for (int i = 0; i < LN_V4; ++i) {
-            const int c = i * 32 + lane;
-            v[i] = c < nv ? load(r, c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        float sum = 0.0f;
-#pragma unroll
-        for (int i = 0; i < LN_V4; ++i) sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-        sum = warp_sum(sum);
-        const float mean = __fdiv_rn(sum, (float)d);
-        float q = 0.0f;
-#pragma unroll
-        for (int i = 0; i < LN_V4; ++i) {
-            const int c = i * 32 + lane;
-            if (c < nv) {
-                v[i].x = __fsub_rn(v[i].x, mean); v[i].y = __fsub_rn(v[i].y, mean);
-                v[i].z = __fsub_rn(v[i].z, mean); v[i].w = __fsub_rn(v[i].w, mean);
-                q = __fadd_rn(q, __fmul_rn(v[i].x, v[i].x)); q = __fadd_rn(q, __fmul_rn(v[i].y, v[i].y));
-                q = __fadd_rn(q, __fmul_rn(v[i].z, v[i].z)); q = __fadd_rn(q, __fmul_rn(v[i].w, v[i].w));
-            }
-        }
-        q = warp_sum(q);
-        const float var = __fdiv_rn(q, (float)d);
-        const float den = eps_outside ? __fadd_rn(__fsqrt_rn(var), eps) : __fsqrt_rn(__fadd_rn(var, eps));
-#pragma unroll
-        for (int i = 0; i < LN_V4; ++i) {
-            const int c = i * 32 + lane;
-            if (c < nv) {
-                const float4 g4 = __ldg(reinterpret_cast<const float4*>(g) + c);
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(b) + c);
-                float4 o;
-                o.x = __fadd_rn(__fmul_rn(__fdiv_rn(v[i].x, den), g4.x), b4.x);
-                o.y = __fadd_rn(__fmul_rn(__fdiv_rn(v[i].y, den), g4.y), b4.y);
-                o.z = __fadd_rn(__fmul_rn(__fdiv_rn(v[i].z, den), g4.z), b4.z);
-                o.w = __fadd_rn(__fmul_rn(__fdiv_rn(v[i].w, den), g4.w), b4.w);
-                store_frag(xhi, xlo, nchunks, r, c * 4, o);
-            }
-        }
-    }
+__device__ __forceinline__ void store_plane_elem(uint4* phi, uint4* plo, int nchunks, int row, int col, float v) {
+    const __half h = __float2half_rn(v);
+    const __half l = __float2half_rn((v - __half2float(h)) * 2048.0f);
+    const int idx = plane_idx(nchunks, row, col);
+    reinterpret_cast<__half*>(phi + idx)[col & 7] = h;
+    reinterpret_cast<__half*>(plo + idx)[col & 7] = l;
 }
 
-// plain copy of src[r][col0 .. col0 + KS) (row stride ld, L2) into the planes; 8 independent loads in flight
-template <int NT8>
-__device__ __forceinline__ void stage_copy_frag(const float* src, int64_t ld, int col0, int KS, int R, uint4* xhi, uint4* xlo) {
-    const int per_row = KS / 4, n4 = NT8 * 8 * per_row, nchunks = KS / 32;
-    for (int i0 = threadIdx.x; i0 < n4; i0 += NT * 8) {
-        float4 v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int i = i0 + u * NT;
-            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (i < n4) {
-                const int r = i / per_row, c = i % per_row;
-                if (r < R) v[u] = __ldcg(reinterpret_cast<const float4*>(src + (int64_t)r * ld + col0) + c);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int i = i0 + u * NT;
-            if (i < n4) store_frag(xhi, xlo, nchunks, i / per_row, (i % per_row) * 4, v[u]);
-        }
-    }
-}
-
-// A fragments of one (16-feature tile, K slice of this warp): rows g and g+8, MAXCH chunks of 32 columns
+// A fragments of one (16-feature tile, K slice of this warp): feature rows g and g+8, MAXCH chunks of 32 columns
 struct AFrag {
-    uint4 lo[MAXCH], hi[MAXCH];   // "lo" = feature row g, "hi" = feature row g + 8
+    uint4 r0[MAXCH], r8[MAXCH];
     float bias;
 };
-// item = slab * n_tiles + tile; this warp's slice of the slab = columns [warp * KS / 8, +KS / 8)
-__device__ __forceinline__ void load_afrag(const __half* __restrict__ W, const float* __restrict__ bias, int K, int KS, int n_tiles,
-                                           int item, AFrag& f) {
+// item = slab * n_tiles + tile; this warp's slice of the slab (= d columns) is [warp * d / 8, +d / 8)
+__device__ __forceinline__ void load_afrag(const GemmDesc& D, int d, int item, AFrag& f) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    const int tile = item % n_tiles, slab = item / n_tiles;
-    const int nch = KS >> 8;
-    const int k0 = slab * KS + warp * (KS >> 3) + t * 8;
-    const uint4* p0 = reinterpret_cast<const uint4*>(W + (int64_t)(tile * 16 + g) * K + k0);
-    const uint4* p1 = reinterpret_cast<const uint4*>(W + (int64_t)(tile * 16 + g + 8) * K + k0);
+    const int n_tiles = D.N >> 4, tile = item % n_tiles, slab = item / n_tiles;
+    const int K = D.n_slabs * d, nch = d >> 8;
+    const int k0 = slab * d + warp * (d >> 3) + t * 8;
+    const __half* Wh = reinterpret_cast<const __half*>(D.W);
+    const uint4* p0 = reinterpret_cast<const uint4*>(Wh + (int64_t)(tile * 16 + g) * K + k0);
+    const uint4* p1 = reinterpret_cast<const uint4*>(Wh + (int64_t)(tile * 16 + g + 8) * K + k0);
 #pragma unroll
     for (int c = 0; c < MAXCH; ++c) {
         if (c < nch) {
-            f.lo[c] = __ldg(p0 + c * 4);
-            f.hi[c] = __ldg(p1 + c * 4);
+            f.r0[c] = __ldg(p0 + c * 4);
+            f.r8[c] = __ldg(p1 + c * 4);
         }
     }
-    f.bias = (bias != nullptr && slab == 0) ? __ldg(bias + tile * 16 + (threadIdx.x & 15)) : 0.0f;
-}
-
-// One linear layer for all rows: out[r][n] = sum_k x[r][k] W[n][k] (+ bias on slab 0).
-//   stage(slab): fills the planes with columns [slab*KS, +KS) of the input (called between two __syncthreads);
-//   pre(n, r)  : optional early load (e.g. the residual) issued before the MMAs;
-//   emit(n, r, slab, value, pre_value): called for r < R by the thread that owns (feature n, row r).
-template <int NT8, typename StageF, typename PreF, typename EmitF>
-__device__ __forceinline__ void gemm_phase(const __half* __restrict__ W, const float* __restrict__ bias, int N, int K, int KS, int R,
-                                           AFrag& pf, StageF&& stage, PreF&& pre, EmitF&& emit, uint4* xhi, uint4* xlo, float* red) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    const int n_tiles = N / 16, n_items = n_tiles * (K / KS);
-    const int nch = KS >> 8, nchunks = KS >> 5;
-    constexpr int NE = (16 * NT8 * 8 + NT - 1) / NT;
-    int staged_slab = -1;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int tile = item % n_tiles, slab = item / n_tiles;
-        AFrag cur = pf;
-        if (item + (int)gridDim.x < n_items) load_afrag(W, bias, K, KS, n_tiles, item + gridDim.x, pf);   // next item of this CTA
-        float prev[NE];
-#pragma unroll
-        for (int e = 0; e < NE; ++e) {
-            const int idx = tid + e * NT;
-            prev[e] = (idx < 16 * NT8 * 8 && (idx >> 4) < R) ? pre(tile * 16 + (idx & 15), idx >> 4) : 0.0f;
-        }
-        if (slab != staged_slab) {
-            __syncthreads();
-            stage(slab);
-            staged_slab = slab;
-        }
-        __syncthreads();
-        float ah[NT8][4], al[NT8][4];
-#pragma unroll
-        for (int j = 0; j < NT8; ++j)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) { ah[j][c] = 0.0f; al[j][c] = 0.0f; }
-#pragma unroll
-        for (int c = 0; c < MAXCH; ++c) {
-            if (c < nch) {
-                const int chunk = warp * nch + c;
-#pragma unroll
-                for (int j = 0; j < NT8; ++j) {
-                    const uint4 bh = xhi[(j * nchunks + chunk) * 32 + lane];
-                    const uint4 bl = xlo[(j * nchunks + chunk) * 32 + lane];
-                    mma16816(ah[j], cur.lo[c].x, cur.hi[c].x, cur.lo[c].y, cur.hi[c].y, bh.x, bh.y);
-                    mma16816(ah[j], cur.lo[c].z, cur.hi[c].z, cur.lo[c].w, cur.hi[c].w, bh.z, bh.w);
-                    mma16816(al[j], cur.lo[c].x, cur.hi[c].x, cur.lo[c].y, cur.hi[c].y, bl.x, bl.y);
-                    mma16816(al[j], cur.lo[c].z, cur.hi[c].z, cur.lo[c].w, cur.hi[c].w, bl.z, bl.w);
-                }
-            }
-        }
-        // C fragment: c0,c1 -> (feature g, rows 2t, 2t+1), c2,c3 -> (feature g+8, rows 2t, 2t+1)
-        float* my = red + warp * (NT8 * 8 * RED_LD);
-#pragma unroll
-        for (int j = 0; j < NT8; ++j) {
-            const int r0 = j * 8 + 2 * t;
-            my[r0 * RED_LD + g] = fmaf(al[j][0], 1.0f / 2048.0f, ah[j][0]);
-            my[(r0 + 1) * RED_LD + g] = fmaf(al[j][1], 1.0f / 2048.0f, ah[j][1]);
-            my[r0 * RED_LD + g + 8] = fmaf(al[j][2], 1.0f / 2048.0f, ah[j][2]);
-            my[(r0 + 1) * RED_LD + g + 8] = fmaf(al[j][3], 1.0f / 2048.0f, ah[j][3]);
-        }
-        __syncthreads();
-#pragma unroll
-        for (int e = 0; e < NE; ++e) {
-            const int idx = tid + e * NT;
-            if (idx < 16 * NT8 * 8) {
-                const int f = idx & 15, r = idx >> 4;
-                float s = 0.0f;
-#pragma unroll
-                for (int w = 0; w < NW; ++w) s += red[w * (NT8 * 8 * RED_LD) + r * RED_LD + f];
-                if (r < R) emit(tile * 16 + f, r, slab, s + cur.bias, prev[e]);
-            }
-        }
-    }
-    __syncthreads();
+    f.bias = (D.bias != nullptr && slab == 0) ? __ldg(D.bias + tile * 16 + (threadIdx.x & 15)) : 0.0f;
 }
 
 // =====================================================================================================
-template <int NT8, int KC, typename KVT>
+// Stage slots of one layer (descriptor a.d5[l * 16 + slot]); the logits use a.d5[L * 16 + {11, 12}].
+enum { SL_LN1 = 0, SL_QKV, SL_SELF, SL_OUT, SL_LN2, SL_CQ, SL_CROSS, SL_COUT, SL_LN3, SL_MLP1, SL_MLP2, SL_LNF, SL_LOGITS, SL_COUNT };
+
+template <int NT8, int DV, typename KVT>
 __global__ void __launch_bounds__(NT, 1)
 dec5_kernel(const Dec3Args a) {
     extern __shared__ __align__(16) float sm[];
@@ -244,16 +126,19 @@ dec5_kernel(const Dec3Args a) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int gw = blockIdx.x * NW + warp, n_gw = gridDim.x * NW;
     constexpr int RP = NT8 * 8;
+    constexpr int KC = DEC5_KC;
+    constexpr int NE = (16 * RP + NT - 1) / NT;
+    const int nchunks = d >> 5, nch = d >> 8, nv = d >> 2;
     uint4* xhi = reinterpret_cast<uint4*>(sm);            // [NT8][d/32][32] fragment-order fp16 hi plane
-    uint4* xlo = xhi + NT8 * (d / 32) * 32;               // same, residual * 2^11
-    float* red = reinterpret_cast<float*>(xlo + NT8 * (d / 32) * 32);   // [NW][RP][RED_LD]; also cross-merge weights
-    float* qs = red + NW * RP * RED_LD;                   // [64]
-    float* wm = qs + 64;                                  // [NW]
+    uint4* xlo = xhi + NT8 * nchunks * 32;                // same, residual * 2^11
+    float* red = reinterpret_cast<float*>(reinterpret_cast<char*>(sm) + max(2 * NT8 * nchunks * 32 * 16, NW * RING_W));   // [NW][RP][RED_LD]; also cross-merge weights
+    float* qs = red + NW * RP * RED_LD;                   // [2][64] query of the attention unit of each 4-warp group
+    float* wm = qs + 128;                                 // [NW]
     float* wl = wm + NW;                                  // [NW]
     float* wo = wl + NW;                                  // [NW][64]
-    float* ao = wo + NW * 64;                             // [64]
-    float* ML = ao + 64;                                  // [2]
-    int* tok_s = reinterpret_cast<int*>(ML + 2);          // [RP]
+    GemmDesc* ds = reinterpret_cast<GemmDesc*>(wo + NW * 64);   // [L * 16 + 16] stage descriptors: a global load per stage would be a dependent round trip
+    for (int i = tid; i < (L * 16 + 16) * (int)(sizeof(GemmDesc) / 16); i += NT) reinterpret_cast<uint4*>(ds)[i] = __ldg(reinterpret_cast<const uint4*>(a.d5) + i);
+    __syncthreads();
     unsigned int gen = 0;
     int tr_n = 0;
     WB_TRACE();
@@ -261,131 +146,215 @@ dec5_kernel(const Dec3Args a) {
     const int S = a.n_splits;
     const float* yp = a.ypart;                            // [4][R][d] MLP2 partial sums of the previous layer
     const int64_t yps = (int64_t)R * d;
-    auto no_pre = [](int, int) { return 0.0f; };
-    // The residual stream ping-pongs between two buffers: the MLP2 partial sums of layer l-1 are folded into x by
-    // the LayerNorm staging of layer l (every CTA, fixed order); CTA r % grid publishes the folded row into the
-    // OTHER buffer, so no CTA can read a row that was already folded.  xc = current buffer.
-    float* xc = a.x;
-    float* xo = a.x2;
-    auto fold = [&](int r, int c4) {
-        float4 v = __ldcg(reinterpret_cast<const float4*>(xc + (int64_t)r * d) + c4);
-        const float4 p0 = __ldcg(reinterpret_cast<const float4*>(yp + (int64_t)r * d) + c4);
-        const float4 p1 = __ldcg(reinterpret_cast<const float4*>(yp + yps + (int64_t)r * d) + c4);
-        const float4 p2 = __ldcg(reinterpret_cast<const float4*>(yp + 2 * yps + (int64_t)r * d) + c4);
-        const float4 p3 = __ldcg(reinterpret_cast<const float4*>(yp + 3 * yps + (int64_t)r * d) + c4);
-        const float4 s = make_float4(__fadd_rn(__fadd_rn(p0.x, p1.x), __fadd_rn(p2.x, p3.x)), __fadd_rn(__fadd_rn(p0.y, p1.y), __fadd_rn(p2.y, p3.y)),
-                                     __fadd_rn(__fadd_rn(p0.z, p1.z), __fadd_rn(p2.z, p3.z)), __fadd_rn(__fadd_rn(p0.w, p1.w), __fadd_rn(p2.w, p3.w)));
-        return make_float4(__fadd_rn(v.x, s.x), __fadd_rn(v.y, s.y), __fadd_rn(v.z, s.z), __fadd_rn(v.w, s.w));
-    };
-    auto load_x_folded = [&](int r, int c4) {     // P1 of layers > 0: fold and publish into the other buffer
-        const float4 v = fold(r, c4);
-        if (r % (int)gridDim.x == (int)blockIdx.x) *reinterpret_cast<float4*>(xo + (int64_t)r * d + c4 * 4) = v;
-        return v;
-    };
-    auto load_x = [&](int r, int c4) { return __ldcg(reinterpret_cast<const float4*>(xc + (int64_t)r * d) + c4); };
+    const int64_t pl_plane = (int64_t)PL_ROWS * d / 8;    // uint4 per global plane (one slab)
+    uint4* att_hi = reinterpret_cast<uint4*>(a.att_pl);   // attention output planes: hi, lo
+    uint4* att_lo = att_hi + pl_plane;
+    uint4* xn_hi = att_lo + pl_plane;                     // LayerNorm output planes: hi, lo
+    uint4* xn_lo = xn_hi + pl_plane;
+    uint4* hid_hi = reinterpret_cast<uint4*>(a.hid_pl);   // [4 slabs] hi planes, then [4 slabs] lo planes
+    uint4* hid_lo = hid_hi + 4 * pl_plane;
+    float* x = a.x;
 
     AFrag pf;
+    bool pf_valid = false;
     for (int step = 0; step < a.n_steps; ++step) {
         const int p = a.pos0 + step;
         const bool want_logits = p >= a.logits_from;
         for (int l = 0; l < L; ++l) {
-            const Dec3Layer& W = a.layers[l];
             KVT* kcl = reinterpret_cast<KVT*>(a.kc) + (size_t)l * a.Rmax * t_max * d;
             KVT* vcl = reinterpret_cast<KVT*>(a.vc) + (size_t)l * a.Rmax * t_max * d;
-            // ================= P1: q | k | v = LN(x) Wqkv + b   (mod.rs:429-431)
-            if (l == 0) {
-                load_afrag(reinterpret_cast<const __half*>(W.Wqkv), W.bqkv, d, d, 3 * d / 16, blockIdx.x % (3 * d / 16), pf);
-                if (tid < RP) tok_s[tid] = tid < R ? (a.use_cur_tok ? __ldcg(a.cur_tok + tid) : __ldcg(a.tokens + (int64_t)tid * t_max + p)) : 0;
-            }
-            {
-                const float* pe = a.pos_emb + (int64_t)p * d;
-                auto load_emb = [&](int r, int c4) {   // x = tok_emb[token] + pos_emb[p]  (mod.rs:141-146)
-                    const float4 e4 = __ldg(reinterpret_cast<const float4*>(a.tok_emb + (int64_t)tok_s[r] * d) + c4);
-                    const float4 p4 = __ldg(reinterpret_cast<const float4*>(pe) + c4);
-                    const float4 v = make_float4(__fadd_rn(e4.x, p4.x), __fadd_rn(e4.y, p4.y), __fadd_rn(e4.z, p4.z), __fadd_rn(e4.w, p4.w));
-                    if (r % (int)gridDim.x == (int)blockIdx.x) *reinterpret_cast<float4*>(xc + (int64_t)r * d + c4 * 4) = v;
-                    return v;
-                };
-                auto stage = [&](int) {
-                    if (l == 0) stage_ln_frag<NT8>(load_emb, R, d, W.ln1_g, W.ln1_b, W.ln1_eps, a.eps_outside, xhi, xlo);
-                    else stage_ln_frag<NT8>(load_x_folded, R, d, W.ln1_g, W.ln1_b, W.ln1_eps, a.eps_outside, xhi, xlo);
-                };
-                gemm_phase<NT8>(reinterpret_cast<const __half*>(W.Wqkv), W.bqkv, 3 * d, d, d, R, pf, stage, no_pre,
-                                [&](int n, int r, int, float v, float) {
-                                    if (n < 2 * d) v = __fmul_rn(v, scale);
-                                    if (n < d) a.q[(int64_t)r * d + n] = v;
-                                    else if (n < 2 * d) kcl[((int64_t)r * t_max + p) * d + (n - d)] = (KVT)v;
-                                    else vcl[((int64_t)r * t_max + p) * d + (n - 2 * d)] = (KVT)v;
-                                }, xhi, xlo, red);
-                if (l > 0) { float* tmp = xc; xc = xo; xo = tmp; }   // the folded rows were published into the other buffer
-            }
-            if ((int)blockIdx.x < d / 16) load_afrag(reinterpret_cast<const __half*>(W.Wo), W.bo, d, d, d / 16, blockIdx.x, pf);
-            WB_TRACE();
-            grid_sync(a.bar, gen);
-            WB_TRACE();
-            // ================= P2: self attention over positions 0..p of the row's ancestry (mask == causal)
-            for (int u = blockIdx.x; u < R * H; u += gridDim.x) {
-                const int r = u / H, h = u % H;
-                if (tid < 16) *reinterpret_cast<float4*>(qs + tid * 4) = __ldcg(reinterpret_cast<const float4*>(a.q + (int64_t)r * d + h * 64) + tid);
-                __syncthreads();
-                const int* anc = a.anc ? a.anc + (int64_t)r * t_max : nullptr;
-                const KVT* kb = kcl + h * 64;
-                const KVT* vb = vcl + h * 64;
-                auto kp = [&](int j) { return kb + ((int64_t)((anc && j < p) ? __ldcg(anc + j) : r) * t_max + j) * d; };
-                auto vp = [&](int j) { return vb + ((int64_t)((anc && j < p) ? __ldcg(anc + j) : r) * t_max + j) * d; };
-                attn_cta(qs, p + 1, kp, vp, wm, wl, wo, ao, ML);
-                if (tid < 64) a.att[(int64_t)r * d + h * 64 + tid] = __fdiv_rn(ao[tid], ML[1]);
-                __syncthreads();
-            }
-            WB_TRACE();
-            grid_sync(a.bar, gen);
-            WB_TRACE();
-            // ================= P3: x += att Wo + bo   (mod.rs:435, :346)
-            gemm_phase<NT8>(reinterpret_cast<const __half*>(W.Wo), W.bo, d, d, d, R, pf,
-                            [&](int) { stage_copy_frag<NT8>(a.att, d, 0, d, R, xhi, xlo); },
-                            [&](int n, int r) { return __ldcg(xc + (int64_t)r * d + n); },
-                            [&](int n, int r, int, float v, float xold) { xc[(int64_t)r * d + n] = __fadd_rn(xold, v); }, xhi, xlo, red);
-            if ((int)blockIdx.x < d / 16) load_afrag(reinterpret_cast<const __half*>(W.Wcq), W.bcq, d, d, d / 16, blockIdx.x, pf);
-            WB_TRACE();
-            grid_sync(a.bar, gen);
-            WB_TRACE();
-            // ================= P4: cross query = LN(x) Wq + b   (mod.rs:483)
-            gemm_phase<NT8>(reinterpret_cast<const __half*>(W.Wcq), W.bcq, d, d, d, R, pf,
-                            [&](int) { stage_ln_frag<NT8>(load_x, R, d, W.ln2_g, W.ln2_b, W.ln2_eps, a.eps_outside, xhi, xlo); }, no_pre,
-                            [&](int n, int r, int, float v, float) { a.q[(int64_t)r * d + n] = __fmul_rn(v, scale); }, xhi, xlo, red);
-            if ((int)blockIdx.x < d / 16) load_afrag(reinterpret_cast<const __half*>(W.Wco), W.bco, d, d, d / 16, blockIdx.x, pf);
-            WB_TRACE();
-            grid_sync(a.bar, gen);
-            WB_TRACE();
-            // ================= P5: cross attention, split over the window's encoder positions
-            {
-                const KVT* ckvl = reinterpret_cast<const KVT*>(a.ckv) + (size_t)l * a.Mcap * 2 * d;
-                for (int u = blockIdx.x; u < R * H * S; u += gridDim.x) {
-                    const int sp = u % S, h = (u / S) % H, r = u / (S * H);
-                    if (tid < 16) *reinterpret_cast<float4*>(qs + tid * 4) = __ldcg(reinterpret_cast<const float4*>(a.q + (int64_t)r * d + h * 64) + tid);
-                    __syncthreads();
-                    const int w = __ldcg(a.row_window + r);
-                    const int T = a.win_T[w];
-                    const int per = (T + S - 1) / S;
-                    const int kb0 = sp * per;
-                    const int nk = max(0, min(T, kb0 + per) - kb0);
-                    const KVT* kbase = ckvl + (a.win_row_off[w] + kb0) * (int64_t)(2 * d) + h * 64;
-                    const int64_t ld = 2 * (int64_t)d;
-                    auto kp = [&](int j) { return kbase + j * ld; };
-                    auto vp = [&](int j) { return kbase + j * ld + d; };
-                    attn_cta(qs, nk, kp, vp, wm, wl, wo, ao, ML);
-                    const int64_t o = ((int64_t)r * H + h) * S + sp;
-                    if (tid < 64) a.part_o[o * 64 + tid] = ao[tid];
-                    if (tid == 0) { a.part_m[o] = nk > 0 ? ML[0] : -INFINITY; a.part_l[o] = ML[1]; }
-                    __syncthreads();
-                }
-            }
-            WB_TRACE();
-            grid_sync(a.bar, gen);
-            WB_TRACE();
-            // ================= P6: x += merge(cross partials) Wo + bo   (mod.rs:489, :347)
-            gemm_phase<NT8>(reinterpret_cast<const __half*>(W.Wco), W.bco, d, d, d, R, pf,
-                            [&](int) {
+            const int n_slots = (l == L - 1 && want_logits) ? SL_COUNT : SL_LNF;
+#pragma unroll 1
+            for (int slot = 0; slot < n_slots; ++slot) {
+                const GemmDesc& D = ds[(slot >= SL_LNF ? L : l) * 16 + slot];
+                if (D.kind == D5_KIND_LN) {
+                    // ================= LayerNorm (burn 0.9 form, dec_common.cuh stage_ln) of row blockIdx.x by ONE warp of ONE CTA,
+                    // written as fragment-order hi/lo planes for the next linear stage (every CTA copies them after the barrier).
+                    // EMB: x = tok_emb[token] + pos_emb[p] (mod.rs:141-146); FOLD: x += the four MLP2 partial sums of the
+                    // previous layer (fixed order); both publish the fp32 row for the residual adds of this layer.
+                    const int r = blockIdx.x;
+                    if (r < R && warp == 0) {
+                        float4 v[DV], g4[DV], b4[DV];
+#pragma unroll
+                        for (int i = 0; i < DV; ++i) {
+                            const int c = i * 32 + lane;
+                            if (c < nv) {
+                                g4[i] = __ldg(reinterpret_cast<const float4*>(D.g) + c);
+                                b4[i] = __ldg(reinterpret_cast<const float4*>(D.b) + c);
+                            }
+                        }
+                        if (D.stage == ST_LN_EMB) {
+                            const int tok = a.use_cur_tok ? __ldcg(a.cur_tok + r) : __ldcg(a.tokens + (int64_t)r * t_max + p);
+                            const float* pe = a.pos_emb + (int64_t)p * d;
+#pragma unroll
+                            for (int i = 0; i < DV; ++i) {
+                                const int c = i * 32 + lane;
+                                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (c < nv) {
+                                    const float4 e4 = __ldg(reinterpret_cast<const float4*>(a.tok_emb + (int64_t)tok * d) + c);
+                                    const float4 p4 = __ldg(reinterpret_cast<const float4*>(pe) + c);
+                                    v[i] = make_float4(__fadd_rn(e4.x, p4.x), __fadd_rn(e4.y, p4.y), __fadd_rn(e4.z, p4.z), __fadd_rn(e4.w, p4.w));
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < DV; ++i) {
+                                const int c = i * 32 + lane;
+                                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (c < nv) {
+                                    v[i] = __ldcg(reinterpret_cast<const float4*>(x + (int64_t)r * d) + c);
+                                    if (D.stage != ST_LN_X) {
+                                        const float4 p0 = __ldcg(reinterpret_cast<const float4*>(yp + (int64_t)r * d) + c);
+                                        const float4 p1 = __ldcg(reinterpret_cast<const float4*>(yp + yps + (int64_t)r * d) + c);
+                                        const float4 p2 = __ldcg(reinterpret_cast<const float4*>(yp + 2 * yps + (int64_t)r * d) + c);
+                                        const float4 p3 = __ldcg(reinterpret_cast<const float4*>(yp + 3 * yps + (int64_t)r * d) + c);
+                                        v[i].x = __fadd_rn(v[i].x, __fadd_rn(__fadd_rn(p0.x, p1.x), __fadd_rn(p2.x, p3.x)));
+                                        v[i].y = __fadd_rn(v[i].y, __fadd_rn(__fadd_rn(p0.y, p1.y), __fadd_rn(p2.y, p3.y)));
+                                        v[i].z = __fadd_rn(v[i].z, __fadd_rn(__fadd_rn(p0.z, p1.z), __fadd_rn(p2.z, p3.z)));
+                                        v[i].w = __fadd_rn(v[i].w, __fadd_rn(__fadd_rn(p0.w, p1.w), __fadd_rn(p2.w, p3.w)));
+                                    }
+                                }
+                            }
+                        }
+                        if (D.stage == ST_LN_EMB || D.stage == ST_LN_FOLD) {   // only this warp touches row r in this stage: in place
+#pragma unroll
+                            for (int i = 0; i < DV; ++i) {
+                                const int c = i * 32 + lane;
+                                if (c < nv) reinterpret_cast<float4*>(x + (int64_t)r * d)[c] = v[i];
+                            }
+                        }
+                        float sum = 0.0f;
+#pragma unroll
+                        for (int i = 0; i < DV; ++i) sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+                        sum = warp_sum(sum);
+                        const float mean = __fdiv_rn(sum, (float)d);
+                        float q = 0.0f;
+#pragma unroll
+                        for (int i = 0; i < DV; ++i) {
+                            const int c = i * 32 + lane;
+                            if (c < nv) {
+                                v[i].x = __fsub_rn(v[i].x, mean); v[i].y = __fsub_rn(v[i].y, mean);
+                                v[i].z = __fsub_rn(v[i].z, mean); v[i].w = __fsub_rn(v[i].w, mean);
+                                q = __fadd_rn(q, __fmul_rn(v[i].x, v[i].x)); q = __fadd_rn(q, __fmul_rn(v[i].y, v[i].y));
+                                q = __fadd_rn(q, __fmul_rn(v[i].z, v[i].z)); q = __fadd_rn(q, __fmul_rn(v[i].w, v[i].w));
+                            }
+                        }
+                        q = warp_sum(q);
+                        const float var = __fdiv_rn(q, (float)d);
+                        const float den = a.eps_outside ? __fadd_rn(__fsqrt_rn(var), D.eps) : __fsqrt_rn(__fadd_rn(var, D.eps));
+#pragma unroll
+                        for (int i = 0; i < DV; ++i) {
+                            const int c = i * 32 + lane;
+                            if (c < nv) {
+                                float4 o;
+                                o.x = __fadd_rn(__fmul_rn(__fdiv_rn(v[i].x, den), g4[i].x), b4[i].x);
+                                o.y = __fadd_rn(__fmul_rn(__fdiv_rn(v[i].y, den), g4[i].y), b4[i].y);
+                                o.z = __fadd_rn(__fmul_rn(__fdiv_rn(v[i].z, den), g4[i].z), b4[i].z);
+                                o.w = __fadd_rn(__fmul_rn(__fdiv_rn(v[i].w, den), g4[i].w), b4[i].w);
+                                store_frag(xn_hi, xn_lo, nchunks, r, c * 4, o);
+                            }
+                        }
+                    }
+                } else if (D.kind == D5_KIND_ATTN) {
+                    // ================= attention: self (causal over the row's ancestry) / cross (split over keys).
+                    // Two (row, head[, split]) units per CTA at a time, 4 warps each (named barriers).
+                    const bool is_cross = slot == SL_CROSS;
+                    const int U = is_cross ? R * H * S : R * H;
+                    const int grp = warp >> 2, wg = warp & 3, gt = tid & 127;
+                    const KVT* ckvl = reinterpret_cast<const KVT*>(a.ckv) + (size_t)l * a.Mcap * 2 * d;
+                    for (int u = blockIdx.x * 2 + grp; u < U; u += 2 * gridDim.x) {
+                        int r, h, sp = 0;
+                        if (is_cross) { sp = u % S; h = (u / S) % H; r = u / (S * H); }
+                        else { r = u / H; h = u % H; }
+                        if (gt < 16) *reinterpret_cast<float4*>(qs + grp * 64 + gt * 4) = __ldcg(reinterpret_cast<const float4*>(a.q + (int64_t)r * d + h * 64) + gt);
+                        bar_named(1 + grp, 128);
+                        int nk = p + 1;
+                        const KVT* kbase = nullptr;
+                        const int* anc = nullptr;
+                        if (is_cross) {
+                            const int w = __ldcg(a.row_window + r);
+                            const int T = a.win_T[w];
+                            const int per = (T + S - 1) / S;
+                            const int kb0 = sp * per;
+                            nk = max(0, min(T, kb0 + per) - kb0);
+                            kbase = ckvl + (a.win_row_off[w] + kb0) * (int64_t)(2 * d) + h * 64;
+                        } else {
+                            anc = a.anc ? a.anc + (int64_t)r * t_max : nullptr;
+                        }
+                        const int64_t ld = 2 * (int64_t)d;
+                        auto kp = [&](int j) -> const KVT* {
+                            if (is_cross) return kbase + j * ld;
+                            const int rr = (anc && j < p) ? __ldcg(anc + j) : r;
+                            return kcl + ((int64_t)rr * t_max + j) * d + h * 64;
+                        };
+                        auto vp = [&](int j) -> const KVT* {
+                            if (is_cross) return kbase + j * ld + d;
+                            const int rr = (anc && j < p) ? __ldcg(anc + j) : r;
+                            return vcl + ((int64_t)rr * t_max + j) * d + h * 64;
+                        };
+                        AttnAcc A;
+                        // fp32 cache: register-staged loop (measured faster: 23 vs 30 us per small.en cross stage); fp16 cache: cp.async ring
+                        if constexpr (sizeof(KVT) == 4) attn_warp(qs + grp * 64, nk, wg, 4, kp, vp, A);
+                        else attn_warp_ring<RING_W / 2048>(qs + grp * 64, nk, wg, 4, kp, vp, reinterpret_cast<uint4*>(sm) + warp * (RING_W / 16), A);
+                        if (lane < 4) {
+#pragma unroll
+                            for (int c = 0; c < 16; ++c) wo[warp * 64 + lane * 16 + c] = A.o[c];
+                        }
+                        if (lane == 0) { wm[warp] = A.m; wl[warp] = A.l; }
+                        bar_named(1 + grp, 128);
+                        if (gt < 64) {
+                            float M = -INFINITY;
+#pragma unroll
+                            for (int w2 = 0; w2 < 4; ++w2) M = fmaxf(M, wm[grp * 4 + w2]);
+                            float Ls = 0.0f, o = 0.0f;
+#pragma unroll
+                            for (int w2 = 0; w2 < 4; ++w2) {
+                                const float m = wm[grp * 4 + w2];
+                                const float sc = m > -INFINITY ? expf(m - M) : 0.0f;
+                                Ls += sc * wl[grp * 4 + w2];
+                                o += sc * wo[(grp * 4 + w2) * 64 + gt];
+                            }
+                            if (!is_cross || S == 1) {
+                                store_plane_elem(att_hi, att_lo, nchunks, r, h * 64 + gt, __fdiv_rn(o, Ls));
+                            } else {
+                                const int64_t oi = ((int64_t)r * H + h) * S + sp;
+                                a.part_o[oi * 64 + gt] = o;
+                                if (gt == 0) { a.part_m[oi] = nk > 0 ? M : -INFINITY; a.part_l[oi] = Ls; }
+                            }
+                        }
+                        bar_named(1 + grp, 128);
+                    }
+                } else {
+                    // ================= one linear layer for all rows: out[r][n] = sum_k in[r][k] W[n][k] (+ bias)
+                    const bool merge = D.stage == ST_CROSS && S > 1;
+                    const bool lg = D.emit == EM_LOGITS;
+                    const int n_tiles = D.N >> 4;
+                    const int n_items = lg ? (int)gridDim.x : n_tiles * D.n_slabs;
+                    int staged = -1;
+                    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                        const int tile = lg ? 0 : item % n_tiles, slab = lg ? 0 : item / n_tiles;
+                        if (!lg && !pf_valid) load_afrag(D, d, item, pf);
+                        float prev[NE];
+#pragma unroll
+                        for (int e = 0; e < NE; ++e) {
+                            const int idx = tid + e * NT;
+                            prev[e] = (D.emit == EM_RESID && idx < 16 * RP && (idx >> 4) < R) ? __ldcg(x + (int64_t)(idx >> 4) * d + tile * 16 + (idx & 15)) : 0.0f;
+                        }
+                        if (slab != staged) {
+                            staged = slab;
+                            __syncthreads();
+                            if (!merge) {
+                                // ---- the producer wrote the planes in fragment order: plain asynchronous copy (rows < RP are a prefix)
+                                const uint4* sh = (D.src == 2 ? hid_hi : D.src == 3 ? xn_hi : att_hi) + (int64_t)slab * pl_plane;
+                                const uint4* sl = sh + (D.src == 2 ? 4 * pl_plane : pl_plane);
+                                const int n16 = NT8 * nchunks * 32;
+                                for (int i = tid; i < n16; i += NT) {
+                                    cp_async16(xhi + i, sh + i);
+                                    cp_async16(xlo + i, sl + i);
+                                }
+                                cp_async_wait_all();
+                            } else {
+                                // ---- merge the cross-attention split partials (S > 1) while staging
                                 float* wn = red;   // [RP][H][S] normalised split weights
                                 for (int i = tid; i < RP * H; i += NT) {
                                     const int r = i / H, h = i % H;
@@ -419,136 +388,289 @@ dec5_kernel(const Dec3Args a) {
                                     const int h = c / 64;
                                     const float4* po = reinterpret_cast<const float4*>(a.part_o + (((int64_t)rc * H + h) * S) * 64 + (c & 63));
                                     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 8
+#pragma unroll 4
                                     for (int s = 0; s < S; ++s) {
                                         const float4 v = __ldcg(po + s * 16);
                                         const float wgt = wn[(r * H + h) * S + s];
                                         acc.x = fmaf(wgt, v.x, acc.x); acc.y = fmaf(wgt, v.y, acc.y);
                                         acc.z = fmaf(wgt, v.z, acc.z); acc.w = fmaf(wgt, v.w, acc.w);
                                     }
-                                    store_frag(xhi, xlo, d / 32, r, c, acc);
+                                    store_frag(xhi, xlo, nchunks, r, c, acc);
                                 }
-                            },
-                            [&](int n, int r) { return __ldcg(xc + (int64_t)r * d + n); },
-                            [&](int n, int r, int, float v, float xold) { xc[(int64_t)r * d + n] = __fadd_rn(xold, v); }, xhi, xlo, red);
-            load_afrag(reinterpret_cast<const __half*>(W.W1), W.b1, d, d, 4 * d / 16, blockIdx.x % (4 * d / 16), pf);
-            WB_TRACE();
-            grid_sync(a.bar, gen);
-            WB_TRACE();
-            // ================= P7: hid = gelu(LN(x) W1 + b1)   (mod.rs:377-378)
-            gemm_phase<NT8>(reinterpret_cast<const __half*>(W.W1), W.b1, 4 * d, d, d, R, pf,
-                            [&](int) { stage_ln_frag<NT8>(load_x, R, d, W.ln3_g, W.ln3_b, W.ln3_eps, a.eps_outside, xhi, xlo); }, no_pre,
-                            [&](int n, int r, int, float v, float) { a.hid[(int64_t)r * 4 * d + n] = gelu_erf(v); }, xhi, xlo, red);
-            load_afrag(reinterpret_cast<const __half*>(W.W2), W.b2, 4 * d, d, d / 16, blockIdx.x % (4 * (d / 16)), pf);
-            WB_TRACE();
-            grid_sync(a.bar, gen);
-            WB_TRACE();
-            // ================= P8: MLP2 partials: ypart[slab] = hid[:, slab] W2[:, slab]^T (+ b2 on slab 0); folded into x by the next LN
-            gemm_phase<NT8>(reinterpret_cast<const __half*>(W.W2), W.b2, d, 4 * d, d, R, pf,
-                            [&](int slab) { stage_copy_frag<NT8>(a.hid, 4 * d, slab * d, d, R, xhi, xlo); }, no_pre,
-                            [&](int n, int r, int slab, float v, float) { a.ypart[slab * yps + (int64_t)r * d + n] = v; }, xhi, xlo, red);
-            if (l + 1 < L) {
-                const Dec3Layer& Wn = a.layers[l + 1];
-                load_afrag(reinterpret_cast<const __half*>(Wn.Wqkv), Wn.bqkv, d, d, 3 * d / 16, blockIdx.x % (3 * d / 16), pf);
-            }
-            WB_TRACE();
-            grid_sync(a.bar, gen);
-            WB_TRACE();
-        }
-        if (want_logits) {
-            // ================= logits = LN(x) tok_emb^T (mod.rs:155-156) -> lgbuf[R][V] (L2 resident)
-            float* lgbuf = a.lgbuf;
-            {
-                __syncthreads();
-                stage_ln_frag<NT8>(fold, R, d, a.lnf_g, a.lnf_b, a.lnf_eps, a.eps_outside, xhi, xlo);   // nobody reads x afterwards: no publish
-                __syncthreads();
-                const __half* E = reinterpret_cast<const __half*>(a.E);
-                const int g = lane >> 2, t = lane & 3;
-                const int n_tiles = (V + 15) / 16, ngrp = d / (32 * GC), nchunks = d / 32;
-                const int my_tiles = gw < n_tiles ? (n_tiles - gw + n_gw - 1) / n_gw : 0;
-                const int total = my_tiles * ngrp;
-                uint4 A0[GC][2], A1[GC][2];
-                auto load_grp = [&](int it, uint4 (&A)[GC][2]) {
-                    const int tile = gw + (it / ngrp) * n_gw, grp = it % ngrp;
-                    const int ra = min(tile * 16 + g, V - 1), rb = min(tile * 16 + g + 8, V - 1);
-                    const uint4* pa = reinterpret_cast<const uint4*>(E + (int64_t)ra * d + grp * (32 * GC) + t * 8);
-                    const uint4* pb = reinterpret_cast<const uint4*>(E + (int64_t)rb * d + grp * (32 * GC) + t * 8);
-#pragma unroll
-                    for (int c = 0; c < GC; ++c) { A[c][0] = __ldg(pa + c * 4); A[c][1] = __ldg(pb + c * 4); }
-                };
-                if (total > 0) load_grp(0, A0);
-                float ah[NT8][4], al[NT8][4];
-                for (int it = 0; it < total; ++it) {
-                    const int grp = it % ngrp;
-                    if (grp == 0) {
-#pragma unroll
-                        for (int j = 0; j < NT8; ++j)
-#pragma unroll
-                            for (int c = 0; c < 4; ++c) { ah[j][c] = 0.0f; al[j][c] = 0.0f; }
-                    }
-                    if (it + 1 < total) load_grp(it + 1, A1);
-#pragma unroll
-                    for (int c = 0; c < GC; ++c) {
-                        const int chunk = grp * GC + c;
-#pragma unroll
-                        for (int j = 0; j < NT8; ++j) {
-                            const uint4 bh = xhi[(j * nchunks + chunk) * 32 + lane];
-                            const uint4 bl = xlo[(j * nchunks + chunk) * 32 + lane];
-                            mma16816(ah[j], A0[c][0].x, A0[c][1].x, A0[c][0].y, A0[c][1].y, bh.x, bh.y);
-                            mma16816(ah[j], A0[c][0].z, A0[c][1].z, A0[c][0].w, A0[c][1].w, bh.z, bh.w);
-                            mma16816(al[j], A0[c][0].x, A0[c][1].x, A0[c][0].y, A0[c][1].y, bl.x, bl.y);
-                            mma16816(al[j], A0[c][0].z, A0[c][1].z, A0[c][0].w, A0[c][1].w, bl.z, bl.w);
+                            }
                         }
-                    }
-                    if (grp == ngrp - 1) {
-                        const int n0 = (gw + (it / ngrp) * n_gw) * 16;
+                        __syncthreads();
+                        if (!lg) {
+                            const AFrag cur = pf;
+                            pf_valid = false;
+                            if (item + (int)gridDim.x < n_items) { load_afrag(D, d, item + gridDim.x, pf); pf_valid = true; }   // next item of this CTA
+                            float ah[NT8][4], al[NT8][4];
 #pragma unroll
-                        for (int j = 0; j < NT8; ++j) {
-                            const int r0 = j * 8 + 2 * t;
+                            for (int j = 0; j < NT8; ++j)
 #pragma unroll
-                            for (int c = 0; c < 4; ++c) {
-                                const int n = n0 + g + (c >> 1) * 8, r = r0 + (c & 1);
-                                if (n < V && r < R) lgbuf[(int64_t)r * V + n] = fmaf(al[j][c], 1.0f / 2048.0f, ah[j][c]);
+                                for (int c = 0; c < 4; ++c) { ah[j][c] = 0.0f; al[j][c] = 0.0f; }
+#pragma unroll
+                            for (int c = 0; c < MAXCH; ++c) {
+                                if (c < nch) {
+                                    const int chunk = warp * nch + c;
+#pragma unroll
+                                    for (int j = 0; j < NT8; ++j) {
+                                        const uint4 bh = xhi[(j * nchunks + chunk) * 32 + lane];
+                                        const uint4 bl = xlo[(j * nchunks + chunk) * 32 + lane];
+                                        mma16816(ah[j], cur.r0[c].x, cur.r8[c].x, cur.r0[c].y, cur.r8[c].y, bh.x, bh.y);
+                                        mma16816(ah[j], cur.r0[c].z, cur.r8[c].z, cur.r0[c].w, cur.r8[c].w, bh.z, bh.w);
+                                        mma16816(al[j], cur.r0[c].x, cur.r8[c].x, cur.r0[c].y, cur.r8[c].y, bl.x, bl.y);
+                                        mma16816(al[j], cur.r0[c].z, cur.r8[c].z, cur.r0[c].w, cur.r8[c].w, bl.z, bl.w);
+                                    }
+                                }
+                            }
+                            // C fragment: c0,c1 -> (feature g, rows 2t, 2t+1), c2,c3 -> (feature g+8, rows 2t, 2t+1)
+                            {
+                                const int g = lane >> 2, t = lane & 3;
+                                float* my = red + warp * (RP * RED_LD);
+#pragma unroll
+                                for (int j = 0; j < NT8; ++j) {
+                                    const int r0 = j * 8 + 2 * t;
+                                    my[r0 * RED_LD + g] = fmaf(al[j][0], 1.0f / 2048.0f, ah[j][0]);
+                                    my[(r0 + 1) * RED_LD + g] = fmaf(al[j][1], 1.0f / 2048.0f, ah[j][1]);
+                                    my[r0 * RED_LD + g + 8] = fmaf(al[j][2], 1.0f / 2048.0f, ah[j][2]);
+                                    my[(r0 + 1) * RED_LD + g + 8] = fmaf(al[j][3], 1.0f / 2048.0f, ah[j][3]);
+                                }
+                            }
+                            __syncthreads();
+#pragma unroll
+                            for (int e = 0; e < NE; ++e) {
+                                const int idx = tid + e * NT;
+                                if (idx < 16 * RP) {
+                                    const int f = idx & 15, r = idx >> 4, n = tile * 16 + f;
+                                    float v = cur.bias;
+#pragma unroll
+                                    for (int w = 0; w < NW; ++w) v += red[w * (RP * RED_LD) + r * RED_LD + f];
+                                    if (r < R) {
+                                        switch (D.emit) {
+                                            case EM_QKV:      // mod.rs:429-431; q and k carry the (d/H)^-0.25 scale (:500-503)
+                                                if (n < 2 * d) v = __fmul_rn(v, scale);
+                                                if (n < d) a.q[(int64_t)r * d + n] = v;
+                                                else if (n < 2 * d) kcl[((int64_t)r * t_max + p) * d + (n - d)] = (KVT)v;   // fp16 cache: round-to-nearest
+                                                else vcl[((int64_t)r * t_max + p) * d + (n - 2 * d)] = (KVT)v;
+                                                break;
+                                            case EM_RESID:    // x += out-projection (mod.rs:346-347)
+                                                x[(int64_t)r * d + n] = __fadd_rn(prev[e], v);
+                                                break;
+                                            case EM_CQ:       // cross query (mod.rs:483)
+                                                a.q[(int64_t)r * d + n] = __fmul_rn(v, scale);
+                                                break;
+                                            case EM_HID:      // gelu(LN(x) W1 + b1) (mod.rs:377-378), written as fragment-order planes
+                                                store_plane_elem(hid_hi + (n / d) * pl_plane, hid_lo + (n / d) * pl_plane, nchunks, r, n % d, gelu_erf(v));
+                                                break;
+                                            default:          // EM_PART: MLP2 partial sum of this K slab
+                                                a.ypart[slab * yps + (int64_t)r * d + n] = v;
+                                                break;
+                                        }
+                                    }
+                                }
+                            }
+                        } else {
+                            // ================= logits = LN(x) tok_emb^T (mod.rs:155-156) -> lgbuf[R][V]; a warp streams 16-row tiles of E
+                            const __half* E = reinterpret_cast<const __half*>(D.W);
+                            const int g = lane >> 2, t = lane & 3;
+                            const int v_tiles = (V + 15) / 16, ngrp = d / (32 * GC);
+                            const int my_tiles = gw < v_tiles ? (v_tiles - gw + n_gw - 1) / n_gw : 0;
+                            const int total = my_tiles * ngrp;
+                            uint4 A0[GC][2], A1[GC][2];
+                            auto load_grp = [&](int it, uint4 (&A)[GC][2]) {
+                                const int vt = gw + (it / ngrp) * n_gw, grp = it % ngrp;
+                                const int ra = min(vt * 16 + g, V - 1), rb = min(vt * 16 + g + 8, V - 1);
+                                const uint4* pa = reinterpret_cast<const uint4*>(E + (int64_t)ra * d + grp * (32 * GC) + t * 8);
+                                const uint4* pb = reinterpret_cast<const uint4*>(E + (int64_t)rb * d + grp * (32 * GC) + t * 8);
+#pragma unroll
+                                for (int c = 0; c < GC; ++c) { A[c][0] = __ldg(pa + c * 4); A[c][1] = __ldg(pb + c * 4); }
+                            };
+                            if (total > 0) load_grp(0, A0);
+                            float ah[NT8][4], al[NT8][4];
+#pragma unroll 1
+                            for (int it = 0; it < total; ++it) {
+                                const int grp = it % ngrp;
+                                if (grp == 0) {
+#pragma unroll
+                                    for (int j = 0; j < NT8; ++j)
+#pragma unroll
+                                        for (int c = 0; c < 4; ++c) { ah[j][c] = 0.0f; al[j][c] = 0.0f; }
+                                }
+                                if (it + 1 < total) load_grp(it + 1, A1);
+#pragma unroll
+                                for (int c = 0; c < GC; ++c) {
+                                    const int chunk = grp * GC + c;
+#pragma unroll
+                                    for (int j = 0; j < NT8; ++j) {
+                                        const uint4 bh = xhi[(j * nchunks + chunk) * 32 + lane];
+                                        const uint4 bl = xlo[(j * nchunks + chunk) * 32 + lane];
+                                        mma16816(ah[j], A0[c][0].x, A0[c][1].x, A0[c][0].y, A0[c][1].y, bh.x, bh.y);
+                                        mma16816(ah[j], A0[c][0].z, A0[c][1].z, A0[c][0].w, A0[c][1].w, bh.z, bh.w);
+                                        mma16816(al[j], A0[c][0].x, A0[c][1].x, A0[c][0].y, A0[c][1].y, bl.x, bl.y);
+                                        mma16816(al[j], A0[c][0].z, A0[c][1].z, A0[c][0].w, A0[c][1].w, bl.z, bl.w);
+                                    }
+                                }
+                                if (grp == ngrp - 1) {
+                                    const int n0 = (gw + (it / ngrp) * n_gw) * 16;
+#pragma unroll
+                                    for (int j = 0; j < NT8; ++j) {
+                                        const int r0 = j * 8 + 2 * t;
+#pragma unroll
+                                        for (int c = 0; c < 4; ++c) {
+                                            const int n = n0 + g + (c >> 1) * 8, r = r0 + (c & 1);
+                                            if (n < V && r < R) a.lgbuf[(int64_t)r * V + n] = fmaf(al[j][c], 1.0f / 2048.0f, ah[j][c]);
+                                        }
+                                    }
+                                }
+#pragma unroll
+                                for (int c = 0; c < GC; ++c) { A0[c][0] = A1[c][0]; A0[c][1] = A1[c][1]; }
                             }
                         }
                     }
-#pragma unroll
-                    for (int c = 0; c < GC; ++c) { A0[c][0] = A1[c][0]; A0[c][1] = A1[c][1]; }
+                    __syncthreads();
                 }
+                // prefetch the first A fragments of the NEXT linear stage: weights do not depend on activations
+                if (!pf_valid) {
+                    int l2 = l, s2 = -1;
+                    if (slot < SL_QKV) s2 = SL_QKV;
+                    else if (slot < SL_OUT) s2 = SL_OUT;
+                    else if (slot < SL_CQ) s2 = SL_CQ;
+                    else if (slot < SL_COUT) s2 = SL_COUT;
+                    else if (slot < SL_MLP1) s2 = SL_MLP1;
+                    else if (slot < SL_MLP2) s2 = SL_MLP2;
+                    else if (slot == SL_MLP2) {
+                        if (l + 1 < L) { l2 = l + 1; s2 = SL_QKV; }
+                        else if (!want_logits && step + 1 < a.n_steps) { l2 = 0; s2 = SL_QKV; }
+                    }
+                    if (s2 >= 0) {
+                        const GemmDesc& Dn = ds[l2 * 16 + s2];
+                        if ((int)blockIdx.x < (Dn.N >> 4) * Dn.n_slabs) { load_afrag(Dn, d, blockIdx.x, pf); pf_valid = true; }
+                    }
+                }
+                WB_TRACE();
+                grid_sync(a.bar, gen);
+                WB_TRACE();
             }
-            WB_TRACE();
-            grid_sync(a.bar, gen);
-            WB_TRACE();
+        }
+        if (want_logits) {
             // ================= per (row, slice): special-token mask (transcribe.rs:271-275), max, sum-exp, top candidates
             const int NSL = a.lg_slices;
             {
                 const bool use_mask = a.is_special != nullptr && (a.mask_mode == 1 || (a.mask_mode == 2 && p + 1 <= 5));
                 const int per = (V + NSL - 1) / NSL;
+                // k == 1 (greedy): a compact scan -- running (max, sum-exp) and the best (value, lowest index); this code runs
+                // once per step, i.e. from a cold instruction cache, so its size is its cost
+                if (a.k == 1) {
+                    for (int u = blockIdx.x; u < R * NSL; u += gridDim.x) {
+                        const int r = u / NSL, sl = u % NSL;
+                        const int n_begin = sl * per, n_end = min(V, n_begin + per);
+                        const float* row = a.lgbuf + (int64_t)r * V;
+                        float m_run = -INFINITY, s_run = 0.0f, bv = -INFINITY;
+                        int bi = INT_MAX;
+#pragma unroll 1
+                        for (int n0 = n_begin + tid; n0 < n_end; n0 += NT * 8) {
+                            float val[8];
+                            unsigned char spf[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int n = min(n0 + i * NT, n_end - 1);
+                                val[i] = __ldcg(row + n);
+                                spf[i] = use_mask ? a.is_special[n] : (unsigned char)0;
+                            }
+                            float bm = -INFINITY;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                if (spf[i]) val[i] = __fadd_rn(val[i], -INFINITY);
+                                if (n0 + i * NT >= n_end) val[i] = -INFINITY;
+                                bm = fmaxf(bm, val[i]);
+                                if (val[i] > bv) { bv = val[i]; bi = n0 + i * NT; }   // indices grow: ties keep the lower id
+                            }
+                            if (bm > -INFINITY) {
+                                const float mn = fmaxf(m_run, bm);
+                                float acc = s_run * expf(m_run - mn);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) acc += val[i] > -INFINITY ? expf(val[i] - mn) : 0.0f;
+                                s_run = acc;
+                                m_run = mn;
+                            }
+                        }
+                        float* rec = red + warp * 4;
+#pragma unroll 1
+                        for (int pass = 0; pass < 2; ++pass) {   // pass 0: lanes of a warp, pass 1: the 8 warp records (one code path)
+                            if (pass == 1) {
+                                __syncthreads();
+                                if (warp != 0) break;
+                                m_run = lane < NW ? red[lane * 4] : -INFINITY;
+                                s_run = lane < NW ? red[lane * 4 + 1] : 0.0f;
+                                bv = lane < NW ? red[lane * 4 + 2] : -INFINITY;
+                                bi = lane < NW ? __float_as_int(red[lane * 4 + 3]) : INT_MAX;
+                            }
+#pragma unroll 1
+                            for (int off = 1; off < 32; off <<= 1) {
+                                const float m2 = __shfl_xor_sync(0xffffffffu, m_run, off), s2 = __shfl_xor_sync(0xffffffffu, s_run, off);
+                                const float v2 = __shfl_xor_sync(0xffffffffu, bv, off);
+                                const int i2 = __shfl_xor_sync(0xffffffffu, bi, off);
+                                const float mn = fmaxf(m_run, m2);
+                                s_run = (m_run > -INFINITY ? s_run * expf(m_run - mn) : 0.0f) + (m2 > -INFINITY ? s2 * expf(m2 - mn) : 0.0f);
+                                m_run = mn;
+                                if (v2 > bv || (v2 == bv && i2 < bi)) { bv = v2; bi = i2; }
+                            }
+                            if (pass == 0 && lane == 0) { rec[0] = m_run; rec[1] = s_run; rec[2] = bv; rec[3] = __int_as_float(bi); }
+                        }
+                        if (tid == 0) {
+                            const int64_t o = (int64_t)sl * R + r;
+                            a.lg_m[o] = m_run;
+                            a.lg_s[o] = s_run;
+                            a.lg_v[o * KC] = bv;
+                            a.lg_i[o * KC] = bi;
+                        }
+                        __syncthreads();
+                    }
+                } else
                 for (int u = blockIdx.x; u < R * NSL; u += gridDim.x) {
                     const int r = u / NSL, sl = u % NSL;
                     const int n_begin = sl * per, n_end = min(V, n_begin + per);
-                    const float* row = lgbuf + (int64_t)r * V;
+                    const float* row = a.lgbuf + (int64_t)r * V;
                     float m_run = -INFINITY, s_run = 0.0f;
                     Cand<KC> cand;
                     cand.init();
+#pragma unroll 1
                     for (int n0 = n_begin + tid; n0 < n_end; n0 += NT * 8) {
-                        float raw[8];
+                        float val[8];
+                        unsigned char spf[8];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) raw[i] = (n0 + i * NT < n_end) ? __ldcg(row + n0 + i * NT) : 0.0f;
+                        for (int i = 0; i < 8; ++i) {   // all loads of the batch first (clamped addresses, no control flow in between)
+                            const int n = min(n0 + i * NT, n_end - 1);
+                            val[i] = __ldcg(row + n);
+                            spf[i] = use_mask ? a.is_special[n] : (unsigned char)0;
+                        }
+                        float bm = -INFINITY;
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            const int n = n0 + i * NT;
-                            if (n < n_end) {
-                                const float v = (use_mask && a.is_special[n]) ? __fadd_rn(raw[i], -INFINITY) : raw[i];
-                                if (v > -INFINITY) {
-                                    if (v > m_run) { s_run = s_run * expf(m_run - v) + 1.0f; m_run = v; }
-                                    else s_run += expf(v - m_run);
-                                }
-                                cand.push(v, n);
+                            if (spf[i]) val[i] = __fadd_rn(val[i], -INFINITY);
+                            if (n0 + i * NT >= n_end) val[i] = -INFINITY;
+                            bm = fmaxf(bm, val[i]);
+                        }
+                        if (bm > -INFINITY) {   // one rescale per batch, then 8 independent exponentials
+                            const float mn = fmaxf(m_run, bm);
+                            float acc = s_run * expf(m_run - mn);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) acc += val[i] > -INFINITY ? expf(val[i] - mn) : 0.0f;
+                            s_run = acc;
+                            m_run = mn;
+                        }
+                        if (bm > cand.v[KC - 1]) {   // rarely taken once the candidates have warmed up (ties never replace: indices only grow)
+#pragma unroll 1
+                            for (int i = 0; i < 8; ++i) {
+                                float rv = val[0];
+#pragma unroll
+                                for (int k = 1; k < 8; ++k) rv = (i == k) ? val[k] : rv;
+                                if (n0 + i * NT < n_end) cand.push(rv, n0 + i * NT);
                             }
                         }
                     }
-#pragma unroll
+#pragma unroll 1
                     for (int off = 1; off < 32; off <<= 1) {
                         const float m2 = __shfl_xor_sync(0xffffffffu, m_run, off);
                         const float s2 = __shfl_xor_sync(0xffffffffu, s_run, off);
@@ -561,8 +683,14 @@ dec5_kernel(const Dec3Args a) {
                         const float e2 = m2 > -INFINITY ? expf(m2 - mn) : 0.0f;
                         s_run = s_run * e1 + s2 * e2;
                         m_run = mn;
+#pragma unroll 1
+                        for (int k = 0; k < a.k; ++k) {   // only the k best are ever needed (candidate lists are sorted)
+                            float pv = cv[0];
+                            int pi = ci[0];
 #pragma unroll
-                        for (int k = 0; k < KC; ++k) cand.push(cv[k], ci[k]);
+                            for (int kk = 1; kk < KC; ++kk) { pv = (k == kk) ? cv[kk] : pv; pi = (k == kk) ? ci[kk] : pi; }
+                            cand.push(pv, pi);
+                        }
                     }
                     float* rec = red + warp * (2 + 2 * KC);
                     if (lane == 0) {
@@ -581,8 +709,7 @@ dec5_kernel(const Dec3Args a) {
                         for (int w = 0; w < NW; ++w) {
                             const float* rc = red + w * (2 + 2 * KC);
                             if (rc[0] > -INFINITY) Ssum += rc[1] * expf(rc[0] - M);
-#pragma unroll
-                            for (int k = 0; k < KC; ++k) best.push(rc[2 + k], __float_as_int(rc[2 + KC + k]));
+                            for (int k = 0; k < a.k; ++k) best.push(rc[2 + k], __float_as_int(rc[2 + KC + k]));
                         }
                         const int64_t o = (int64_t)sl * R + r;
                         a.lg_m[o] = M;
@@ -597,6 +724,37 @@ dec5_kernel(const Dec3Args a) {
             grid_sync(a.bar, gen);
             WB_TRACE();
             // ================= finish: log_softmax of the candidates, k best (ties -> lower id), greedy bookkeeping
+            if (a.k == 1) {   // greedy: one warp per row over the NSL <= 16 slice records (beam.rs:9-37 with beam_size 1)
+                for (int r = blockIdx.x; r < R; r += gridDim.x) {
+                    if (warp == 0) {
+                        const bool have = lane < NSL;
+                        const float m = have ? __ldcg(a.lg_m + (int64_t)lane * R + r) : -INFINITY;
+                        const float sv = have ? __ldcg(a.lg_s + (int64_t)lane * R + r) : 0.0f;
+                        float bv = have ? __ldcg(a.lg_v + ((int64_t)lane * R + r) * KC) : -INFINITY;
+                        int bi = have ? __ldcg(a.lg_i + ((int64_t)lane * R + r) * KC) : INT_MAX;
+                        float mx = m;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                        const float se = warp_sum(m > -INFINITY ? sv * expf(m - mx) : 0.0f);
+                        const float lse = logf(se);
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                        }
+                        if (lane == 0) {
+                            a.topk_id[r] = bi == INT_MAX ? -1 : bi;
+                            a.topk_lp[r] = __fsub_rn(__fsub_rn(bv, mx), lse);
+                            if (a.greedy && !__ldcg(a.finished + r)) {
+                                a.tokens[(int64_t)r * t_max + p + 1] = bi;
+                                a.lengths[r] = p + 2;
+                                if (bi == a.eot) a.finished[r] = 1;
+                            }
+                        }
+                    }
+                }
+            } else
             for (int r = blockIdx.x; r < R; r += gridDim.x) {
                 float* s_f = wm;   // [NW] scratch
                 int* s_i = reinterpret_cast<int*>(wl);
@@ -686,14 +844,14 @@ dec5_kernel(const Dec3Args a) {
     }
 }
 
-size_t dec5_smem_bytes(int d, int NT8) {
-    return (size_t)2 * NT8 * (d / 32) * 32 * 16 + sizeof(float) * ((size_t)NW * NT8 * 8 * RED_LD + 64 + 2 * NW + NW * 64 + 64 + 2 + NT8 * 8 + 8);
+size_t dec5_smem_bytes(int d, int NT8, int L) {
+    return std::max((size_t)2 * NT8 * (d / 32) * 32 * 16, (size_t)NW * RING_W) + sizeof(float) * ((size_t)NW * NT8 * 8 * RED_LD + 128 + 2 * NW + NW * 64) + (size_t)(L * 16 + 16) * sizeof(Dec5Desc) + 64;
 }
 
-template <int NT8, int KC, typename KVT>
+template <int NT8, int DV, typename KVT>
 bool launch5_t(const Dec3Args& a, int n_ctas, cudaStream_t st) {
-    const size_t smem = dec5_smem_bytes(a.d, NT8);
-    auto k = dec5_kernel<NT8, KC, KVT>;
+    const size_t smem = dec5_smem_bytes(a.d, NT8, a.L);
+    auto k = dec5_kernel<NT8, DV, KVT>;
     static size_t configured = 0;   // per instantiation
     if (configured != smem) {
         if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -713,23 +871,23 @@ bool launch5_t(const Dec3Args& a, int n_ctas, cudaStream_t st) {
 
 }  // namespace
 
+size_t dec5_plane_uint4(int d) { return (size_t)PL_ROWS * d / 8; }   // uint4 per global plane (one K slab of d columns)
+
 // Returns false when this configuration is not covered (caller falls back to decoder3.cu).
 bool launch_dec5(const Dec3Args& a, int n_ctas, bool w_half, cudaStream_t st) {
-    if (!w_half || a.R < 1 || a.R > 32 || a.d % 256 != 0 || a.d > 1280 || a.H * 64 != a.d) return false;
-    if (a.lgbuf == nullptr || a.ypart == nullptr || a.lg_slices < 1) return false;
-    if ((size_t)a.R * a.H * a.n_splits > (size_t)NW * ((a.R + 7) / 8) * 8 * RED_LD) return false;   // cross-merge weights live in the reduction buffer
+    if (!w_half || a.R < 1 || a.R > 32 || a.d % 256 != 0 || a.d > 1280 || a.H * 64 != a.d || n_ctas < 32) return false;
+    if (a.lgbuf == nullptr || a.ypart == nullptr || a.att_pl == nullptr || a.hid_pl == nullptr || a.d5 == nullptr || a.lg_slices < 1 || a.k > DEC5_KC) return false;
+    if (a.n_splits > 16 || (size_t)a.R * a.H * a.n_splits > (size_t)NW * ((a.R + 7) / 8) * 8 * RED_LD) return false;   // cross-merge weights live in the reduction buffer
     const int nt8 = (a.R + 7) / 8;
-    const bool wide = a.k > 1;
-#define WB_D5(NT8_)                                                                                          \
-    do {                                                                                                     \
-        if (a.kv_half) return wide ? launch5_t<NT8_, 8, __half>(a, n_ctas, st) : launch5_t<NT8_, 2, __half>(a, n_ctas, st); \
-        return wide ? launch5_t<NT8_, 8, float>(a, n_ctas, st) : launch5_t<NT8_, 2, float>(a, n_ctas, st);    \
-    } while (0)
-    if (nt8 == 1) WB_D5(1);
-    if (nt8 == 2) WB_D5(2);
-    if (nt8 == 3) WB_D5(3);
-    WB_D5(4);
+    // DV = float4 per lane of an x row held in registers by the LayerNorm staging (d / 128, rounded up to an instantiated size)
+#define WB_D5K(NT8_, DV_) (a.kv_half ? launch5_t<NT8_, DV_, __half>(a, n_ctas, st) : launch5_t<NT8_, DV_, float>(a, n_ctas, st))
+#define WB_D5(NT8_) (a.d <= 256 ? WB_D5K(NT8_, 2) : a.d <= 768 ? WB_D5K(NT8_, 6) : WB_D5K(NT8_, 10))
+    if (nt8 == 1) return WB_D5(1);
+    if (nt8 == 2) return WB_D5(2);
+    if (nt8 == 3) return WB_D5(3);
+    return WB_D5(4);
 #undef WB_D5
+#undef WB_D5K
 }
 
 }  // namespace wb

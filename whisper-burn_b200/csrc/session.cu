@@ -55,7 +55,11 @@ Session::Session(Model* model, int64_t max_w, int64_t max_b, int64_t max_text_le
     }
     if (kv == WB_KV_F16) { kc16.alloc((size_t)L * Rmax * t_max * d); vc16.alloc((size_t)L * Rmax * t_max * d); }
     else { kc.alloc((size_t)L * Rmax * t_max * d); vc.alloc((size_t)L * Rmax * t_max * d); }
-    dx.alloc((size_t)Rmax * d); dx2.alloc((size_t)Rmax * d); dq.alloc((size_t)Rmax * d); dhid.alloc((size_t)Rmax * 4 * d);
+    dx.alloc((size_t)Rmax * d); dx2.alloc((size_t)Rmax * d);
+    att_pl.alloc(4 * dec5_plane_uint4(d)); hid_pl.alloc(8 * dec5_plane_uint4(d));   // attention + LayerNorm output planes (hi, lo each), MLP hidden planes
+    WB_CUDA(cudaMemsetAsync(att_pl.p, 0, 4 * dec5_plane_uint4(d) * sizeof(uint4), st));
+    WB_CUDA(cudaMemsetAsync(hid_pl.p, 0, 8 * dec5_plane_uint4(d) * sizeof(uint4), st));
+    dq.alloc((size_t)Rmax * d); dhid.alloc((size_t)Rmax * 4 * d);
     logits.alloc((size_t)Rmax * V);
     part_o.alloc((size_t)Rmax * H * n_splits * 64); part_m.alloc((size_t)Rmax * H * n_splits);
     part_l.alloc((size_t)Rmax * H * n_splits);
@@ -93,6 +97,34 @@ Session::Session(Model* model, int64_t max_w, int64_t max_b, int64_t max_text_le
             }
             d3_layers.alloc((size_t)L);
             WB_CUDA(cudaMemcpy(d3_layers.p, lay.data(), lay.size() * sizeof(Dec3Layer), cudaMemcpyHostToDevice));
+            if (h16) {   // decoder5.cu stage descriptors
+                std::vector<Dec5Desc> ds((size_t)L * 16 + 16);
+                auto gemm = [&](Dec5Desc& q, const void* Wp, const float* bias, int N, int n_slabs, int stage, int emit, int src) {
+                    q.kind = D5_KIND_GEMM; q.W = Wp; q.bias = bias; q.N = N; q.n_slabs = n_slabs; q.stage = stage; q.emit = emit; q.src = src;
+                };
+                auto ln = [&](Dec5Desc& q, const LayerNormW& w, int stage) {
+                    q.kind = D5_KIND_LN; q.g = w.g; q.b = w.b; q.eps = w.eps; q.stage = stage;
+                };
+                for (int l = 0; l < L; ++l) {
+                    const DecBlockW& B = m->dec[(size_t)l];
+                    Dec5Desc* q = ds.data() + (size_t)l * 16;
+                    ln(q[0], B.attn_ln, l == 0 ? D5_ST_LN_EMB : D5_ST_LN_FOLD);
+                    gemm(q[1], B.qkv.w16, B.qkv.b, 3 * d, 1, D5_ST_PLANES, D5_EM_QKV, 3);
+                    q[2].kind = D5_KIND_ATTN;
+                    gemm(q[3], B.out.w16, B.out.b, d, 1, D5_ST_PLANES, D5_EM_RESID, 1);
+                    ln(q[4], B.cross_ln, D5_ST_LN_X);
+                    gemm(q[5], B.cq.w16, B.cq.b, d, 1, D5_ST_PLANES, D5_EM_CQ, 3);
+                    q[6].kind = D5_KIND_ATTN;
+                    gemm(q[7], B.cout.w16, B.cout.b, d, 1, D5_ST_CROSS, D5_EM_RESID, 1);
+                    ln(q[8], B.mlp_ln, D5_ST_LN_X);
+                    gemm(q[9], B.mlp1.w16, B.mlp1.b, 4 * d, 1, D5_ST_PLANES, D5_EM_HID, 3);
+                    gemm(q[10], B.mlp2.w16, B.mlp2.b, d, 4, D5_ST_PLANES, D5_EM_PART, 2);
+                }
+                ln(ds[(size_t)L * 16 + 11], m->dec_ln, D5_ST_LN_FOLD_NOPUB);
+                gemm(ds[(size_t)L * 16 + 12], m->tok_emb16, nullptr, V, 1, D5_ST_PLANES, D5_EM_LOGITS, 3);
+                d5_desc.alloc(ds.size());
+                WB_CUDA(cudaMemcpy(d5_desc.p, ds.data(), ds.size() * sizeof(Dec5Desc), cudaMemcpyHostToDevice));
+            }
         }
         const size_t n_part = (size_t)std::max(H * n_splits, 4 * d / 32);
         ypart.alloc(n_part * Rmax * d);
@@ -448,7 +480,7 @@ void Session::launch_v3(int R_, int pos0, int n_steps, int logits_from, bool use
     a.E = m->fp16_exact ? (const void*)m->tok_emb16 : (const void*)m->tok_emb32;
     a.lnf_g = m->dec_ln.g; a.lnf_b = m->dec_ln.b; a.lnf_eps = m->dec_ln.eps;
     a.x = dx.p; a.q = dq.p; a.att = datt.p; a.hid = dhid.p;
-    a.x2 = dx2.p; a.ypart = ypart.p; a.lgbuf = logits.p;
+    a.x2 = dx2.p; a.ypart = ypart.p; a.lgbuf = logits.p; a.att_pl = att_pl.p; a.hid_pl = hid_pl.p; a.d5 = d5_desc.p;
     a.lg_slices = std::max(1, std::min(16, n_sm / std::max(1, R_)));
     a.kv_half = kv_dtype == WB_KV_F16 ? 1 : 0;
     if (a.kv_half) { a.kc = kc16.p; a.vc = vc16.p; a.ckv = ckv16.p; } else { a.kc = kc.p; a.vc = vc.p; a.ckv = ckv.p; }
