@@ -179,6 +179,13 @@ int wb_find_chunk_overlap(const int64_t* prev, int64_t n_prev, const int64_t* cu
  * the reference's output order (ascending score); returns how many were kept. */
 int64_t wb_beam_get_top_elements(const double* scores, int64_t n, int64_t num, int64_t* idx_out);
 
+/* ---- transcribe binary helpers (host) ---------------------------------------------------------- */
+/* load_audio_waveform (src/bin/transcribe/main.rs:31-55): PCM int samples / (2^(bits-1) - 1), float samples as they
+ * are, interleaved.  strict_16k_mono != 0 enforces the reference's asserts (16 kHz, one channel) as WB_ERR_INVALID_ARG.
+ * out may be NULL to query the sample count. */
+int wb_load_wav(const char* path, int strict_16k_mono, float* out, int64_t capacity, int64_t* n_samples_out,
+                int64_t* sample_rate_out, int* channels_out);
+
 /* ---- measurement ----------------------------------------------------------------------------- */
 /* Diagnostics: which persistent decoder kernel the last decode launch used: 4 = cluster/DSMEM (decoder4.cu), 5 = batched
  * tensor-core (decoder5.cu), 3 = grid-barrier FMA fallback (decoder3.cu), 0 = none yet. */

@@ -17,14 +17,17 @@ L = dims.n_text_layer
 print("stamps", len(t), "total ms", (t[-1] - t[0]) / 1e6)
 # layout: start; prefill steps: 8L stamps each; decode steps: 8L + 6 stamps (pre/post of 3 grid barriers)
 pre = 1 + 3 * 8 * L
-per = 8 * L + 9
+per = 8 * L + 8
 body = t[pre:]
 n = len(body) // per
 body = body[:n * per].reshape(n, per)
 prev = np.concatenate([[t[pre - 1]], body[:-1, -1]])
 d = np.diff(np.concatenate([prev[:, None], body], axis=1), axis=1) / 1e3
-names = [f"L{l}.{s}" for l in range(L) for s in ("qkv", "self", "out", "cq", "cross", "cout", "mlp1", "mlp2")] + ["publish", "G1", "lg_ln", "lg_loop", "lg_merge", "pre_G2", "G2", "finish", "G3"]
+names = [f"L{l}.{s}" for l in range(L) for s in ("qkv", "self", "out", "cq", "cross", "cout", "mlp1", "mlp2")] + ["publish", "G1", "lg_ln", "lg_loop", "lg_merge", "G2", "finish", "G3"]
 print("steps", n, "mean step us", d.sum(1).mean())
 m = d.mean(0)
-for nm, v in zip(names, m):
+kinds = ("qkv", "self", "out", "cq", "cross", "cout", "mlp1", "mlp2")
+for k, nm in enumerate(kinds):
+    print(f"{nm:10s} {np.mean([m[l * 8 + k] for l in range(L)]):7.2f} us (mean over layers, stage + cluster barrier)")
+for nm, v in zip(names[8 * L:], m[8 * L:]):
     print(f"{nm:10s} {v:7.2f} us")

@@ -12,4 +12,4 @@ There is no CPU fallback anywhere in this package: every compute call goes throu
 and raises ``WbError`` when the library or a CUDA device is missing.
 """
 from .ffi import WbError, lib, library_path  # noqa: F401
-from . import audio, beam, model, npytree, shard, synth, transcribe  # noqa: F401
+from . import audio, beam, model, npytree, shard, synth, tokens, transcribe, wav  # noqa: F401

@@ -492,6 +492,24 @@ int64_t wb_beam_get_top_elements(const double* scores, int64_t n, int64_t num, i
     return (int64_t)top.size();
 }
 
+int wb_load_wav(const char* path, int strict_16k_mono, float* out, int64_t capacity, int64_t* n_samples_out, int64_t* sample_rate_out,
+                int* channels_out) {
+    return guarded([&] {
+        WB_REQUIRE(path && n_samples_out, "load_wav: null pointer");
+        std::vector<float> v;
+        int64_t sr = 0;
+        int ch = 0;
+        wb::load_wav(path, strict_16k_mono != 0, v, sr, ch);
+        *n_samples_out = (int64_t)v.size();
+        if (sample_rate_out) *sample_rate_out = sr;
+        if (channels_out) *channels_out = ch;
+        if (out) {
+            WB_REQUIRE(capacity >= (int64_t)v.size(), "load_wav: capacity too small");
+            std::memcpy(out, v.data(), v.size() * sizeof(float));
+        }
+    });
+}
+
 int wb_session_last_decoder(const wb_session* s) { return s ? s->impl->last_decoder : -1; }
 
 int64_t wb_kernel_launch_count(void) { return wb::g_launch_count; }

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <type_traits>
 #include <cfloat>
+#include <cuda_fp16.h>
 #include <climits>
 
 #include "decoder.h"
@@ -552,6 +553,38 @@ __device__ __forceinline__ void attn_cta(const float* q_smem, int n_keys, KF&& k
         if (tid == 0) { ML[0] = M; ML[1] = L; }
     }
     __syncthreads();
+}
+
+// ---- tensor-core helpers (mma.sync m16n8k16, fp16 hi/lo split of fp32 activations; see decoder5.cu) -------------
+__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+
+// 4 consecutive fp32 values -> fp16 hi and fp16 (residual * 2048); x == hi + lo / 2048 up to 2^-23 |x|
+__device__ __forceinline__ void split4(const float4 v, uint2& hi, uint2& lo) {
+    const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+    const __half2 l01 = __floats2half2_rn((v.x - f01.x) * 2048.0f, (v.y - f01.y) * 2048.0f);
+    const __half2 l23 = __floats2half2_rn((v.z - f23.x) * 2048.0f, (v.w - f23.y) * 2048.0f);
+    hi = make_uint2(h2_bits(h01), h2_bits(h23));
+    lo = make_uint2(h2_bits(l01), h2_bits(l23));
+}
+
+// Fragment-order planes: element (row, col) of an activation matrix [rows][K] lives in the uint4
+//   ((row / 8) * (K / 32) + col / 32) * 32 + (row % 8) * 4 + (col % 32) / 8,   half (col % 8)
+// i.e. lane (g = row % 8, t) of the MMA finds the 8 halves x[row][chunk*32 + t*8 .. +8) in ONE 16-byte word.
+__device__ __forceinline__ int plane_idx(int nchunks, int row, int col) {
+    return ((row >> 3) * nchunks + (col >> 5)) * 32 + (row & 7) * 4 + ((col & 31) >> 3);
+}
+__device__ __forceinline__ void store_frag(uint4* xhi, uint4* xlo, int nchunks, int row, int col, const float4 v) {
+    uint2 hi, lo;
+    split4(v, hi, lo);
+    const int idx = plane_idx(nchunks, row, col), half = (col & 7) >> 2;
+    reinterpret_cast<uint2*>(xhi + idx)[half] = hi;
+    reinterpret_cast<uint2*>(xlo + idx)[half] = lo;
 }
 
 // ---- top candidates --------------------------------------------------------------------------------------

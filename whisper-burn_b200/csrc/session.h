@@ -122,6 +122,9 @@ std::vector<std::pair<int64_t, int64_t>> window_bounds(int64_t n_samples, int64_
 bool find_chunk_overlap(const int64_t* prev, int64_t n_prev, const int64_t* curr, int64_t n_curr, int64_t max_n_offsets,
                         int64_t min_n_overlaps, int64_t* prev_index, int64_t* curr_index);
 
+// wav.cu: load_audio_waveform (src/bin/transcribe/main.rs:31-55)
+void load_wav(const std::string& path, bool strict, std::vector<float>& out, int64_t& sample_rate, int& channels);
+
 // npytree.cu: the reference's model-file format (src/model/load.rs, python/dump.py)
 void npy_tree_probe(const std::string& dir, wb_dims& dims);
 void npy_tree_load(Model& m, const std::string& dir);
