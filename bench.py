@@ -296,7 +296,7 @@ def run_ours(args):
         prof_steps = args.max_depth
         n_launch_steps = prof_steps + 3
         T_rows = sum((min(l // 160, dims.n_audio_ctx - 10) + 10 - 1) // 2 + 1 for l in lens)
-        clusters = R if (d in (128, 384) and R <= 7) else 1          # decoder4: every row's cluster streams the layer weights
+        clusters = R if (d in (128, 384) and R <= 7) else 1          # decoder4: every row's cluster streams the layer weights (decoder5 / decoder3-small: once)
         per_step_fixed = L * 14 * d * d * wbytes * clusters + V * d * wbytes + L * 2 * T_rows * d * kvb + R * d * 4 * 8 * L
         self_kv = sum(L * 2 * (t + 1) * d * kvb * R for t in range(n_launch_steps))
         alg_bytes = per_step_fixed * n_launch_steps - 3 * V * d * wbytes + self_kv      # prefill positions skip the logits
@@ -304,14 +304,28 @@ def run_ours(args):
             k_ms, _ = sess.profile_decode(sp, prof_steps)          # per-step average of one timed launch
             launch_ms = k_ms * n_launch_steps
             ach = alg_bytes / (launch_ms * 1e-3) / 1e9
-            # DRAM traffic of the same launch from the committed ncu --set full capture (profiles/r01_v4_ncu_full_summary.txt)
-            traffic = 2.625e9 + 12.15e6 if (args.model == "tiny.en" and args.kv == "f32" and R == 3 and args.max_depth == 100) else None
-            roof = {"bound": "hbm", "kernel": "dec4_kernel<384,4,float> (persistent cluster/DSMEM decoder; one launch = 103 positions)",
+            dec = sess.last_decoder()
+            # DRAM traffic of the same launch from the committed ncu --set full captures (profiles/r01_*_ncu_full_summary.txt)
+            traffic, kernel, note = None, f"dec{dec}_kernel", ""
+            if dec == 4:
+                kernel = f"dec4_kernel<{d},..> (persistent cluster/DSMEM decoder, decoder4.cu; one launch = {n_launch_steps} positions)"
+                note = ("latency-bound chain of 32 cluster + 3 grid barriers per step (ncu: issue active 9.8 %, DRAM 1.9 % of peak, L2 hit 70 %): "
+                        "DRAM traffic is BELOW the algorithmic bytes because weights and K/V stay L2-resident across steps")
+                if args.model == "tiny.en" and args.kv == "f32" and R == 3 and args.max_depth == 100:
+                    traffic = 2.625e9 + 12.15e6
+            elif dec == 5:
+                kernel = (f"dec5_kernel<{(R + 7) // 8},..> (persistent batched tensor-core decoder, decoder5.cu: mma.sync swap-AB, fp16 hi/lo activation "
+                          f"planes; one launch = {n_launch_steps} positions)")
+                note = ("per step: 11 stages per layer + 4, each behind a grid barrier; the HBM-bound part is the cross-attention K/V stream "
+                        "(every row has its own window), the linear stages are latency-bound (ncu: profiles/r01_dec5_ncu_full_summary.txt)")
+                if args.model == "small.en" and args.kv == "f32" and R == 24:
+                    traffic = D5_SMALL_EN_DRAM_BYTES_PER_STEP * n_launch_steps
+            else:
+                kernel = "dec3_kernel (persistent grid-barrier FMA decoder, decoder3.cu)"
+            roof = {"bound": "hbm", "kernel": kernel,
                     "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic,
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes), "ms_per_launch": launch_ms,
-                    "us_per_step": k_ms * 1e3, "steps_per_launch": n_launch_steps,
-                    "note": "latency-bound chain of 32 cluster + 3 grid barriers per step (ncu: issue active 9.8 %, DRAM 1.9 % of peak, "
-                            "L2 hit 70 %): DRAM traffic is BELOW the algorithmic bytes because weights and K/V stay L2-resident across steps"}
+                    "us_per_step": k_ms * 1e3, "steps_per_launch": n_launch_steps, "note": note}
         except Exception as ex:   # noqa: BLE001
             roof = {"bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": None,
                     "error": str(ex)}
@@ -354,6 +368,9 @@ def run_ours(args):
 
 
 _REAL_STDOUT = None
+# DRAM bytes per decoder step of the small.en / 24-row launch (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum of the
+# dec5 launch divided by its positions; profiles/r01_dec5_ncu_full_summary.txt)
+D5_SMALL_EN_DRAM_BYTES_PER_STEP = 1.39e9
 
 
 def emit(line: dict) -> None:

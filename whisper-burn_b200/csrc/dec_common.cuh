@@ -334,9 +334,11 @@ __device__ __forceinline__ float pick_row(const float (&acc)[RC], int rr) {
 struct AttnAcc {
     float m, l, o[16];
 };
+// swz >= 0: the keys come from the head-major cross K/V layout (encoder.cu ckv_relayout_kernel), whose 16-byte chunks are
+// XOR-4 swizzled on odd positions (swz = absolute position of key 0); the lane then finds its 16 dims one block over.
 template <typename KF, typename VF>
 __device__ __forceinline__ void attn_warp(const float* q_smem, int n_keys, int first, int stride, KF&& kptr, VF&& vptr,
-                                          AttnAcc& A) {
+                                          AttnAcc& A, int swz = -1) {
     const int lane = threadIdx.x & 31, sub = lane >> 2, l4 = lane & 3;
     float q[16];
 #pragma unroll
@@ -358,14 +360,15 @@ __device__ __forceinline__ void attn_warp(const float* q_smem, int n_keys, int f
             const int j = jb + (u * 8 + sub) * stride;
             ok[u] = j < n_keys;
             if (ok[u]) {
+                const int par = swz >= 0 ? ((swz + j) & 1) : 0;
                 if constexpr (sizeof(KT) == 4) {
-                    const float4* kp = reinterpret_cast<const float4*>(kptr(j)) + l4 * 4;
-                    const float4* vp = reinterpret_cast<const float4*>(vptr(j)) + l4 * 4;
+                    const float4* kp = reinterpret_cast<const float4*>(kptr(j)) + (l4 ^ par) * 4;
+                    const float4* vp = reinterpret_cast<const float4*>(vptr(j)) + (l4 ^ par) * 4;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) { kk[u][c] = __ldcg(kp + c); vv[u][c] = __ldcg(vp + c); }
                 } else {   // fp16 cache: 16 dims = 32 bytes = two 16-byte loads
-                    const uint4* kp = reinterpret_cast<const uint4*>(kptr(j)) + l4 * 2;
-                    const uint4* vp = reinterpret_cast<const uint4*>(vptr(j)) + l4 * 2;
+                    const uint4* kp = reinterpret_cast<const uint4*>(kptr(j)) + (l4 ^ (2 * par)) * 2;
+                    const uint4* vp = reinterpret_cast<const uint4*>(vptr(j)) + (l4 ^ (2 * par)) * 2;
                     uint4 kr[2], vr[2];
                     kr[0] = __ldcg(kp); kr[1] = __ldcg(kp + 1); vr[0] = __ldcg(vp); vr[1] = __ldcg(vp + 1);
 #pragma unroll
@@ -431,7 +434,7 @@ __device__ __forceinline__ void attn_warp(const float* q_smem, int n_keys, int f
 // ring: this warp's NSTG * 8 * NV2 * 32 uint4 (NV2 = 16-byte vectors of K plus V per lane and key: 8 fp32 / 4 fp16).
 template <int NSTG, typename KF, typename VF>
 __device__ __forceinline__ void attn_warp_ring(const float* q_smem, int n_keys, int first, int stride, KF&& kptr, VF&& vptr,
-                                               uint4* ring, AttnAcc& A) {
+                                               uint4* ring, AttnAcc& A, int swz = -1) {
     using KT = typename std::remove_cv<typename std::remove_pointer<decltype(kptr(0))>::type>::type;
     constexpr int NV = sizeof(KT) == 4 ? 4 : 2;   // 16-byte vectors per lane and tensor (16 dims)
     const int lane = threadIdx.x & 31, sub = lane >> 2, l4 = lane & 3;
@@ -451,8 +454,9 @@ __device__ __forceinline__ void attn_warp_ring(const float* q_smem, int n_keys, 
         const int j = first + (it * 8 + sub) * stride;
         if (it < n_it && j < n_keys) {
             uint4* dst = ring + (it % NSTG) * (2 * NV * 32) + lane;   // vector c of this lane at [c][lane]: conflict-free
-            const uint4* kp = reinterpret_cast<const uint4*>(kptr(j)) + l4 * NV;
-            const uint4* vp = reinterpret_cast<const uint4*>(vptr(j)) + l4 * NV;
+            const int blk = swz >= 0 ? (l4 ^ (((swz + j) & 1) * (NV == 4 ? 1 : 2))) : l4;
+            const uint4* kp = reinterpret_cast<const uint4*>(kptr(j)) + blk * NV;
+            const uint4* vp = reinterpret_cast<const uint4*>(vptr(j)) + blk * NV;
 #pragma unroll
             for (int c = 0; c < NV; ++c) {
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + c * 32)), "l"(kp + c) : "memory");
@@ -527,10 +531,10 @@ __device__ __forceinline__ void attn_warp_ring(const float* q_smem, int n_keys, 
 // (M, L) and the unnormalised output in out[64] (shared memory), valid after the trailing __syncthreads().
 template <typename KF, typename VF>
 __device__ __forceinline__ void attn_cta(const float* q_smem, int n_keys, KF&& kptr, VF&& vptr, float* wm, float* wl,
-                                         float* wo, float* out, float* ML) {
+                                         float* wo, float* out, float* ML, int swz = -1) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     AttnAcc A;
-    attn_warp(q_smem, n_keys, warp, NW, kptr, vptr, A);
+    attn_warp(q_smem, n_keys, warp, NW, kptr, vptr, A, swz);
     if (lane < 4) {
 #pragma unroll
         for (int c = 0; c < 16; ++c) wo[warp * 64 + lane * 16 + c] = A.o[c];

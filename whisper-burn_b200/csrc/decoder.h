@@ -219,6 +219,7 @@ struct Dec3Args {
     int lg_slices = 1;                      // decoder5.cu: vocabulary slices per row in the softmax / candidate stage
     void *kc = nullptr, *vc = nullptr;    // [L][Rmax][t_max][d]  fp32 or fp16 (kv_half)
     const void* ckv = nullptr;            // [L][Mcap][2d]
+    int ckv_hm = 0;                       // 1: head-major cross K/V (encoder.cu ckv_relayout_kernel), 0: GEMM row-major order
     int kv_half = 0;
     const int* row_window = nullptr;
     const int64_t* win_row_off = nullptr;

@@ -152,11 +152,12 @@ dec3_kernel(const Dec3Args a) {
                     const int per = (T + S - 1) / S;
                     const int kb0 = sp * per;
                     const int nk = max(0, min(T, kb0 + per) - kb0);
-                    const KVT* kbase = ckvl + (a.win_row_off[w] + kb0) * (int64_t)(2 * d) + h * 64;
-                    const int64_t ld = 2 * (int64_t)d;
+                    const KVT* kbase = ckvl + a.win_row_off[w] * (int64_t)(2 * d) + (a.ckv_hm ? ((int64_t)h * T + kb0) * 128 : kb0 * (int64_t)(2 * d) + h * 64);
+                    const int64_t ld = a.ckv_hm ? 128 : 2 * (int64_t)d;
+                    const int voff = a.ckv_hm ? 64 : d;
                     auto kp = [&](int j) { return kbase + j * ld; };
-                    auto vp = [&](int j) { return kbase + j * ld + d; };
-                    attn_cta(qs, nk, kp, vp, wm, wl, wo, ao, ML);
+                    auto vp = [&](int j) { return kbase + j * ld + voff; };
+                    attn_cta(qs, nk, kp, vp, wm, wl, wo, ao, ML, a.ckv_hm ? kb0 : -1);
                     const int64_t o = ((int64_t)r * H + h) * S + sp;
                     if (tid < 64) a.part_o[o * 64 + tid] = ao[tid];
                     if (tid == 0) { a.part_m[o] = nk > 0 ? ML[0] : -INFINITY; a.part_l[o] = ML[1]; }

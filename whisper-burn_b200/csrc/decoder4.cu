@@ -308,13 +308,14 @@ dec4_kernel(const Dec3Args a) {
                     const int w = __ldcg(a.row_window + row);
                     const int T = a.win_T[w];
                     const KVT* ckvl = reinterpret_cast<const KVT*>(a.ckv) + (size_t)l * a.Mcap * 2 * D;
-                    const KVT* kbase = ckvl + a.win_row_off[w] * (int64_t)(2 * D) + h * 64;
-                    const int64_t ld = 2 * (int64_t)D;
+                    const KVT* kbase = ckvl + a.win_row_off[w] * (int64_t)(2 * D) + (a.ckv_hm ? (int64_t)h * T * 128 : (int64_t)h * 64);
+                    const int64_t ld = a.ckv_hm ? 128 : 2 * (int64_t)D;
+                    const int voff = a.ckv_hm ? 64 : D;
                     auto kp = [&](int j) { return kbase + j * ld; };
-                    auto vp = [&](int j) { return kbase + j * ld + D; };
+                    auto vp = [&](int j) { return kbase + j * ld + voff; };
                     // keys j == ci*NW + warp (mod nch*NW)
                     AttnAcc A;
-                    attn_warp(q2_s + h * 64, T, ci * NW + warp, nch * NW, kp, vp, A);
+                    attn_warp(q2_s + h * 64, T, ci * NW + warp, nch * NW, kp, vp, A, a.ckv_hm ? 0 : -1);
                     if (lane < 4) {
 #pragma unroll
                         for (int c = 0; c < 16; ++c) wo[warp * 64 + lane * 16 + c] = A.o[c];

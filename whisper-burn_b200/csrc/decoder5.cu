@@ -238,7 +238,7 @@ dec5_kernel(const Dec3Args a) {
                         else { r = u / H; h = u % H; }
                         if (gt < 16) *reinterpret_cast<float4*>(qs + grp * 64 + gt * 4) = __ldcg(reinterpret_cast<const float4*>(a.q + (int64_t)r * d + h * 64) + gt);
                         bar_named(1 + grp, 128);
-                        int nk = p + 1;
+                        int nk = p + 1, swz = -1;
                         const KVT* kbase = nullptr;
                         const int* anc = nullptr;
                         if (is_cross) {
@@ -247,25 +247,27 @@ dec5_kernel(const Dec3Args a) {
                             const int per = (T + S - 1) / S;
                             const int kb0 = sp * per;
                             nk = max(0, min(T, kb0 + per) - kb0);
-                            kbase = ckvl + (a.win_row_off[w] + kb0) * (int64_t)(2 * d) + h * 64;
+                            swz = a.ckv_hm ? kb0 : -1;
+                            kbase = ckvl + a.win_row_off[w] * (int64_t)(2 * d) + (a.ckv_hm ? ((int64_t)h * T + kb0) * 128 : kb0 * (int64_t)(2 * d) + h * 64);
                         } else {
                             anc = a.anc ? a.anc + (int64_t)r * t_max : nullptr;
                         }
-                        const int64_t ld = 2 * (int64_t)d;
+                        const int64_t ld = a.ckv_hm ? 128 : 2 * (int64_t)d;
+                        const int voff = a.ckv_hm ? 64 : d;
                         auto kp = [&](int j) -> const KVT* {
                             if (is_cross) return kbase + j * ld;
                             const int rr = (anc && j < p) ? __ldcg(anc + j) : r;
                             return kcl + ((int64_t)rr * t_max + j) * d + h * 64;
                         };
                         auto vp = [&](int j) -> const KVT* {
-                            if (is_cross) return kbase + j * ld + d;
+                            if (is_cross) return kbase + j * ld + voff;
                             const int rr = (anc && j < p) ? __ldcg(anc + j) : r;
                             return vcl + ((int64_t)rr * t_max + j) * d + h * 64;
                         };
                         AttnAcc A;
                         // fp32 cache: register-staged loop (measured faster: 23 vs 30 us per small.en cross stage); fp16 cache: cp.async ring
-                        if constexpr (sizeof(KVT) == 4) attn_warp(qs + grp * 64, nk, wg, 4, kp, vp, A);
-                        else attn_warp_ring<RING_W / 2048>(qs + grp * 64, nk, wg, 4, kp, vp, reinterpret_cast<uint4*>(sm) + warp * (RING_W / 16), A);
+                        if constexpr (sizeof(KVT) == 4) attn_warp(qs + grp * 64, nk, wg, 4, kp, vp, A, swz);
+                        else attn_warp_ring<RING_W / 2048>(qs + grp * 64, nk, wg, 4, kp, vp, reinterpret_cast<uint4*>(sm) + warp * (RING_W / 16), A, swz);
                         if (lane < 4) {
 #pragma unroll
                             for (int c = 0; c < 16; ++c) wo[warp * 64 + lane * 16 + c] = A.o[c];

@@ -1,5 +1,6 @@
 // Encoder-side kernels other than the GEMMs: LayerNorm and non-causal multi-head attention
 // (reference: burn nn::LayerNorm used at src/model/mod.rs:300-301,259; qkv_attention mod.rs:493-533).
+#include <cuda_fp16.h>
 #include "wb_internal.h"
 
 namespace wb {
@@ -224,6 +225,58 @@ void launch_encoder_attention(const float* qkv, float* out, float* out_lo, const
     }
     dim3 grid((max_T + AQ - 1) / AQ, n_head, n_windows);
     enc_attention_kernel<<<grid, ATT_THREADS, ATT_SMEM, st>>>(qkv, out, out_lo, win_dev, d);
+    WB_LAUNCH_CHECK();
+}
+
+
+// ---- cross K/V re-layout -------------------------------------------------------------------------------
+// The cross-attention K|V projection (C[M][2d], row = encoder position, written by the GEMM) is re-laid out
+// HEAD-MAJOR for the decoders: window w (rows [off_w, off_w + T_w)) keeps its byte range, inside it head h owns the
+// contiguous block [T_w][128] = per position 64 key dims then 64 value dims (16-byte chunks XOR-4 swizzled on odd positions).  A decoder (row, head) unit then
+// streams ONE contiguous T_w * 512-byte (fp32) block instead of 256-byte pieces at a 2d stride: full DRAM pages,
+// and a key batch is a single bulk copy.  Also the place where the fp16 cache is rounded (round-to-nearest).
+namespace {
+template <typename OT>
+__global__ void ckv_relayout_kernel(const float* __restrict__ src, OT* __restrict__ dst, const int64_t* __restrict__ win_row_off,
+                                    const int* __restrict__ win_T, int n_windows, int64_t M, int d) {
+    const int64_t n4 = M * (2 * d / 4);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t m = i / (2 * d / 4);
+        const int c = (int)(i % (2 * d / 4)) * 4;
+        int lo = 0, hi = n_windows - 1;   // last window whose first row is <= m
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (win_row_off[mid] <= m) lo = mid; else hi = mid - 1;
+        }
+        const int64_t off = win_row_off[lo];
+        const int T = win_T[lo];
+        const int which = c / d, cc = c % d, h = cc >> 6, e = cc & 63;
+        const float4 v = *reinterpret_cast<const float4*>(src + m * 2 * d + c);
+        // XOR-4 swizzle of the 16-byte chunks on odd positions: two consecutive positions staged in shared memory at a
+        // 512 / 256-byte pitch then never share a bank group (conflict-free 16-byte reads of 8 keys x 4 lanes)
+        constexpr int CH = 16 / (int)sizeof(OT);
+        const int j = (int)(m - off);
+        const int e_phys = (((e / CH) ^ (4 * (j & 1))) * CH) + e % CH;
+        OT* o = dst + off * 2 * d + (int64_t)h * T * 128 + (int64_t)j * 128 + which * 64 + e_phys;
+        if constexpr (sizeof(OT) == 4) {
+            *reinterpret_cast<float4*>(o) = v;
+        } else {
+            const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+            uint2 u;
+            u.x = *reinterpret_cast<const uint32_t*>(&a);
+            u.y = *reinterpret_cast<const uint32_t*>(&b);
+            *reinterpret_cast<uint2*>(o) = u;
+        }
+    }
+}
+}  // namespace
+
+void launch_ckv_relayout(const float* src, void* dst, bool dst_half, const int64_t* win_row_off, const int* win_T, int n_windows,
+                         int64_t M, int d, cudaStream_t st) {
+    const int64_t n4 = M * (2 * d / 4);
+    const int blocks = (int)std::min<int64_t>((n4 + 255) / 256, 148 * 16);
+    if (dst_half) ckv_relayout_kernel<__half><<<blocks, 256, 0, st>>>(src, reinterpret_cast<__half*>(dst), win_row_off, win_T, n_windows, M, d);
+    else ckv_relayout_kernel<float><<<blocks, 256, 0, st>>>(src, reinterpret_cast<float*>(dst), win_row_off, win_T, n_windows, M, d);
     WB_LAUNCH_CHECK();
 }
 

@@ -74,6 +74,8 @@ Session::Session(Model* model, int64_t max_w, int64_t max_b, int64_t max_text_le
         if (e && e[0] == '2') dec_version = 2;
         if (e && e[0] == '3') dec_version = 3;
         if (kv == WB_KV_F16 && dec_version < 3) dec_version = 3;   // the fp16 cache exists in the persistent decoders only
+        ckv_hm = dec_version >= 3;
+        if (ckv_hm) ckv_tmp.alloc(Mcap * 2 * d);
         cudaDeviceProp prop;
         WB_CUDA(cudaGetDeviceProperties(&prop, m->device));
         n_sm = prop.multiProcessorCount;
@@ -349,7 +351,8 @@ void Session::run_cross_kv() {
         const DecBlockW& B = m->dec[(size_t)l];
         GemmParams p;
         p.A = xa.p; p.lda = d; p.B = B.ckv.w32; p.ldc = 2 * d;
-        if (kv_dtype == WB_KV_F16) p.C16 = ckv16.p + (size_t)l * Mcap * 2 * d; else p.C = ckv.p + (size_t)l * Mcap * 2 * d;
+        if (ckv_hm) p.C = ckv_tmp.p;
+        else if (kv_dtype == WB_KV_F16) p.C16 = ckv16.p + (size_t)l * Mcap * 2 * d; else p.C = ckv.p + (size_t)l * Mcap * 2 * d;
         p.N = 2 * d; p.K = d; p.bias = B.ckv.b; p.scale = qk_scale; p.scale_cols = d; p.max_rows = (int)M_tot;
         if (use_tc && gemm_tc_supported(p)) {
             if (!tc) {   // the encoder output itself stays intact (it is returned through the ABI)
@@ -360,6 +363,10 @@ void Session::run_cross_kv() {
             launch_gemm_tc(p, lo_b.p, 0, (int)M_tot, st);
         } else {
             launch_gemm(p, st);
+        }
+        if (ckv_hm) {
+            void* dst = kv_dtype == WB_KV_F16 ? (void*)(ckv16.p + (size_t)l * Mcap * 2 * d) : (void*)(ckv.p + (size_t)l * Mcap * 2 * d);
+            launch_ckv_relayout(ckv_tmp.p, dst, kv_dtype == WB_KV_F16, d_win_row_off.p, d_win_T.p, n_windows, M_tot, d, st);
         }
     }
 }
@@ -480,7 +487,7 @@ void Session::launch_v3(int R_, int pos0, int n_steps, int logits_from, bool use
     a.E = m->fp16_exact ? (const void*)m->tok_emb16 : (const void*)m->tok_emb32;
     a.lnf_g = m->dec_ln.g; a.lnf_b = m->dec_ln.b; a.lnf_eps = m->dec_ln.eps;
     a.x = dx.p; a.q = dq.p; a.att = datt.p; a.hid = dhid.p;
-    a.x2 = dx2.p; a.ypart = ypart.p; a.lgbuf = logits.p; a.att_pl = att_pl.p; a.hid_pl = hid_pl.p; a.d5 = d5_desc.p;
+    a.x2 = dx2.p; a.ypart = ypart.p; a.lgbuf = logits.p; a.att_pl = att_pl.p; a.hid_pl = hid_pl.p; a.d5 = d5_desc.p; a.ckv_hm = ckv_hm ? 1 : 0;
     a.lg_slices = std::max(1, std::min(16, n_sm / std::max(1, R_)));
     a.kv_half = kv_dtype == WB_KV_F16 ? 1 : 0;
     if (a.kv_half) { a.kc = kc16.p; a.vc = vc16.p; a.ckv = ckv16.p; } else { a.kc = kc.p; a.vc = vc.p; a.ckv = ckv.p; }
@@ -527,6 +534,7 @@ void Session::step_core(bool with_logits, int mask_mode, int k, bool greedy, int
         ++host_pos;
         return;
     }
+    if (ckv_hm) fail(WB_ERR_UNSUPPORTED, "k > 7 candidates per row needs the per-op decoder (WB200_DECODER=1): the persistent decoders keep the cross K/V head-major");
     if (dec_version == 2 && k <= DEC2_KC - 1) {
         step_core_v2(with_logits, mask_mode, k, greedy, eot);
         return;

@@ -43,6 +43,8 @@ struct Session {
     bool use_tc = true;                // WB200_GEMM=simt forces the fp32 CUDA-core GEMM
     void gemm(const GemmParams& p, float* a_mut, float* lo_buf);   // tensor-core when possible
     DevBuf<float> ckv;     // [L][Mcap][2d]  cross keys (scaled) | values, projected once per window
+    DevBuf<float> ckv_tmp; // [Mcap][2d] one layer's projection in GEMM (row-major) order, before the head-major re-layout
+    bool ckv_hm = false;   // cross K/V stored head-major (persistent decoders); the per-op decoders (WB200_DECODER=1|2) read it row-major
     // ---- device: decode state
     DevBuf<float> kc, vc;  // [L][Rmax][t_max][d] self keys (scaled) / values
     DevBuf<__half> kc16, vc16, ckv16;   // fp16 caches (WB_KV_F16)

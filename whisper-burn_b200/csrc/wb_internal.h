@@ -193,6 +193,9 @@ void launch_chan_to_rows(const float* chan, float* rows, int n_frames, int64_t c
 
 // ---- encoder pieces (encoder.cu) -----------------------------------------------------------------
 // y_lo != null: y receives the TF32 hi plane of LayerNorm(x) and y_lo the lo plane (prologue of a tensor-core GEMM)
+// head-major re-layout of one layer's cross K|V rows (see encoder.cu)
+void launch_ckv_relayout(const float* src, void* dst, bool dst_half, const int64_t* win_row_off, const int* win_T, int n_windows,
+                         int64_t M, int d, cudaStream_t st);
 void launch_layernorm(const float* x, float* y, float* y_lo, const LayerNormW& ln, int rows, int d, int eps_outside,
                       cudaStream_t st);
 struct AttnWindow {
