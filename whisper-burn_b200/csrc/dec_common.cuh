@@ -527,6 +527,118 @@ __device__ __forceinline__ void attn_warp_ring(const float* q_smem, int n_keys, 
     }
 }
 
+// Bulk-copy variant for the head-major cross K/V layout (encoder.cu ckv_relayout_kernel): the unit's keys are ONE contiguous
+// [n_keys][128] block, so a batch of 8 keys (K and V) is a single cp.async.bulk (TMA engine, no tensor map) into this warp's
+// ring, completion on the stage's mbarrier; NSTG-1 batches are in flight per warp.  The warps of the unit take batches
+// round-robin (wslot of nwarps).  Lane (sub, l4) handles key `sub` of the batch and the 16-byte chunks l4 + 4c of its K and V
+// rows -- with the layout's XOR-4 swizzle on odd positions the 8 lanes of a quarter warp hit 8 distinct bank groups.
+// ring_count: batches this warp has pushed through its ring since kernel start (stage / parity bookkeeping).
+template <typename KT>
+__device__ __forceinline__ int attn_bulk_dim(int l4, int i) {   // which of the 64 head dims is o[i] / q[i] of lane l4
+    constexpr int CE = 16 / (int)sizeof(KT);                    // elements per 16-byte chunk
+    return (l4 + 4 * (i / CE)) * CE + i % CE;
+}
+template <int NSTG, typename KT>
+__device__ __forceinline__ void attn_warp_bulk(const float* q_smem, const KT* base, int n_keys, int wslot, int nwarps, int swz,
+                                               unsigned char* ring, uint64_t* mbar, unsigned int& ring_count, AttnAcc& A) {
+    constexpr int CE = 16 / (int)sizeof(KT), NC = 16 / CE;      // chunk elements; chunks per lane and tensor
+    constexpr int ROWB = 128 * (int)sizeof(KT), STGB = 8 * ROWB;
+    const int lane = threadIdx.x & 31, sub = lane >> 2, l4 = lane & 3;
+    float q[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) q[i] = q_smem[attn_bulk_dim<KT>(l4, i)];
+    A.m = -INFINITY;
+    A.l = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) A.o[c] = 0.0f;
+    const int n_batches = (n_keys + 7) >> 3;
+    const int n_it = n_batches > wslot ? (n_batches - wslot + nwarps - 1) / nwarps : 0;
+    auto issue = [&](int it) {
+        if (it < n_it && lane == 0) {
+            const int bb = wslot + it * nwarps;
+            const unsigned int cnt = ring_count + (unsigned int)it;
+            const int slot = (int)(cnt % NSTG);
+            const uint32_t bytes = (uint32_t)min(8, n_keys - bb * 8) * ROWB;
+            const uint32_t mb = (uint32_t)__cvta_generic_to_shared(mbar + slot);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             (uint32_t)__cvta_generic_to_shared(ring + slot * STGB)),
+                         "l"(base + (int64_t)bb * 8 * 128), "r"(bytes), "r"(mb)
+                         : "memory");
+        }
+    };
+#pragma unroll
+    for (int s = 0; s < NSTG - 1; ++s) issue(s);
+#pragma unroll 1
+    for (int it = 0; it < n_it; ++it) {
+        __syncwarp();                 // every lane is done with the slot that is refilled now (consumed one iteration ago)
+        issue(it + NSTG - 1);
+        const unsigned int cnt = ring_count + (unsigned int)it;
+        const int slot = (int)(cnt % NSTG);
+        {
+            const uint32_t mb = (uint32_t)__cvta_generic_to_shared(mbar + slot), parity = (cnt / NSTG) & 1;
+            uint32_t done = 0;
+            while (!done) {
+                asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(mb), "r"(parity) : "memory");
+            }
+        }
+        const int bb = wslot + it * nwarps;
+        const int j = bb * 8 + sub;
+        if (j < n_keys) {
+            const int par = (swz + j) & 1;
+            const unsigned char* row = ring + slot * STGB + sub * ROWB;
+            float kf[16], vf[16];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const int phys = (l4 + 4 * c) ^ (4 * par);
+                const uint4 kk = *reinterpret_cast<const uint4*>(row + phys * 16);
+                const uint4 vv = *reinterpret_cast<const uint4*>(row + ROWB / 2 + phys * 16);
+                if constexpr (sizeof(KT) == 4) {
+                    kf[c * 4] = __uint_as_float(kk.x); kf[c * 4 + 1] = __uint_as_float(kk.y); kf[c * 4 + 2] = __uint_as_float(kk.z); kf[c * 4 + 3] = __uint_as_float(kk.w);
+                    vf[c * 4] = __uint_as_float(vv.x); vf[c * 4 + 1] = __uint_as_float(vv.y); vf[c * 4 + 2] = __uint_as_float(vv.z); vf[c * 4 + 3] = __uint_as_float(vv.w);
+                } else {
+                    float w[8];
+                    cvt8(kk, w);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) kf[c * 8 + e] = w[e];
+                    cvt8(vv, w);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) vf[c * 8 + e] = w[e];
+                }
+            }
+            float s = 0.0f;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) s = fmaf(q[c], kf[c], s);
+            s += __shfl_xor_sync(0xfu << (lane & 28), s, 1);
+            s += __shfl_xor_sync(0xfu << (lane & 28), s, 2);
+            const float mn = fmaxf(A.m, s);
+            const float corr = expf(A.m - mn);
+            const float e = expf(s - mn);
+            A.l = A.l * corr + e;
+            A.m = mn;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) A.o[c] = fmaf(e, vf[c], A.o[c] * corr);
+        }
+    }
+    ring_count += (unsigned int)n_it;
+    __syncwarp();
+#pragma unroll
+    for (int off = 4; off < 32; off <<= 1) {   // merge the 8 key sub-groups (same l4 = same dims)
+        const float m2 = __shfl_xor_sync(0xffffffffu, A.m, off);
+        const float l2 = __shfl_xor_sync(0xffffffffu, A.l, off);
+        const float mn = fmaxf(A.m, m2);
+        const float c1 = A.m > -INFINITY ? expf(A.m - mn) : 0.0f;
+        const float c2 = m2 > -INFINITY ? expf(m2 - mn) : 0.0f;
+        A.l = A.l * c1 + l2 * c2;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const float o2 = __shfl_xor_sync(0xffffffffu, A.o[c], off);
+            A.o[c] = A.o[c] * c1 + o2 * c2;
+        }
+        A.m = mn;
+    }
+}
+
 // one (query row, head) unit handled by the 8 warps of a CTA (keys strided over warps); returns the merged
 // (M, L) and the unnormalised output in out[64] (shared memory), valid after the trailing __syncthreads().
 template <typename KF, typename VF>

@@ -108,6 +108,13 @@ dec5_kernel(const Dec3Args a) {
     float* wo = wl + NW;                                  // [NW][64]
     GemmDesc* ds = reinterpret_cast<GemmDesc*>(wo + NW * 64);   // [L * 16 + 16] stage descriptors: a global load per stage would be a dependent round trip
     for (int i = tid; i < (L * 16 + 16) * (int)(sizeof(GemmDesc) / 16); i += NT) reinterpret_cast<uint4*>(ds)[i] = __ldg(reinterpret_cast<const uint4*>(a.d5) + i);
+    uint64_t* kv_bar = reinterpret_cast<uint64_t*>(ds + L * 16 + 16);   // [NW][KV_STG] cross-attention K/V ring: one mbarrier per stage
+    constexpr int KV_STG = RING_W / (8 * 128 * (int)sizeof(KVT));          // fp32: 4 stages of 8 keys, fp16: 8
+    if (lane == 0) {
+        for (int j = 0; j < KV_STG; ++j) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(kv_bar + warp * KV_STG + j)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    unsigned int kv_count = 0;   // batches this warp has pushed through its K/V ring
     __syncthreads();
     unsigned int gen = 0;
     int tr_n = 0;
@@ -229,6 +236,7 @@ dec5_kernel(const Dec3Args a) {
                     // ================= attention: self (causal over the row's ancestry) / cross (split over keys).
                     // Two (row, head[, split]) units per CTA at a time, 4 warps each (named barriers).
                     const bool is_cross = slot == SL_CROSS;
+                    if (is_cross) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the ring aliases the planes written through the generic proxy
                     const int U = is_cross ? R * H * S : R * H;
                     const int grp = warp >> 2, wg = warp & 3, gt = tid & 127;
                     const KVT* ckvl = reinterpret_cast<const KVT*>(a.ckv) + (size_t)l * a.Mcap * 2 * d;
@@ -265,12 +273,18 @@ dec5_kernel(const Dec3Args a) {
                             return vcl + ((int64_t)rr * t_max + j) * d + h * 64;
                         };
                         AttnAcc A;
-                        // fp32 cache: register-staged loop (measured faster: 23 vs 30 us per small.en cross stage); fp16 cache: cp.async ring
-                        if constexpr (sizeof(KVT) == 4) attn_warp(qs + grp * 64, nk, wg, 4, kp, vp, A, swz);
-                        else attn_warp_ring<RING_W / 2048>(qs + grp * 64, nk, wg, 4, kp, vp, reinterpret_cast<uint4*>(sm) + warp * (RING_W / 16), A, swz);
+                        const bool bulk = is_cross && a.ckv_hm;
+                        if (bulk) {   // contiguous head-major block: 8-key batches by bulk copy into this warp's ring (aliases the planes, dead here)
+                            attn_warp_bulk<KV_STG, KVT>(qs + grp * 64, kbase, nk, wg, 4, swz, reinterpret_cast<unsigned char*>(sm) + warp * RING_W,
+                                                        kv_bar + warp * KV_STG, kv_count, A);
+                        } else if constexpr (sizeof(KVT) == 4) {
+                            attn_warp(qs + grp * 64, nk, wg, 4, kp, vp, A, swz);
+                        } else {
+                            attn_warp_ring<RING_W / 2048>(qs + grp * 64, nk, wg, 4, kp, vp, reinterpret_cast<uint4*>(sm) + warp * (RING_W / 16), A, swz);
+                        }
                         if (lane < 4) {
 #pragma unroll
-                            for (int c = 0; c < 16; ++c) wo[warp * 64 + lane * 16 + c] = A.o[c];
+                            for (int c = 0; c < 16; ++c) wo[warp * 64 + (bulk ? attn_bulk_dim<KVT>(lane, c) : lane * 16 + c)] = A.o[c];
                         }
                         if (lane == 0) { wm[warp] = A.m; wl[warp] = A.l; }
                         bar_named(1 + grp, 128);
@@ -817,7 +831,7 @@ dec5_kernel(const Dec3Args a) {
 }
 
 size_t dec5_smem_bytes(int d, int NT8, int L) {
-    return std::max((size_t)2 * NT8 * (d / 32) * 32 * 16, (size_t)NW * RING_W) + sizeof(float) * ((size_t)NW * NT8 * 8 * RED_LD + 128 + 2 * NW + NW * 64) + (size_t)(L * 16 + 16) * sizeof(Dec5Desc) + 64;
+    return std::max((size_t)2 * NT8 * (d / 32) * 32 * 16, (size_t)NW * RING_W) + sizeof(float) * ((size_t)NW * NT8 * 8 * RED_LD + 128 + 2 * NW + NW * 64) + (size_t)(L * 16 + 16) * sizeof(Dec5Desc) + NW * 8 * 8 + 64;
 }
 
 template <int NT8, int DV, typename KVT>
