@@ -30,6 +30,7 @@ namespace {
 constexpr int CS = 16;   // CTAs per cluster
 constexpr int LG_NBUF = 3;                 // logits stage: ring slots per warp
 constexpr int LG_RB = 8;                   // vocabulary rows per slot
+constexpr int KV_STG = 4;                  // cross attention: stages (8 keys each) of the per-warp K/V ring
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -204,14 +205,18 @@ dec4_kernel(const Dec3Args a) {
     float* ML = ao + 64;              // [2]
     float* xs = ML + 4;               // logits stage: [RC][D] LayerNorm rows, then merge scratch
     float* red = xs + RC * D;         // [NW*4][RC][2 + 2*KC]
+    constexpr int RINGW = (LG_NBUF * LG_RB * D * 2 > KV_STG * 8 * 128 * 4) ? LG_NBUF * LG_RB * D * 2 : KV_STG * 8 * 128 * 4;   // bytes of a warp's ring (logits rows / cross K/V batches)
     constexpr int LG_PITCH = D * 2;                                        // bytes per staged vocabulary row (rows contiguous: one bulk copy per block)
     uint8_t* ring = reinterpret_cast<uint8_t*>(red + NW * 4 * RC * 6);      // [NW][LG_NBUF][LG_RB][LG_PITCH]
-    uint64_t* lg_bar = reinterpret_cast<uint64_t*>(ring + (size_t)NW * LG_NBUF * LG_RB * LG_PITCH);   // [NW][LG_NBUF]
+    uint64_t* lg_bar = reinterpret_cast<uint64_t*>(ring + (size_t)NW * RINGW);   // [NW][LG_NBUF]
+    uint64_t* kv_bar = lg_bar + NW * LG_NBUF;   // [NW][KV_STG] cross-attention K/V ring (aliases the logits ring: different stages)
     if (lane == 0) {
+        for (int j = 0; j < KV_STG; ++j) mbar_init(kv_bar + warp * KV_STG + j, 1);
         for (int j = 0; j < LG_NBUF; ++j) mbar_init(lg_bar + warp * LG_NBUF + j, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    unsigned int kv_count = 0;   // batches this warp has pushed through its K/V ring
     unsigned int lg_count = 0;   // blocks this warp has pushed through its ring since kernel start (slot / parity bookkeeping)
     unsigned int gen = 0;
     int tr_n = 0;
@@ -315,10 +320,15 @@ dec4_kernel(const Dec3Args a) {
                     auto vp = [&](int j) { return kbase + j * ld + voff; };
                     // keys j == ci*NW + warp (mod nch*NW)
                     AttnAcc A;
-                    attn_warp(q2_s + h * 64, T, ci * NW + warp, nch * NW, kp, vp, A, a.ckv_hm ? 0 : -1);
+                    if (a.ckv_hm) {   // contiguous head-major block: 8-key batches by bulk copy into this warp's ring (shared with the logits stage)
+                        attn_warp_bulk<KV_STG, KVT>(q2_s + h * 64, kbase, T, ci * NW + warp, nch * NW, 0, ring + (size_t)warp * RINGW,
+                                                    kv_bar + warp * KV_STG, kv_count, A);
+                    } else {
+                        attn_warp(q2_s + h * 64, T, ci * NW + warp, nch * NW, kp, vp, A, -1);
+                    }
                     if (lane < 4) {
 #pragma unroll
-                        for (int c = 0; c < 16; ++c) wo[warp * 64 + lane * 16 + c] = A.o[c];
+                        for (int c = 0; c < 16; ++c) wo[warp * 64 + (a.ckv_hm ? attn_bulk_dim<KVT>(lane, c) : lane * 16 + c)] = A.o[c];
                     }
                     if (lane == 0) { wm[warp] = A.m; wl[warp] = A.l; }
                     __syncthreads();
@@ -430,7 +440,7 @@ dec4_kernel(const Dec3Args a) {
             // Stream the embedding matrix through this warp's ring: 8-row blocks, one bulk copy (TMA engine)
             // per row into a bank-spread slot, completion on the slot's mbarrier; 2 blocks always in flight.
             const int n_blk = (V + LG_RB - 1) / LG_RB;
-            uint8_t* wring = ring + (size_t)warp * LG_NBUF * LG_RB * LG_PITCH;
+            uint8_t* wring = ring + (size_t)warp * RINGW;
             uint64_t* wbar = lg_bar + warp * LG_NBUF;
             auto issue = [&](int blk, unsigned int cnt) {
                 if (blk >= n_blk) return;
@@ -632,7 +642,7 @@ dec4_kernel(const Dec3Args a) {
 template <int D, int RC>
 size_t dec4_smem() {
     return sizeof(float) * ((size_t)12 * D + CS * 68 + 2 * NW + NW * 64 + 64 + 4 + (size_t)RC * D + (size_t)NW * 4 * RC * 6 + 16) +
-           (size_t)NW * LG_NBUF * LG_RB * (D * 2) + NW * LG_NBUF * 8 + 16;
+           (size_t)NW * std::max(LG_NBUF * LG_RB * D * 2, KV_STG * 8 * 128 * 4) + NW * LG_NBUF * 8 + NW * KV_STG * 8 + 16;
 }
 
 template <int D, int RC, typename KVT>
