@@ -208,6 +208,7 @@ struct Dec3Args {
     const float* tok_emb = nullptr;       // fp32 [V][d] (embedding lookup)
     const float* pos_emb = nullptr;
     const void* E = nullptr;              // logits matrix [V][d] fp16 or fp32
+    const void* E_tiled = nullptr;        // decoder4.cu: the same matrix as contiguous half-tiles [ceil(V/16)][2][16][d/2] fp16
     const float *lnf_g = nullptr, *lnf_b = nullptr;
     float lnf_eps = 1e-5f;
     // state

@@ -204,12 +204,14 @@ dec4_kernel(const Dec3Args a) {
     float* ao = wo + NW * 64;         // [64]
     float* ML = ao + 64;              // [2]
     float* xs = ML + 4;               // logits stage: [RC][D] LayerNorm rows, then merge scratch
-    float* red = xs + RC * D;         // [NW*4][RC][2 + 2*KC]
+    float* red = xs + RC * D;         // [NW][8 rows][m, s, best value, best id] logits merge scratch (sized [NW*4][RC][2 + 2*KC])
     constexpr int RINGW = (LG_NBUF * LG_RB * D * 2 > KV_STG * 8 * 128 * 4) ? LG_NBUF * LG_RB * D * 2 : KV_STG * 8 * 128 * 4;   // bytes of a warp's ring (logits rows / cross K/V batches)
     constexpr int LG_PITCH = D * 2;                                        // bytes per staged vocabulary row (rows contiguous: one bulk copy per block)
     uint8_t* ring = reinterpret_cast<uint8_t*>(red + NW * 4 * RC * 6);      // [NW][LG_NBUF][LG_RB][LG_PITCH]
     uint64_t* lg_bar = reinterpret_cast<uint64_t*>(ring + (size_t)NW * RINGW);   // [NW][LG_NBUF]
     uint64_t* kv_bar = lg_bar + NW * LG_NBUF;   // [NW][KV_STG] cross-attention K/V ring (aliases the logits ring: different stages)
+    uint4* pl_hi = reinterpret_cast<uint4*>(kv_bar + NW * KV_STG);   // logits stage: fragment-order fp16 hi plane of the 8 (padded) LayerNorm rows [D/32][32]
+    uint4* pl_lo = pl_hi + (D / 32) * 32;                           // same, residual * 2^11
     if (lane == 0) {
         for (int j = 0; j < KV_STG; ++j) mbar_init(kv_bar + warp * KV_STG + j, 1);
         for (int j = 0; j < LG_NBUF; ++j) mbar_init(lg_bar + warp * LG_NBUF + j, 1);
@@ -429,130 +431,125 @@ dec4_kernel(const Dec3Args a) {
         // ================= logits (all CTAs): LN(x) tok_emb^T + mask + online softmax + candidates
         {
             const bool use_mask = a.is_special != nullptr && (a.mask_mode == 1 || (a.mask_mode == 2 && p + 1 <= 5));
-            const __half* E = reinterpret_cast<const __half*>(a.E);
-            const int sub = lane >> 3, l8 = lane & 7;
+            const __half* Et = reinterpret_cast<const __half*>(a.E_tiled);
             stage_ln<RC>(a.x, 0, R, D, a.lnf_g, a.lnf_b, a.lnf_eps, a.eps_outside, xs);
             __syncthreads();
+            // fp32 rows -> fp16 hi / lo planes in MMA fragment order (decoder5.cu); rows >= R are zero
+            for (int i = tid; i < 8 * (D / 4); i += NT) {
+                const int row = i / (D / 4), c4 = i % (D / 4);
+                const float4 v = row < RC ? *reinterpret_cast<const float4*>(xs + row * D + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                store_frag(pl_hi, pl_lo, D / 32, row, c4 * 4, v);
+            }
+            __syncthreads();
             WB_TRACE();
-            float m_run = -INFINITY, s_run = 0.0f;
-            Cand<KC> cand;
-            cand.init();
-            // Stream the embedding matrix through this warp's ring: 8-row blocks, one bulk copy (TMA engine)
-            // per row into a bank-spread slot, completion on the slot's mbarrier; 2 blocks always in flight.
-            const int n_blk = (V + LG_RB - 1) / LG_RB;
+            // Swap-AB tensor-core product: a warp owns tiles of 16 vocabulary rows (M), the 8 padded batch rows are N, K = D.
+            // The matrix is streamed as contiguous half-tiles [16][D/2] (one bulk copy each, TMA engine) through this warp's
+            // ring -- LG_NBUF-1 copies in flight while the MMAs of the current half-tile run from shared memory.
+            const int g = lane >> 2, t = lane & 3;
+            constexpr int KH = D / 2, NCH = KH / 32;               // columns / 32-column chunks per half-tile
+            constexpr uint32_t BLKB = 16 * KH * 2;                 // bytes per half-tile
+            static_assert(LG_NBUF * LG_RB * D * 2 >= LG_NBUF * (int)BLKB, "ring slot too small");
+            const int v_tiles = (V + 15) / 16;
+            const int my_tiles = gw < v_tiles ? (v_tiles - gw + n_gw - 1) / n_gw : 0;
+            const int total = my_tiles * 2;                        // half-tiles of this warp
             uint8_t* wring = ring + (size_t)warp * RINGW;
             uint64_t* wbar = lg_bar + warp * LG_NBUF;
-            auto issue = [&](int blk, unsigned int cnt) {
-                if (blk >= n_blk) return;
-                const int slot = cnt % LG_NBUF;
-                const int rows = min(LG_RB, V - blk * LG_RB);
-                if (lane == 0) {
-                    mbar_expect_tx(wbar + slot, (uint32_t)rows * D * 2);
-                    bulk_g2s(wring + (size_t)slot * LG_RB * LG_PITCH, E + (int64_t)blk * LG_RB * D, (uint32_t)rows * D * 2, wbar + slot);
+            auto issue = [&](int it) {
+                if (it < total && lane == 0) {
+                    const int vt = gw + (it >> 1) * n_gw;
+                    const int slot = (int)((lg_count + (unsigned int)it) % LG_NBUF);
+                    mbar_expect_tx(wbar + slot, BLKB);
+                    bulk_g2s(wring + (size_t)slot * BLKB, Et + ((int64_t)vt * 2 + (it & 1)) * 16 * KH, BLKB, wbar + slot);
                 }
             };
-            unsigned int c_issue = lg_count, c_use = lg_count;
-            int blk_issue = gw;
+            float m_run[2] = {-INFINITY, -INFINITY}, s_run[2] = {0.0f, 0.0f}, bv[2] = {-INFINITY, -INFINITY};
+            int bi[2] = {INT_MAX, INT_MAX};
 #pragma unroll
-            for (int j = 0; j < LG_NBUF - 1; ++j) { issue(blk_issue, c_issue); blk_issue += n_gw; ++c_issue; }
-            for (int blk = gw; blk < n_blk; blk += n_gw) {
-                issue(blk_issue, c_issue);
-                blk_issue += n_gw;
-                ++c_issue;
-                const int slot = c_use % LG_NBUF;
-                mbar_wait(wbar + slot, (c_use / LG_NBUF) & 1);
-                const uint8_t* sl = wring + (size_t)slot * LG_RB * LG_PITCH;
-                float acc[2][RC];
+            for (int j = 0; j < LG_NBUF - 1; ++j) issue(j);
+            float ah[4], al[4];
+#pragma unroll 1
+            for (int it = 0; it < total; ++it) {
+                __syncwarp();   // the slot refilled now was read one iteration ago
+                issue(it + LG_NBUF - 1);
+                const unsigned int cnt = lg_count + (unsigned int)it;
+                const int slot = (int)(cnt % LG_NBUF);
+                mbar_wait(wbar + slot, (cnt / LG_NBUF) & 1);
+                const uint8_t* blk = wring + (size_t)slot * BLKB;
+                const int half = it & 1;
+                if (half == 0) {
 #pragma unroll
-                for (int g = 0; g < 2; ++g)
-#pragma unroll
-                    for (int rr = 0; rr < RC; ++rr) acc[g][rr] = 0.0f;
-#pragma unroll
-                for (int k0 = 0; k0 < D; k0 += 64) {
-                    // rows are D*2 bytes apart (a multiple of 128 B), so the four sub-groups would hit the same banks:
-                    // rotate the 16-byte chunk a lane takes within each 64-element group by 2*sub (sum is unchanged)
-                    const int kk = k0 + ((l8 + 2 * sub) & 7) * 8;
-                    float w[2][8];
-#pragma unroll
-                    for (int g = 0; g < 2; ++g) cvt8(*reinterpret_cast<const uint4*>(sl + (size_t)(g * 4 + sub) * LG_PITCH + kk * 2), w[g]);
-#pragma unroll
-                    for (int rr = 0; rr < RC; ++rr)
-#pragma unroll
-                        for (int g = 0; g < 2; ++g) acc[g][rr] = dot8_acc<RC>(w[g], xs + rr * D + kk, acc[g][rr]);
+                    for (int c = 0; c < 4; ++c) { ah[c] = 0.0f; al[c] = 0.0f; }
                 }
 #pragma unroll
-                for (int g = 0; g < 2; ++g)
+                for (int c = 0; c < NCH; ++c) {
+                    // A fragment: 8 consecutive halves of rows g and g+8 (K permutation inside the 32-column chunk, decoder5.cu)
+                    const uint4 a0 = *reinterpret_cast<const uint4*>(blk + (size_t)g * (KH * 2) + c * 64 + t * 16);
+                    const uint4 a8 = *reinterpret_cast<const uint4*>(blk + (size_t)(g + 8) * (KH * 2) + c * 64 + t * 16);
+                    const int chunk = half * NCH + c;
+                    const uint4 bh = pl_hi[chunk * 32 + lane];
+                    const uint4 bl = pl_lo[chunk * 32 + lane];
+                    mma16816(ah, a0.x, a8.x, a0.y, a8.y, bh.x, bh.y);
+                    mma16816(ah, a0.z, a8.z, a0.w, a8.w, bh.z, bh.w);
+                    mma16816(al, a0.x, a8.x, a0.y, a8.y, bl.x, bl.y);
+                    mma16816(al, a0.z, a8.z, a0.w, a8.w, bl.z, bl.w);
+                }
+                if (half == 1) {
+                    // C fragment: c0,c1 -> (vocabulary row g, batch rows 2t, 2t+1), c2,c3 -> (row g+8, same batch rows)
+                    const int n0 = (gw + (it >> 1) * n_gw) * 16;
 #pragma unroll
-                    for (int rr = 0; rr < RC; ++rr) {
-                        float v = acc[g][rr];
-                        v += __shfl_xor_sync(0xffffffffu, v, 4);
-                        v += __shfl_xor_sync(0xffffffffu, v, 2);
-                        v += __shfl_xor_sync(0xffffffffu, v, 1);
-                        acc[g][rr] = v;
-                    }
-                __syncwarp();   // slot fully read before it is refilled two iterations later
-                ++c_use;
-                if (l8 < RC && l8 < R) {
-#pragma unroll
-                    for (int g = 0; g < 2; ++g) {
-                        const int n = blk * LG_RB + g * 4 + sub;
-                        if (n < V) {
-                            const float raw = pick_row<RC>(acc[g], l8);
+                    for (int c = 0; c < 4; ++c) {
+                        const int n = n0 + g + (c >> 1) * 8, e = c & 1;
+                        if (n < V && 2 * t + e < R) {
+                            const float raw = fmaf(al[c], 1.0f / 2048.0f, ah[c]);
                             const float v = (use_mask && a.is_special[n]) ? __fadd_rn(raw, -INFINITY) : raw;
                             if (v > -INFINITY) {
-                                if (v > m_run) { s_run = s_run * expf(m_run - v) + 1.0f; m_run = v; }
-                                else s_run += expf(v - m_run);
+                                if (v > m_run[e]) { s_run[e] = s_run[e] * expf(m_run[e] - v) + 1.0f; m_run[e] = v; }
+                                else s_run[e] += expf(v - m_run[e]);
                             }
-                            cand.push(v, n);
+                            if (v > bv[e] || (v == bv[e] && n < bi[e])) { bv[e] = v; bi[e] = n; }
                         }
                     }
                 }
             }
-            lg_count = c_use;
+            lg_count += (unsigned int)total;
             WB_TRACE();
-            // merge the 4 sub-group states of every batch row inside the warp (lanes l8, l8+8, l8+16, l8+24) ...
+            // merge the 8 lanes that share t (batch rows 2t, 2t+1), then the 8 warps through shared memory
 #pragma unroll
-            for (int off = 8; off < 32; off <<= 1) {
-                const float m2 = __shfl_xor_sync(0xffffffffu, m_run, off);
-                const float s2 = __shfl_xor_sync(0xffffffffu, s_run, off);
-                float cv[KC];
-                int ci[KC];
+            for (int e = 0; e < 2; ++e) {
 #pragma unroll
-                for (int k = 0; k < KC; ++k) { cv[k] = __shfl_xor_sync(0xffffffffu, cand.v[k], off); ci[k] = __shfl_xor_sync(0xffffffffu, cand.i[k], off); }
-                const float mn = fmaxf(m_run, m2);
-                const float e1 = m_run > -INFINITY ? expf(m_run - mn) : 0.0f;
-                const float e2 = m2 > -INFINITY ? expf(m2 - mn) : 0.0f;
-                s_run = s_run * e1 + s2 * e2;
-                m_run = mn;
-#pragma unroll
-                for (int k = 0; k < KC; ++k) cand.push(cv[k], ci[k]);
-            }
-            // ... then the 8 warps through shared memory: one record per (warp, row)
-            if (sub == 0 && l8 < RC) {
-                float* rec = red + (warp * RC + l8) * (2 + 2 * KC);
-                rec[0] = m_run;
-                rec[1] = s_run;
-#pragma unroll
-                for (int k = 0; k < KC; ++k) { rec[2 + k] = cand.v[k]; rec[2 + KC + k] = __int_as_float(cand.i[k]); }
+                for (int off = 4; off < 32; off <<= 1) {
+                    const float m2 = __shfl_xor_sync(0xffffffffu, m_run[e], off), s2 = __shfl_xor_sync(0xffffffffu, s_run[e], off);
+                    const float v2 = __shfl_xor_sync(0xffffffffu, bv[e], off);
+                    const int i2 = __shfl_xor_sync(0xffffffffu, bi[e], off);
+                    const float mn = fmaxf(m_run[e], m2);
+                    s_run[e] = (m_run[e] > -INFINITY ? s_run[e] * expf(m_run[e] - mn) : 0.0f) + (m2 > -INFINITY ? s2 * expf(m2 - mn) : 0.0f);
+                    m_run[e] = mn;
+                    if (v2 > bv[e] || (v2 == bv[e] && i2 < bi[e])) { bv[e] = v2; bi[e] = i2; }
+                }
+                if (g == 0) {
+                    float* rec = red + (warp * 8 + 2 * t + e) * 4;
+                    rec[0] = m_run[e]; rec[1] = s_run[e]; rec[2] = bv[e]; rec[3] = __int_as_float(bi[e]);
+                }
             }
             __syncthreads();
-            if (tid < RC && tid < R) {
+            if (tid < R) {
                 float M = -INFINITY;
-                for (int w2 = 0; w2 < NW; ++w2) M = fmaxf(M, red[(w2 * RC + tid) * (2 + 2 * KC)]);
-                float Ssum = 0.0f;
-                Cand<KC> best;
-                best.init();
+                for (int w2 = 0; w2 < NW; ++w2) M = fmaxf(M, red[(w2 * 8 + tid) * 4]);
+                float Ssum = 0.0f, best_v = -INFINITY;
+                int best_i = INT_MAX;
                 for (int w2 = 0; w2 < NW; ++w2) {
-                    const float* rec = red + (w2 * RC + tid) * (2 + 2 * KC);
+                    const float* rec = red + (w2 * 8 + tid) * 4;
                     if (rec[0] > -INFINITY) Ssum += rec[1] * expf(rec[0] - M);
-#pragma unroll
-                    for (int k = 0; k < KC; ++k) best.push(rec[2 + k], __float_as_int(rec[2 + KC + k]));
+                    const int ci = __float_as_int(rec[3]);
+                    if (rec[2] > best_v || (rec[2] == best_v && ci < best_i)) { best_v = rec[2]; best_i = ci; }
                 }
                 const int64_t o = (int64_t)blockIdx.x * R + tid;
                 a.lg_m[o] = M;
                 a.lg_s[o] = Ssum;
+                a.lg_v[o * KC] = best_v;
+                a.lg_i[o * KC] = best_i;
 #pragma unroll
-                for (int k = 0; k < KC; ++k) { a.lg_v[o * KC + k] = best.v[k]; a.lg_i[o * KC + k] = best.i[k]; }
+                for (int k = 1; k < KC; ++k) { a.lg_v[o * KC + k] = -INFINITY; a.lg_i[o * KC + k] = INT_MAX; }
             }
         }
         WB_TRACE();
@@ -642,7 +639,7 @@ dec4_kernel(const Dec3Args a) {
 template <int D, int RC>
 size_t dec4_smem() {
     return sizeof(float) * ((size_t)12 * D + CS * 68 + 2 * NW + NW * 64 + 64 + 4 + (size_t)RC * D + (size_t)NW * 4 * RC * 6 + 16) +
-           (size_t)NW * std::max(LG_NBUF * LG_RB * D * 2, KV_STG * 8 * 128 * 4) + NW * LG_NBUF * 8 + NW * KV_STG * 8 + 16;
+           (size_t)NW * std::max(LG_NBUF * LG_RB * D * 2, KV_STG * 8 * 128 * 4) + NW * LG_NBUF * 8 + NW * KV_STG * 8 + (size_t)2 * (D / 32) * 32 * 16 + 16;
 }
 
 template <int D, int RC, typename KVT>
@@ -691,7 +688,7 @@ bool launch4_t(const Dec3Args& a, cudaStream_t st) {
 // Returns false when this configuration is not covered (caller falls back to decoder3.cu).
 bool launch_dec4(const Dec3Args& a, bool w_half, cudaStream_t st) {
     if (!w_half || a.R > 8 || a.R < 1 || a.k != 1 || !a.greedy || a.use_cur_tok || a.anc != nullptr || a.logits_out != nullptr) return false;
-    if (a.H * 64 != a.d || a.H > CS) return false;
+    if (a.H * 64 != a.d || a.H > CS || a.E_tiled == nullptr) return false;
 #define WB_D4(DD)                                                                                         \
     do {                                                                                                  \
         if (a.kv_half) return a.R <= 4 ? launch4_t<DD, 4, __half>(a, st) : launch4_t<DD, 8, __half>(a, st); \

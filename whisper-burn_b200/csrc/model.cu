@@ -209,6 +209,17 @@ void model_finalize(Model& m) {
     const Tensor& emb = need(m, "decoder/token_embedding/weight", {D.n_vocab, d});
     m.tok_emb32 = up32(m, emb.second);
     if (h16) m.tok_emb16 = up16(m, emb.second);
+    if (h16 && (d == 128 || d == 384)) {
+        // decoder4.cu streams the logits matrix as contiguous half-tiles [tile of 16 rows][K half][16][d/2] (one bulk copy each,
+        // rows >= V are zero) and feeds them to mma.sync from shared memory
+        const int V = D.n_vocab, tiles = (V + 15) / 16, kh = d / 2;
+        std::vector<float> tl((size_t)tiles * 2 * 16 * kh, 0.0f);
+        for (int t = 0; t < tiles; ++t)
+            for (int hh = 0; hh < 2; ++hh)
+                for (int rr = 0; rr < 16 && t * 16 + rr < V; ++rr)
+                    std::memcpy(&tl[(((size_t)t * 2 + hh) * 16 + rr) * kh], &emb.second[(size_t)(t * 16 + rr) * d + (size_t)hh * kh], sizeof(float) * kh);
+        m.tok_emb16_tiled = up16(m, tl);
+    }
     m.dec_pos = up32(m, need(m, "decoder/positional_embedding", {D.n_text_ctx, d}).second);
     m.dec.resize(D.n_text_layer);
     for (int i = 0; i < D.n_text_layer; ++i) {

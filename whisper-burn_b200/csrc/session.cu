@@ -485,6 +485,7 @@ void Session::launch_v3(int R_, int pos0, int n_steps, int logits_from, bool use
     a.eps_outside = m->ln_eps_outside; a.qk_scale = (float)std::pow((double)d / (double)H, -0.25);
     a.layers = d3_layers.p; a.tok_emb = m->tok_emb32; a.pos_emb = m->dec_pos;
     a.E = m->fp16_exact ? (const void*)m->tok_emb16 : (const void*)m->tok_emb32;
+    a.E_tiled = m->tok_emb16_tiled;
     a.lnf_g = m->dec_ln.g; a.lnf_b = m->dec_ln.b; a.lnf_eps = m->dec_ln.eps;
     a.x = dx.p; a.q = dq.p; a.att = datt.p; a.hid = dhid.p;
     a.x2 = dx2.p; a.ypart = ypart.p; a.lgbuf = logits.p; a.att_pl = att_pl.p; a.hid_pl = hid_pl.p; a.d5 = d5_desc.p; a.ckv_hm = ckv_hm ? 1 : 0;

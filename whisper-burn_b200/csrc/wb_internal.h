@@ -132,6 +132,7 @@ struct Model {
     // decoder
     float* tok_emb32 = nullptr;   // [V][d] (always kept: embedding lookup + fp32 logits path)
     __half* tok_emb16 = nullptr;  // [V][d] when fp16_exact
+    __half* tok_emb16_tiled = nullptr;   // [ceil(V/16)][2][16][d/2] half-tiles for decoder4.cu (d = 128 / 384 only)
     float* dec_pos = nullptr;     // [n_text_ctx][d]
     std::vector<DecBlockW> dec;
     LayerNormW dec_ln;
