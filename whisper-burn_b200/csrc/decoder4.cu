@@ -63,6 +63,7 @@ template <int NR, int VPL>
 struct RowRegs {
     uint4 v[NR][VPL];
     float bias[NR];   // fetched together with the rows, before the barrier
+    float bias_own;   // bias of row (lane >> 1): the row whose sum warp_reduce_owner leaves in this lane
 };
 
 // rows row0, row0 + step, ... of W[.][K] (fp16) -> registers; lane-strided 16-byte vectors
@@ -72,6 +73,7 @@ __device__ __forceinline__ void load_rows(const __half* __restrict__ W, const fl
     const int lane = threadIdx.x & 31, nv = K / 8;
 #pragma unroll
     for (int i = 0; i < NR; ++i) r.bias[i] = __ldg(bias + row0 + i * step);
+    r.bias_own = __ldg(bias + row0 + min(lane >> 1, NR - 1) * step);
 #pragma unroll
     for (int i = 0; i < NR; ++i) {
         const uint4* p = reinterpret_cast<const uint4*>(W + (int64_t)(row0 + i * step) * K);
@@ -83,7 +85,45 @@ __device__ __forceinline__ void load_rows(const __half* __restrict__ W, const fl
     }
 }
 // acc[i] = <row i, xs> (all lanes)
-template <int NR, int VPL>
+// Sums of NR values over the warp with 16 + ... shuffles instead of 5 * NR: recursive halving on the value index -- after the
+// rounds with lane offsets 16, 8, 4, 2 every lane holds ONE value (index lane >> 1), a last exchange completes it.  Returns
+// the total of value (lane >> 1) (NR <= 16; values >= NR are zero padding).
+template <int NR>
+__device__ __forceinline__ float warp_reduce_owner(const float (&acc)[NR]) {
+    const int lane = threadIdx.x & 31;
+    float v8[8], v4[4], v2[2];
+    {
+        const bool up = lane & 16;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float lo = i < NR ? acc[i] : 0.0f, hi = i + 8 < NR ? acc[i + 8] : 0.0f;
+            const float recv = __shfl_xor_sync(0xffffffffu, up ? lo : hi, 16);
+            v8[i] = (up ? hi : lo) + recv;
+        }
+    }
+    {
+        const bool up = lane & 8;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float recv = __shfl_xor_sync(0xffffffffu, up ? v8[i] : v8[i + 4], 8);
+            v4[i] = (up ? v8[i + 4] : v8[i]) + recv;
+        }
+    }
+    {
+        const bool up = lane & 4;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float recv = __shfl_xor_sync(0xffffffffu, up ? v4[i] : v4[i + 2], 4);
+            v2[i] = (up ? v4[i + 2] : v4[i]) + recv;
+        }
+    }
+    const bool up = lane & 2;
+    float v = (up ? v2[1] : v2[0]) + __shfl_xor_sync(0xffffffffu, up ? v2[0] : v2[1], 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+
+template <int NR, int VPL, bool REDUCE = true>
 __device__ __forceinline__ void dot_rows1(const RowRegs<NR, VPL>& r, const float* xs, int K, float (&acc)[NR]) {
     const int lane = threadIdx.x & 31, nv = K / 8;
 #pragma unroll
@@ -105,8 +145,10 @@ __device__ __forceinline__ void dot_rows1(const RowRegs<NR, VPL>& r, const float
             }
         }
     }
+    if constexpr (REDUCE) {
 #pragma unroll
-    for (int i = 0; i < NR; ++i) acc[i] = warp_sum(acc[i]);
+        for (int i = 0; i < NR; ++i) acc[i] = warp_sum(acc[i]);
+    }
 }
 
 // store v into the same shared-memory slot of every CTA of the cluster (lane r -> rank r)
@@ -245,12 +287,16 @@ dec4_kernel(const Dec3Args a) {
                 ln_block<D>(x_s, l > 0 ? dl_s : nullptr, xn_s, W.ln1_g, W.ln1_b, W.ln1_eps, a.eps_outside, wm);   // l > 0: += MLP2 of the previous layer
                 {
                     float acc[NR_QKV];
-                    dot_rows1<NR_QKV, VPL>(w_qkv, xn_s, D, acc);
+                    dot_rows1<NR_QKV, VPL, false>(w_qkv, xn_s, D, acc);
+                    float mine = warp_reduce_owner<NR_QKV>(acc);   // lane 2i: sum of row i
+                    {
+                        mine = __fadd_rn(mine, w_qkv.bias_own);
+                        if (rank * (3 * D / CS) + warp + (lane >> 1) * NW < 2 * D) mine = __fmul_rn(mine, scale);
+                    }
 #pragma unroll
                     for (int i = 0; i < NR_QKV; ++i) {
                         const int n = rank * (3 * D / CS) + warp + i * NW;
-                        float v = __fadd_rn(acc[i], w_qkv.bias[i]);
-                        if (n < 2 * D) v = __fmul_rn(v, scale);
+                        const float v = __shfl_sync(0xffffffffu, mine, 2 * i);
                         bcast(cl, qkv_s + n, v);
                         if (lane == 0 && n >= D) {
                             if (n < 2 * D) kcl[((int64_t)row * t_max + p) * D + (n - D)] = (KVT)v;
@@ -394,11 +440,14 @@ dec4_kernel(const Dec3Args a) {
                 ln_block<D>(x_s, dl_s, xn_s, W.ln3_g, W.ln3_b, W.ln3_eps, a.eps_outside, wm);
                 {
                     float acc[NR_H];
-                    dot_rows1<NR_H, VPL>(w_1, xn_s, D, acc);
+                    dot_rows1<NR_H, VPL, false>(w_1, xn_s, D, acc);
+                    // lane 2i ends up with the sum of row i: ONE erf-GELU per row instead of one per lane and row
+                    float mine = warp_reduce_owner<NR_H>(acc);
+                    mine = gelu_erf(__fadd_rn(mine, w_1.bias_own));
 #pragma unroll
                     for (int i = 0; i < NR_H; ++i) {
                         const int n = rank * (4 * D / CS) + warp + i * NW;
-                        bcast(cl, hid_s + n, gelu_erf(__fadd_rn(acc[i], w_1.bias[i])));
+                        bcast(cl, hid_s + n, __shfl_sync(0xffffffffu, mine, 2 * i));
                     }
                 }
                 RowRegs<NR_D, VPL4> w_2;
@@ -557,63 +606,51 @@ dec4_kernel(const Dec3Args a) {
         WB_TRACE();
         // ================= finish: one CTA per row (greedy: beam.rs:9-37 with beam_size 1)
         for (int r = blockIdx.x; r < R; r += gridDim.x) {
-            float* s_f = wm;
-            int* s_i = reinterpret_cast<int*>(wl);
-            const int NP = gridDim.x;
-            float mx = -INFINITY;
-            for (int c = tid; c < NP; c += NT) mx = fmaxf(mx, __ldcg(a.lg_m + (int64_t)c * R + r));
+            if (warp == 0) {   // one warp per row over the per-CTA records (this code runs once per step: keep it small)
+                const int NP = gridDim.x;   // <= 128 co-resident CTAs: at most 4 records per lane, all loads issued before any use
+                float rm[4], rs[4], rv[4];
+                int ri[4];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-            if (lane == 0) s_f[warp] = mx;
-            __syncthreads();
-            mx = s_f[0];
+                for (int k = 0; k < 4; ++k) {
+                    const int c = min(lane + 32 * k, NP - 1);
+                    rm[k] = __ldcg(a.lg_m + (int64_t)c * R + r);
+                    rs[k] = __ldcg(a.lg_s + (int64_t)c * R + r);
+                    rv[k] = __ldcg(a.lg_v + ((int64_t)c * R + r) * KC);
+                    ri[k] = __ldcg(a.lg_i + ((int64_t)c * R + r) * KC);
+                }
+                float mx = -INFINITY;
 #pragma unroll
-            for (int w2 = 1; w2 < NW; ++w2) mx = fmaxf(mx, s_f[w2]);
-            __syncthreads();
-            float se = 0.0f;
-            for (int c = tid; c < NP; c += NT) {
-                const float m = __ldcg(a.lg_m + (int64_t)c * R + r);
-                if (m > -INFINITY) se += __ldcg(a.lg_s + (int64_t)c * R + r) * expf(m - mx);
-            }
-            se = warp_sum(se);
-            if (lane == 0) s_f[warp] = se;
-            __syncthreads();
-            se = 0.0f;
+                for (int k = 0; k < 4; ++k)
+                    if (lane + 32 * k < NP) mx = fmaxf(mx, rm[k]);
 #pragma unroll
-            for (int w2 = 0; w2 < NW; ++w2) se += s_f[w2];
-            const float lse = logf(se);
-            __syncthreads();
-            float bv = -INFINITY;
-            int bi = INT_MAX;
-            for (int c = tid; c < NP * KC; c += NT) {
-                const int part = c / KC, k = c % KC;
-                const int idx = __ldcg(a.lg_i + ((int64_t)part * R + r) * KC + k);
-                if (idx == INT_MAX) continue;
-                const float v = __fsub_rn(__fsub_rn(__ldcg(a.lg_v + ((int64_t)part * R + r) * KC + k), mx), lse);
-                if (v > bv || (v == bv && idx < bi)) { bv = v; bi = idx; }
-            }
+                for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                float se = 0.0f, bv = -INFINITY;
+                int bi = INT_MAX;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-            }
-            if (lane == 0) { s_f[warp] = bv; s_i[warp] = bi; }
-            __syncthreads();
-            if (tid == 0) {
-                bv = s_f[0];
-                bi = s_i[0];
-                for (int w2 = 1; w2 < NW; ++w2)
-                    if (s_f[w2] > bv || (s_f[w2] == bv && s_i[w2] < bi)) { bv = s_f[w2]; bi = s_i[w2]; }
-                a.topk_id[r] = bi == INT_MAX ? -1 : bi;
-                a.topk_lp[r] = bv;
-                if (!__ldcg(a.finished + r)) {
-                    a.tokens[(int64_t)r * t_max + p + 1] = bi;
-                    a.lengths[r] = p + 2;
-                    if (bi == a.eot) a.finished[r] = 1;
+                for (int k = 0; k < 4; ++k) {
+                    if (lane + 32 * k < NP) {
+                        if (rm[k] > -INFINITY) se += rs[k] * expf(rm[k] - mx);
+                        if (ri[k] != INT_MAX && (rv[k] > bv || (rv[k] == bv && ri[k] < bi))) { bv = rv[k]; bi = ri[k]; }
+                    }
+                }
+                se = warp_sum(se);
+                const float lse = logf(se);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                }
+                if (lane == 0) {
+                    a.topk_id[r] = bi == INT_MAX ? -1 : bi;
+                    a.topk_lp[r] = __fsub_rn(__fsub_rn(bv, mx), lse);
+                    if (!__ldcg(a.finished + r)) {
+                        a.tokens[(int64_t)r * t_max + p + 1] = bi;
+                        a.lengths[r] = p + 2;
+                        if (bi == a.eot) a.finished[r] = 1;
+                    }
                 }
             }
-            __syncthreads();
         }
         WB_TRACE();
         grid_sync(a.bar, gen);
