@@ -312,7 +312,7 @@ def run_ours(args):
                 note = ("latency-bound chain of 32 cluster + 3 grid barriers per step (ncu: issue active 9.8 %, DRAM 1.9 % of peak, L2 hit 70 %): "
                         "DRAM traffic is BELOW the algorithmic bytes because weights and K/V stay L2-resident across steps")
                 if args.model == "tiny.en" and args.kv == "f32" and R == 3 and args.max_depth == 100:
-                    traffic = 2.625e9 + 12.15e6
+                    traffic = 2.265e9 + 9.27e6
             elif dec == 5:
                 kernel = (f"dec5_kernel<{(R + 7) // 8},..> (persistent batched tensor-core decoder, decoder5.cu: mma.sync swap-AB, fp16 hi/lo activation "
                           f"planes; one launch = {n_launch_steps} positions)")
@@ -370,7 +370,7 @@ def run_ours(args):
 _REAL_STDOUT = None
 # DRAM bytes per decoder step of the small.en / 24-row launch (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum of the
 # dec5 launch divided by its positions; profiles/r01_dec5_ncu_full_summary.txt)
-D5_SMALL_EN_DRAM_BYTES_PER_STEP = 1.39e9
+D5_SMALL_EN_DRAM_BYTES_PER_STEP = 1.397e9
 
 
 def emit(line: dict) -> None:
