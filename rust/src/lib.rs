@@ -31,6 +31,9 @@ pub mod ffi {
         pub fn wb_prep_audio(device: c_int, wave: *const f32, n_batch: i64, n_samples: i64, mel_out: *mut f32, n_frames_out: *mut i64) -> c_int;
         pub fn wb_model_create(dims: *const wb_dims, device: c_int, out: *mut *mut c_void) -> c_int;
         pub fn wb_model_set_tensor(m: *mut c_void, path: *const c_char, data: *const f32, shape: *const i64, ndim: c_int) -> c_int;
+        pub fn wb_npy_tree_probe(dir: *const c_char, dims_out: *mut wb_dims) -> c_int;
+        pub fn wb_model_load_npy_tree(dir: *const c_char, device: c_int, ln_eps_outside: c_int, out: *mut *mut c_void) -> c_int;
+        pub fn wb_load_wav(path: *const c_char, strict_16k_mono: c_int, out: *mut f32, capacity: i64, n_samples_out: *mut i64, sample_rate_out: *mut i64, channels_out: *mut c_int) -> c_int;
         pub fn wb_model_set_layernorm_eps_mode(m: *mut c_void, outside: c_int) -> c_int;
         pub fn wb_model_finalize(m: *mut c_void) -> c_int;
         pub fn wb_model_destroy(m: *mut c_void);
@@ -90,6 +93,15 @@ pub mod model {
             }
             check(unsafe { ffi::wb_model_finalize(w.h) })?;
             Ok(w)
+        }
+        /// model::load::load_whisper (src/model/load.rs:295-310): the directory python/dump.py writes.
+        pub fn load_npy_tree(dir: &str) -> Result<Self, Error> {
+            let c = CString::new(dir)?;
+            let mut config: WhisperConfig = unsafe { std::mem::zeroed() };
+            check(unsafe { ffi::wb_npy_tree_probe(c.as_ptr(), &mut config) })?;
+            let mut h = std::ptr::null_mut();
+            check(unsafe { ffi::wb_model_load_npy_tree(c.as_ptr(), 0, 1, &mut h) })?;
+            Ok(Whisper { h, config })
         }
         /// mod.rs:52-54: mel [n_batch, 80, n_ctx] -> [n_batch, (n_ctx-1)/2+1, d]
         pub fn forward_encoder(&self, mel: &[f32], n_batch: usize, n_ctx: usize) -> Result<Vec<f32>, Error> {
