@@ -308,6 +308,21 @@ def test_batched_tensor_core_decoder_greedy_vs_oracle(wide, kv):
     assert solo.transcribe_windows(waves[3:4], sp, is_special_of(sp), beam_size=1, max_depth=14)[0] == got[3]
 
 
+def test_batched_tensor_core_decoder_unsplit_cross_attention():
+    """20 rows x 8 heads >= one (row, head) unit per SM: decoder5.cu runs cross attention unsplit (S = 1) and writes its output
+    directly as tensor-core planes -- the configuration class of the small.en / medium batches in BASELINE.json."""
+    dims, w_np, w_t = synth.make_weights("test-d", seed=0)
+    sp = synth.special_tokens(dims)
+    wh = model.Whisper(dims, w_np)
+    waves = [synth.waveform(24000 + 3000 * i, seed=80 + i) for i in range(20)]
+    sess = transcribe.Session(wh, max_windows=20, max_beams=1, max_text_len=4 + 6 + 1)
+    got = sess.transcribe_windows(waves, sp, is_special_of(sp), beam_size=1, max_depth=6)
+    assert sess.last_decoder() == 5
+    for i in (0, 7, 13, 19):
+        want = o_tr.mels_to_tokens(w_t, dims, sp, o_audio.prep_audio(torch.from_numpy(waves[i])[None]), beam_size=1, max_depth=6)
+        assert got[i] == want
+
+
 def test_batched_tensor_core_decoder_beams_and_logits(wide):
     dims, _, w_t, sp, wh = wide
     waves = [synth.waveform(42000 + 9000 * i, seed=60 + i) for i in range(3)]

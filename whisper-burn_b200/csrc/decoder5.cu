@@ -88,7 +88,7 @@ __device__ __forceinline__ void load_afrag(const GemmDesc& D, int d, int item, A
 // Stage slots of one layer (descriptor a.d5[l * 16 + slot]); the logits use a.d5[L * 16 + {11, 12}].
 enum { SL_LN1 = 0, SL_QKV, SL_SELF, SL_OUT, SL_LN2, SL_CQ, SL_CROSS, SL_COUT, SL_LN3, SL_MLP1, SL_MLP2, SL_LNF, SL_LOGITS, SL_COUNT };
 
-template <int NT8, int DV, typename KVT>
+template <int NT8, typename KVT>
 __global__ void __launch_bounds__(NT, 1)
 dec5_kernel(const Dec3Args a) {
     extern __shared__ __align__(16) float sm[];
@@ -149,67 +149,58 @@ dec5_kernel(const Dec3Args a) {
                     // written as fragment-order hi/lo planes for the next linear stage (every CTA copies them after the barrier).
                     // EMB: x = tok_emb[token] + pos_emb[p] (mod.rs:141-146); FOLD: x += the four MLP2 partial sums of the
                     // previous layer (fixed order); both publish the fp32 row for the residual adds of this layer.
+                    // The whole CTA works on the row (thread t owns the float4 columns t and t + 256): a single warp would spend ~2 us
+                    // in dependent arithmetic; two block reductions through shared memory instead.
                     const int r = blockIdx.x;
-                    if (r < R && warp == 0) {
-                        float4 v[DV], g4[DV], b4[DV];
+                    if (r < R) {
+                        constexpr int PT = 2;   // float4 per thread: d <= 1280 -> d / 4 <= 320 <= 2 * 256
+                        float4 v[PT], g4[PT], b4[PT];
+                        int tok = 0;
+                        if (D.stage == ST_LN_EMB) tok = a.use_cur_tok ? __ldcg(a.cur_tok + r) : __ldcg(a.tokens + (int64_t)r * t_max + p);
+                        const float* pe = a.pos_emb + (int64_t)p * d;
 #pragma unroll
-                        for (int i = 0; i < DV; ++i) {
-                            const int c = i * 32 + lane;
-                            if (c < nv) {
-                                g4[i] = __ldg(reinterpret_cast<const float4*>(D.g) + c);
-                                b4[i] = __ldg(reinterpret_cast<const float4*>(D.b) + c);
-                            }
-                        }
-                        if (D.stage == ST_LN_EMB) {
-                            const int tok = a.use_cur_tok ? __ldcg(a.cur_tok + r) : __ldcg(a.tokens + (int64_t)r * t_max + p);
-                            const float* pe = a.pos_emb + (int64_t)p * d;
-#pragma unroll
-                            for (int i = 0; i < DV; ++i) {
-                                const int c = i * 32 + lane;
-                                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (c < nv) {
-                                    const float4 e4 = __ldg(reinterpret_cast<const float4*>(a.tok_emb + (int64_t)tok * d) + c);
-                                    const float4 p4 = __ldg(reinterpret_cast<const float4*>(pe) + c);
-                                    v[i] = make_float4(__fadd_rn(e4.x, p4.x), __fadd_rn(e4.y, p4.y), __fadd_rn(e4.z, p4.z), __fadd_rn(e4.w, p4.w));
+                        for (int i = 0; i < PT; ++i) {
+                            const int c = min(tid + i * NT, nv - 1);   // clamped: all loads are issued unconditionally, masked at use
+                            g4[i] = __ldg(reinterpret_cast<const float4*>(D.g) + c);
+                            b4[i] = __ldg(reinterpret_cast<const float4*>(D.b) + c);
+                            if (D.stage == ST_LN_EMB) {
+                                const float4 e4 = __ldg(reinterpret_cast<const float4*>(a.tok_emb + (int64_t)tok * d) + c);
+                                const float4 p4 = __ldg(reinterpret_cast<const float4*>(pe) + c);
+                                v[i] = make_float4(__fadd_rn(e4.x, p4.x), __fadd_rn(e4.y, p4.y), __fadd_rn(e4.z, p4.z), __fadd_rn(e4.w, p4.w));
+                            } else {
+                                v[i] = __ldcg(reinterpret_cast<const float4*>(x + (int64_t)r * d) + c);
+                                if (D.stage != ST_LN_X) {
+                                    const float4 p0 = __ldcg(reinterpret_cast<const float4*>(yp + (int64_t)r * d) + c);
+                                    const float4 p1 = __ldcg(reinterpret_cast<const float4*>(yp + yps + (int64_t)r * d) + c);
+                                    const float4 p2 = __ldcg(reinterpret_cast<const float4*>(yp + 2 * yps + (int64_t)r * d) + c);
+                                    const float4 p3 = __ldcg(reinterpret_cast<const float4*>(yp + 3 * yps + (int64_t)r * d) + c);
+                                    v[i].x = __fadd_rn(v[i].x, __fadd_rn(__fadd_rn(p0.x, p1.x), __fadd_rn(p2.x, p3.x)));
+                                    v[i].y = __fadd_rn(v[i].y, __fadd_rn(__fadd_rn(p0.y, p1.y), __fadd_rn(p2.y, p3.y)));
+                                    v[i].z = __fadd_rn(v[i].z, __fadd_rn(__fadd_rn(p0.z, p1.z), __fadd_rn(p2.z, p3.z)));
+                                    v[i].w = __fadd_rn(v[i].w, __fadd_rn(__fadd_rn(p0.w, p1.w), __fadd_rn(p2.w, p3.w)));
                                 }
-                            }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < DV; ++i) {
-                                const int c = i * 32 + lane;
-                                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (c < nv) {
-                                    v[i] = __ldcg(reinterpret_cast<const float4*>(x + (int64_t)r * d) + c);
-                                    if (D.stage != ST_LN_X) {
-                                        const float4 p0 = __ldcg(reinterpret_cast<const float4*>(yp + (int64_t)r * d) + c);
-                                        const float4 p1 = __ldcg(reinterpret_cast<const float4*>(yp + yps + (int64_t)r * d) + c);
-                                        const float4 p2 = __ldcg(reinterpret_cast<const float4*>(yp + 2 * yps + (int64_t)r * d) + c);
-                                        const float4 p3 = __ldcg(reinterpret_cast<const float4*>(yp + 3 * yps + (int64_t)r * d) + c);
-                                        v[i].x = __fadd_rn(v[i].x, __fadd_rn(__fadd_rn(p0.x, p1.x), __fadd_rn(p2.x, p3.x)));
-                                        v[i].y = __fadd_rn(v[i].y, __fadd_rn(__fadd_rn(p0.y, p1.y), __fadd_rn(p2.y, p3.y)));
-                                        v[i].z = __fadd_rn(v[i].z, __fadd_rn(__fadd_rn(p0.z, p1.z), __fadd_rn(p2.z, p3.z)));
-                                        v[i].w = __fadd_rn(v[i].w, __fadd_rn(__fadd_rn(p0.w, p1.w), __fadd_rn(p2.w, p3.w)));
-                                    }
-                                }
-                            }
-                        }
-                        if (D.stage == ST_LN_EMB || D.stage == ST_LN_FOLD) {   // only this warp touches row r in this stage: in place
-#pragma unroll
-                            for (int i = 0; i < DV; ++i) {
-                                const int c = i * 32 + lane;
-                                if (c < nv) reinterpret_cast<float4*>(x + (int64_t)r * d)[c] = v[i];
                             }
                         }
                         float sum = 0.0f;
 #pragma unroll
-                        for (int i = 0; i < DV; ++i) sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+                        for (int i = 0; i < PT; ++i) {
+                            const int c = tid + i * NT;
+                            if (c < nv) {
+                                if (D.stage == ST_LN_EMB || D.stage == ST_LN_FOLD) reinterpret_cast<float4*>(x + (int64_t)r * d)[c] = v[i];   // only this CTA touches row r here
+                                sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+                            }
+                        }
                         sum = warp_sum(sum);
+                        if (lane == 0) red[warp] = sum;
+                        __syncthreads();
+                        sum = 0.0f;
+#pragma unroll
+                        for (int w = 0; w < NW; ++w) sum += red[w];
                         const float mean = __fdiv_rn(sum, (float)d);
                         float q = 0.0f;
 #pragma unroll
-                        for (int i = 0; i < DV; ++i) {
-                            const int c = i * 32 + lane;
-                            if (c < nv) {
+                        for (int i = 0; i < PT; ++i) {
+                            if (tid + i * NT < nv) {
                                 v[i].x = __fsub_rn(v[i].x, mean); v[i].y = __fsub_rn(v[i].y, mean);
                                 v[i].z = __fsub_rn(v[i].z, mean); v[i].w = __fsub_rn(v[i].w, mean);
                                 q = __fadd_rn(q, __fmul_rn(v[i].x, v[i].x)); q = __fadd_rn(q, __fmul_rn(v[i].y, v[i].y));
@@ -217,11 +208,16 @@ dec5_kernel(const Dec3Args a) {
                             }
                         }
                         q = warp_sum(q);
+                        if (lane == 0) red[NW + warp] = q;
+                        __syncthreads();
+                        q = 0.0f;
+#pragma unroll
+                        for (int w = 0; w < NW; ++w) q += red[NW + w];
                         const float var = __fdiv_rn(q, (float)d);
                         const float den = a.eps_outside ? __fadd_rn(__fsqrt_rn(var), D.eps) : __fsqrt_rn(__fadd_rn(var, D.eps));
 #pragma unroll
-                        for (int i = 0; i < DV; ++i) {
-                            const int c = i * 32 + lane;
+                        for (int i = 0; i < PT; ++i) {
+                            const int c = tid + i * NT;
                             if (c < nv) {
                                 float4 o;
                                 o.x = __fadd_rn(__fmul_rn(__fdiv_rn(v[i].x, den), g4[i].x), b4[i].x);
@@ -834,10 +830,10 @@ size_t dec5_smem_bytes(int d, int NT8, int L) {
     return std::max((size_t)2 * NT8 * (d / 32) * 32 * 16, (size_t)NW * RING_W) + sizeof(float) * ((size_t)NW * NT8 * 8 * RED_LD + 128 + 2 * NW + NW * 64) + (size_t)(L * 16 + 16) * sizeof(Dec5Desc) + NW * 8 * 8 + 64;
 }
 
-template <int NT8, int DV, typename KVT>
+template <int NT8, typename KVT>
 bool launch5_t(const Dec3Args& a, int n_ctas, cudaStream_t st) {
     const size_t smem = dec5_smem_bytes(a.d, NT8, a.L);
-    auto k = dec5_kernel<NT8, DV, KVT>;
+    auto k = dec5_kernel<NT8, KVT>;
     static size_t configured = 0;   // per instantiation
     if (configured != smem) {
         if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -865,15 +861,12 @@ bool launch_dec5(const Dec3Args& a, int n_ctas, bool w_half, cudaStream_t st) {
     if (a.lgbuf == nullptr || a.ypart == nullptr || a.att_pl == nullptr || a.hid_pl == nullptr || a.d5 == nullptr || a.lg_slices < 1 || a.k > DEC5_KC) return false;
     if (a.n_splits > 16 || (size_t)a.R * a.H * a.n_splits > (size_t)NW * ((a.R + 7) / 8) * 8 * RED_LD) return false;   // cross-merge weights live in the reduction buffer
     const int nt8 = (a.R + 7) / 8;
-    // DV = float4 per lane of an x row held in registers by the LayerNorm staging (d / 128, rounded up to an instantiated size)
-#define WB_D5K(NT8_, DV_) (a.kv_half ? launch5_t<NT8_, DV_, __half>(a, n_ctas, st) : launch5_t<NT8_, DV_, float>(a, n_ctas, st))
-#define WB_D5(NT8_) (a.d <= 256 ? WB_D5K(NT8_, 2) : a.d <= 768 ? WB_D5K(NT8_, 6) : WB_D5K(NT8_, 10))
+#define WB_D5(NT8_) (a.kv_half ? launch5_t<NT8_, __half>(a, n_ctas, st) : launch5_t<NT8_, float>(a, n_ctas, st))
     if (nt8 == 1) return WB_D5(1);
     if (nt8 == 2) return WB_D5(2);
     if (nt8 == 3) return WB_D5(3);
     return WB_D5(4);
 #undef WB_D5
-#undef WB_D5K
 }
 
 }  // namespace wb
