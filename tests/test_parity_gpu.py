@@ -323,6 +323,20 @@ def test_batched_tensor_core_decoder_unsplit_cross_attention():
         assert got[i] == want
 
 
+def test_batched_tensor_core_decoder_small_en_width():
+    """d = 768: decoder5.cu splits MLP2 (K = 4d) into 3 slabs of 1024 columns (one round of tiles on 148 CTAs)."""
+    dims, w_np, w_t = synth.make_weights("test-e", seed=0)
+    sp = synth.special_tokens(dims)
+    wh = model.Whisper(dims, w_np)
+    waves = [synth.waveform(20000 + 2500 * i, seed=120 + i) for i in range(9)]
+    sess = transcribe.Session(wh, max_windows=9, max_beams=1, max_text_len=4 + 6 + 1)
+    got = sess.transcribe_windows(waves, sp, is_special_of(sp), beam_size=1, max_depth=6)
+    assert sess.last_decoder() == 5
+    for i in (0, 4, 8):
+        want = o_tr.mels_to_tokens(w_t, dims, sp, o_audio.prep_audio(torch.from_numpy(waves[i])[None]), beam_size=1, max_depth=6)
+        assert got[i] == want
+
+
 def test_batched_tensor_core_decoder_beams_and_logits(wide):
     dims, _, w_t, sp, wh = wide
     waves = [synth.waveform(42000 + 9000 * i, seed=60 + i) for i in range(3)]

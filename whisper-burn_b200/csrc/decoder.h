@@ -198,7 +198,10 @@ struct Dec5Desc {
     const float *g = nullptr, *b = nullptr;   // LayerNorm parameters (D5_KIND_LN)
     float eps = 0.0f;
     int src = 0;                   // input planes of a linear stage: 1 = attention output, 2 = MLP hidden, 3 = LayerNorm output
+    int ks = 0;                    // K slab width of a linear stage (= columns staged per item); d except MLP2 when 4d splits into 3
+    int pad_[3] = {0, 0, 0};       // sizeof % 16 == 0: the table is copied to shared memory in 16-byte words
 };
+static_assert(sizeof(Dec5Desc) % 16 == 0, "Dec5Desc must be a whole number of 16-byte words");
 struct Dec3Args {
     int R = 0, Rmax = 0, d = 0, H = 0, L = 0, V = 0, t_max = 0;
     int64_t Mcap = 0;

@@ -44,6 +44,9 @@ enum { ST_LN_EMB = D5_ST_LN_EMB, ST_LN_FOLD = D5_ST_LN_FOLD, ST_LN_FOLD_NOPUB = 
        ST_PLANES = D5_ST_PLANES, ST_CROSS = D5_ST_CROSS };
 enum { EM_QKV = D5_EM_QKV, EM_RESID = D5_EM_RESID, EM_CQ = D5_EM_CQ, EM_HID = D5_EM_HID, EM_PART = D5_EM_PART, EM_LOGITS = D5_EM_LOGITS };
 
+// widest K slab staged in shared memory: d, or 4d/3 when MLP2 splits into 3 slabs (session.cu)
+#define PLANE_COLS_MAX(d_) ((((4 * (d_)) % 3 == 0) && ((4 * (d_) / 3) % 256 == 0) && (4 * (d_) / 3 <= 1280)) ? 4 * (d_) / 3 : (d_))
+
 using GemmDesc = Dec5Desc;   // host-built stage descriptors (decoder.h): no switch in the kernel, so the compiler cannot clone the stage body per case
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -65,12 +68,12 @@ struct AFrag {
     uint4 r0[MAXCH], r8[MAXCH];
     float bias;
 };
-// item = slab * n_tiles + tile; this warp's slice of the slab (= d columns) is [warp * d / 8, +d / 8)
+// item = slab * n_tiles + tile; this warp's slice of the slab (= D.ks columns) is [warp * ks / 8, +ks / 8)
 __device__ __forceinline__ void load_afrag(const GemmDesc& D, int d, int item, AFrag& f) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int n_tiles = D.N >> 4, tile = item % n_tiles, slab = item / n_tiles;
-    const int K = D.n_slabs * d, nch = d >> 8;
-    const int k0 = slab * d + warp * (d >> 3) + t * 8;
+    const int ks = D.ks, K = D.n_slabs * ks, nch = ks >> 8;
+    const int k0 = slab * ks + warp * (ks >> 3) + t * 8;
     const __half* Wh = reinterpret_cast<const __half*>(D.W);
     const uint4* p0 = reinterpret_cast<const uint4*>(Wh + (int64_t)(tile * 16 + g) * K + k0);
     const uint4* p1 = reinterpret_cast<const uint4*>(Wh + (int64_t)(tile * 16 + g + 8) * K + k0);
@@ -100,8 +103,8 @@ dec5_kernel(const Dec3Args a) {
     constexpr int NE = (16 * RP + NT - 1) / NT;
     const int nchunks = d >> 5, nch = d >> 8, nv = d >> 2;
     uint4* xhi = reinterpret_cast<uint4*>(sm);            // [NT8][d/32][32] fragment-order fp16 hi plane
-    uint4* xlo = xhi + NT8 * nchunks * 32;                // same, residual * 2^11
-    float* red = reinterpret_cast<float*>(reinterpret_cast<char*>(sm) + max(2 * NT8 * nchunks * 32 * 16, NW * RING_W));   // [NW][RP][RED_LD]; also cross-merge weights
+    uint4* xlo = xhi + NT8 * (PLANE_COLS_MAX(d) >> 5) * 32;   // same, residual * 2^11 (planes sized for the widest K slab)
+    float* red = reinterpret_cast<float*>(reinterpret_cast<char*>(sm) + max(2 * NT8 * (PLANE_COLS_MAX(d) >> 5) * 32 * 16, NW * RING_W));   // [NW][RP][RED_LD]; also cross-merge weights
     float* qs = red + NW * RP * RED_LD;                   // [2][64] query of the attention unit of each 4-warp group
     float* wm = qs + 128;                                 // [NW]
     float* wl = wm + NW;                                  // [NW]
@@ -128,8 +131,10 @@ dec5_kernel(const Dec3Args a) {
     uint4* att_lo = att_hi + pl_plane;
     uint4* xn_hi = att_lo + pl_plane;                     // LayerNorm output planes: hi, lo
     uint4* xn_lo = xn_hi + pl_plane;
-    uint4* hid_hi = reinterpret_cast<uint4*>(a.hid_pl);   // [4 slabs] hi planes, then [4 slabs] lo planes
+    uint4* hid_hi = reinterpret_cast<uint4*>(a.hid_pl);   // [slabs] hi planes, then [slabs] lo planes (slab width hks columns: 4d in 4 or 3 slabs)
     uint4* hid_lo = hid_hi + 4 * pl_plane;
+    const int n_part = ds[SL_MLP2].n_slabs;               // MLP2 partial sums to fold (3 or 4)
+    const int hks = ds[SL_MLP2].ks;                       // K slab width of MLP2 = column width of the hidden-layer planes
     float* x = a.x;
 
     AFrag pf;
@@ -173,7 +178,7 @@ dec5_kernel(const Dec3Args a) {
                                     const float4 p0 = __ldcg(reinterpret_cast<const float4*>(yp + (int64_t)r * d) + c);
                                     const float4 p1 = __ldcg(reinterpret_cast<const float4*>(yp + yps + (int64_t)r * d) + c);
                                     const float4 p2 = __ldcg(reinterpret_cast<const float4*>(yp + 2 * yps + (int64_t)r * d) + c);
-                                    const float4 p3 = __ldcg(reinterpret_cast<const float4*>(yp + 3 * yps + (int64_t)r * d) + c);
+                                    const float4 p3 = n_part > 3 ? __ldcg(reinterpret_cast<const float4*>(yp + 3 * yps + (int64_t)r * d) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
                                     v[i].x = __fadd_rn(v[i].x, __fadd_rn(__fadd_rn(p0.x, p1.x), __fadd_rn(p2.x, p3.x)));
                                     v[i].y = __fadd_rn(v[i].y, __fadd_rn(__fadd_rn(p0.y, p1.y), __fadd_rn(p2.y, p3.y)));
                                     v[i].z = __fadd_rn(v[i].z, __fadd_rn(__fadd_rn(p0.z, p1.z), __fadd_rn(p2.z, p3.z)));
@@ -310,6 +315,7 @@ dec5_kernel(const Dec3Args a) {
                     // ================= one linear layer for all rows: out[r][n] = sum_k in[r][k] W[n][k] (+ bias)
                     const bool merge = D.stage == ST_CROSS && S > 1;
                     const bool lg = D.emit == EM_LOGITS;
+                    const int ks = D.ks, nch_s = ks >> 8, nchunks_s = ks >> 5;   // this stage's K slab: chunks per warp / per row
                     const int n_tiles = D.N >> 4;
                     const int n_items = lg ? (int)gridDim.x : n_tiles * D.n_slabs;
                     int staged = -1;
@@ -327,9 +333,9 @@ dec5_kernel(const Dec3Args a) {
                             __syncthreads();
                             if (!merge) {
                                 // ---- the producer wrote the planes in fragment order: plain asynchronous copy (rows < RP are a prefix)
-                                const uint4* sh = (D.src == 2 ? hid_hi : D.src == 3 ? xn_hi : att_hi) + (int64_t)slab * pl_plane;
+                                const uint4* sh = (D.src == 2 ? hid_hi : D.src == 3 ? xn_hi : att_hi) + (int64_t)slab * (PL_ROWS * ks / 8);
                                 const uint4* sl = sh + (D.src == 2 ? 4 * pl_plane : pl_plane);
-                                const int n16 = NT8 * nchunks * 32;
+                                const int n16 = NT8 * nchunks_s * 32;
                                 for (int i = tid; i < n16; i += NT) {
                                     cp_async16(xhi + i, sh + i);
                                     cp_async16(xlo + i, sl + i);
@@ -393,12 +399,12 @@ dec5_kernel(const Dec3Args a) {
                                 for (int c = 0; c < 4; ++c) { ah[j][c] = 0.0f; al[j][c] = 0.0f; }
 #pragma unroll
                             for (int c = 0; c < MAXCH; ++c) {
-                                if (c < nch) {
-                                    const int chunk = warp * nch + c;
+                                if (c < nch_s) {
+                                    const int chunk = warp * nch_s + c;
 #pragma unroll
                                     for (int j = 0; j < NT8; ++j) {
-                                        const uint4 bh = xhi[(j * nchunks + chunk) * 32 + lane];
-                                        const uint4 bl = xlo[(j * nchunks + chunk) * 32 + lane];
+                                        const uint4 bh = xhi[(j * nchunks_s + chunk) * 32 + lane];
+                                        const uint4 bl = xlo[(j * nchunks_s + chunk) * 32 + lane];
                                         mma16816(ah[j], cur.r0[c].x, cur.r8[c].x, cur.r0[c].y, cur.r8[c].y, bh.x, bh.y);
                                         mma16816(ah[j], cur.r0[c].z, cur.r8[c].z, cur.r0[c].w, cur.r8[c].w, bh.z, bh.w);
                                         mma16816(al[j], cur.r0[c].x, cur.r8[c].x, cur.r0[c].y, cur.r8[c].y, bl.x, bl.y);
@@ -443,7 +449,7 @@ dec5_kernel(const Dec3Args a) {
                                                 a.q[(int64_t)r * d + n] = __fmul_rn(v, scale);
                                                 break;
                                             case EM_HID:      // gelu(LN(x) W1 + b1) (mod.rs:377-378), written as fragment-order planes
-                                                store_plane_elem(hid_hi + (n / d) * pl_plane, hid_lo + (n / d) * pl_plane, nchunks, r, n % d, gelu_erf(v));
+                                                store_plane_elem(hid_hi + (n / hks) * (PL_ROWS * hks / 8), hid_lo + (n / hks) * (PL_ROWS * hks / 8), hks >> 5, r, n % hks, gelu_erf(v));
                                                 break;
                                             default:          // EM_PART: MLP2 partial sum of this K slab
                                                 a.ypart[slab * yps + (int64_t)r * d + n] = v;
@@ -827,7 +833,7 @@ dec5_kernel(const Dec3Args a) {
 }
 
 size_t dec5_smem_bytes(int d, int NT8, int L) {
-    return std::max((size_t)2 * NT8 * (d / 32) * 32 * 16, (size_t)NW * RING_W) + sizeof(float) * ((size_t)NW * NT8 * 8 * RED_LD + 128 + 2 * NW + NW * 64) + (size_t)(L * 16 + 16) * sizeof(Dec5Desc) + NW * 8 * 8 + 64;
+    return std::max((size_t)2 * NT8 * (PLANE_COLS_MAX(d) / 32) * 32 * 16, (size_t)NW * RING_W) + sizeof(float) * ((size_t)NW * NT8 * 8 * RED_LD + 128 + 2 * NW + NW * 64) + (size_t)(L * 16 + 16) * sizeof(Dec5Desc) + NW * 8 * 8 + 64;
 }
 
 template <int NT8, typename KVT>

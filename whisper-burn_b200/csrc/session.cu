@@ -102,7 +102,7 @@ Session::Session(Model* model, int64_t max_w, int64_t max_b, int64_t max_text_le
             if (h16) {   // decoder5.cu stage descriptors
                 std::vector<Dec5Desc> ds((size_t)L * 16 + 16);
                 auto gemm = [&](Dec5Desc& q, const void* Wp, const float* bias, int N, int n_slabs, int stage, int emit, int src) {
-                    q.kind = D5_KIND_GEMM; q.W = Wp; q.bias = bias; q.N = N; q.n_slabs = n_slabs; q.stage = stage; q.emit = emit; q.src = src;
+                    q.kind = D5_KIND_GEMM; q.W = Wp; q.bias = bias; q.N = N; q.n_slabs = n_slabs; q.stage = stage; q.emit = emit; q.src = src; q.ks = d;
                 };
                 auto ln = [&](Dec5Desc& q, const LayerNormW& w, int stage) {
                     q.kind = D5_KIND_LN; q.g = w.g; q.b = w.b; q.eps = w.eps; q.stage = stage;
@@ -121,6 +121,9 @@ Session::Session(Model* model, int64_t max_w, int64_t max_b, int64_t max_text_le
                     ln(q[8], B.mlp_ln, D5_ST_LN_X);
                     gemm(q[9], B.mlp1.w16, B.mlp1.b, 4 * d, 1, D5_ST_PLANES, D5_EM_HID, 3);
                     gemm(q[10], B.mlp2.w16, B.mlp2.b, d, 4, D5_ST_PLANES, D5_EM_PART, 2);
+                    // MLP2 K = 4d: 3 slabs of 4d/3 when that keeps the 8-warp K split (multiple of 256, <= 1280): d/16 tiles x 3 slabs
+                    // = 144 items for small.en -> ONE round on 148 CTAs instead of 192 items in two
+                    if ((4 * d) % 3 == 0 && (4 * d / 3) % 256 == 0 && 4 * d / 3 <= 1280) { q[10].n_slabs = 3; q[10].ks = 4 * d / 3; }
                 }
                 ln(ds[(size_t)L * 16 + 11], m->dec_ln, D5_ST_LN_FOLD_NOPUB);
                 gemm(ds[(size_t)L * 16 + 12], m->tok_emb16, nullptr, V, 1, D5_ST_PLANES, D5_EM_LOGITS, 3);
