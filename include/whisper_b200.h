@@ -179,6 +179,11 @@ int wb_find_chunk_overlap(const int64_t* prev, int64_t n_prev, const int64_t* cu
  * the reference's output order (ascending score); returns how many were kept. */
 int64_t wb_beam_get_top_elements(const double* scores, int64_t n, int64_t num, int64_t* idx_out);
 
+/* beam::beam_search (beam.rs:9-37) with a table-driven `next` (see csrc/api.cu): the complete host search, for tests.  Returns the
+ * length of the best sequence written to seq_out, or -1 on bad arguments. */
+int64_t wb_beam_search_table(const double* table, int64_t n_ctx, int64_t n_vocab, int64_t first_token, int64_t eot,
+                             int64_t beam_size, int64_t max_depth, int64_t* seq_out, int64_t capacity);
+
 /* ---- transcribe binary helpers (host) ---------------------------------------------------------- */
 /* load_audio_waveform (src/bin/transcribe/main.rs:31-55): PCM int samples / (2^(bits-1) - 1), float samples as they
  * are, interleaved.  strict_16k_mono != 0 enforces the reference's asserts (16 kHz, one channel) as WB_ERR_INVALID_ARG.

@@ -44,6 +44,7 @@ pub mod ffi {
         pub fn wb_waveform_to_tokens(s: *mut c_void, waveform: *const f32, n_samples: i64, sample_rate: i64, beam_size: c_int, max_depth: c_int,
                                      ids: *const wb_special_ids, is_special: *const u8, tokens_out: *mut i64, capacity: i64, n_tokens_out: *mut i64) -> c_int;
         pub fn wb_beam_get_top_elements(scores: *const f64, n: i64, num: i64, idx_out: *mut i64) -> i64;
+        pub fn wb_beam_search_table(table: *const f64, n_ctx: i64, n_vocab: i64, first_token: i64, eot: i64, beam_size: i64, max_depth: i64, seq_out: *mut i64, capacity: i64) -> i64;
     }
 }
 

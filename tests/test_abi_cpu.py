@@ -93,3 +93,24 @@ def test_npy_tree_probe_reads_reference_format(tmp_path):
     with pytest.raises(ffi.WbError) as e:
         npytree.probe(tmp_path)
     assert e.value.code == ffi.WB_ERR_STATE and "n_mels" in e.value.msg
+
+
+@pytest.mark.parametrize("beam_size,quant", [(1, 0), (5, 0), (5, 3), (3, 2)])
+def test_host_beam_search_matches_oracle(beam_size, quant):
+    """The complete C++ host search (host/beam.hpp: step, finished-beam carry, earlier-wins / last-max tie-breaks, beam.rs:9-110)
+    against the oracle's restatement, driven by the same table-defined `next`; quant > 0 rounds the log-probs to create exact ties."""
+    from oracle import beam as o_beam
+    from whisper_burn_b200 import beam as w_beam
+    rng = np.random.default_rng(100 + beam_size * 7 + quant)
+    n_ctx, V, eot = 37, 23, 22
+    for trial in range(6):
+        table = np.log(rng.dirichlet(np.ones(V) * 0.7, size=n_ctx))
+        if quant:
+            table = np.round(table, quant)
+        table[:, eot] += 0.5 * trial                     # later trials finish early
+
+        def next_fn(beams):
+            return [[(v, b.log_prob + float(table[(b.seq[-1] * 131 + len(b.seq)) % n_ctx, v])) for v in range(V)] for b in beams]
+
+        want = o_beam.beam_search([o_beam.BeamNode(seq=[3], log_prob=0.0)], next_fn, lambda s: s[-1] == eot, beam_size, 12)
+        assert w_beam.beam_search_table(table, 3, eot, beam_size, 12) == want

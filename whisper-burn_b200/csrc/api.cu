@@ -512,6 +512,34 @@ int wb_load_wav(const char* path, int strict_16k_mono, float* out, int64_t capac
 
 int wb_session_last_decoder(const wb_session* s) { return s ? s->impl->last_decoder : -1; }
 
+// beam::beam_search (src/beam.rs:9-37) over a TABLE-driven `next`: the continuation log-prob of token v after a beam whose last
+// token is t and whose length is n is table[((t * 131 + n) % n_ctx) * n_vocab + v] (added to the beam's cumulative f64 log-prob);
+// a beam is finished when its last token is eot.  Host only: lets the CPU tests drive the complete C++ search (host/beam.hpp:
+// step, carry of finished beams, both tie-break rules) against the oracle without a GPU.
+int64_t wb_beam_search_table(const double* table, int64_t n_ctx, int64_t n_vocab, int64_t first_token, int64_t eot, int64_t beam_size,
+                             int64_t max_depth, int64_t* seq_out, int64_t capacity) {
+    if (!table || !seq_out || n_ctx < 1 || n_vocab < 1 || beam_size < 1 || max_depth < 0) return -1;
+    using Node = wb::beam::BeamNode<int64_t>;
+    auto next = [&](const std::vector<Node>& beams) {
+        std::vector<std::vector<std::pair<int64_t, double>>> out(beams.size());
+        for (size_t b = 0; b < beams.size(); ++b) {
+            const int64_t t = beams[b].seq.back(), n = (int64_t)beams[b].seq.size();
+            const double* row = table + ((t * 131 + n) % n_ctx) * n_vocab;
+            out[b].reserve((size_t)n_vocab);
+            for (int64_t v = 0; v < n_vocab; ++v) out[b].emplace_back(v, beams[b].log_prob + row[v]);
+        }
+        return out;
+    };
+    auto fin = [&](const std::vector<int64_t>& seq) { return !seq.empty() && seq.back() == eot; };
+    std::vector<Node> init(1);
+    init[0].seq = {first_token};
+    init[0].log_prob = 0.0;
+    const std::vector<int64_t> best = wb::beam::beam_search(init, next, fin, (size_t)beam_size, (size_t)max_depth);
+    if ((int64_t)best.size() > capacity) return -1;
+    for (size_t i = 0; i < best.size(); ++i) seq_out[i] = best[i];
+    return (int64_t)best.size();
+}
+
 int64_t wb_kernel_launch_count(void) { return wb::g_launch_count; }
 void wb_kernel_launch_count_reset(void) { wb::g_launch_count = 0; }
 

@@ -75,6 +75,7 @@ SYMBOLS = {
     "wb_waveforms_to_tokens": (C.c_int, [_P, C.POINTER(C.c_void_p), _I64, C.c_int64, C.c_int64, C.c_int, C.c_int,
                                          C.POINTER(SpecialIds), _U8, _I64, C.c_int64, _I64]),
     "wb_session_last_decoder": (C.c_int, [_P]),
+    "wb_beam_search_table": (C.c_int64, [C.POINTER(C.c_double), C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _I64, C.c_int64]),
     "wb_load_wav": (C.c_int, [C.c_char_p, C.c_int, _F, C.c_int64, _I64, _I64, C.POINTER(C.c_int)]),
     "wb_window_count": (C.c_int64, [C.c_int64, C.c_int64, C.c_int64]),
     "wb_window_bounds": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, _I64, _I64]),
