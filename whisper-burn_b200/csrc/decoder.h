@@ -216,7 +216,7 @@ struct Dec3Args {
     float lnf_eps = 1e-5f;
     // state
     float *x = nullptr, *q = nullptr, *att = nullptr, *hid = nullptr;
-    float *x2 = nullptr, *ypart = nullptr;   // decoder5.cu: second residual buffer (ping-pong), MLP2 partial sums [4][R][d]
+    float* ypart = nullptr;                 // decoder5.cu: MLP2 partial sums [n_slabs][R][d], folded by the next LayerNorm stage
     const Dec5Desc* d5 = nullptr;           // decoder5.cu: device array [L * 8 + 1]
     void *att_pl = nullptr, *hid_pl = nullptr;   // decoder5.cu: fragment-order fp16 hi/lo planes of the attention output / MLP hidden layer
     float* lgbuf = nullptr;                 // decoder5.cu: [R][V] logits scratch (== logits_out when that is requested)

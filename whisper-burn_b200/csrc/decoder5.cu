@@ -8,18 +8,22 @@
 //     mma.sync.m16n8k16 with M = 16 output features, N = 8 batch rows per n-tile (up to 4 n-tiles), K = 16;
 //   * the fp32 activations are split into fp16 hi + fp16 (lo * 2^11) planes (22 mantissa bits; products with
 //     the fp16 weights are exact, accumulation is fp32) held in FRAGMENT ORDER, so a B fragment is one
-//     conflict-free 16-byte shared load.  Attention outputs and the MLP hidden layer are WRITTEN in that layout
-//     by their producers (global planes), so staging them is a plain cp.async copy; LayerNorm inputs are
-//     normalised from fp32 x by every CTA (warp per row, rows software-pipelined);
+//     conflict-free 16-byte shared load.  Attention outputs, LayerNorm outputs and the MLP hidden layer are WRITTEN in
+//     that layout by their producers (global planes), so staging them is a plain cp.async copy; a LayerNorm is its own
+//     stage: row r is normalised ONCE, by all 256 threads of CTA r (every CTA recomputing all rows cost 12-18 us per
+//     stage in L2 -> SM bandwidth, a single warp per row ~3 us of dependent arithmetic, the block-wide version 1.5 us);
 //   * the A fragments come straight from global memory as 16-byte loads (a K permutation inside each
 //     32-column chunk makes 8 consecutive halves of a weight row the a0..a3 registers of two MMAs) and are
 //     prefetched BEFORE the grid barrier that precedes the stage: weights do not depend on activations;
 //   * the 8 warps of a CTA split K; partial tiles are reduced through shared memory in a fixed order;
-//   * MLP2 (K = 4d) is split over CTAs into 4 slabs of d: the partial sums are folded into x by the next
-//     consumer of x (fixed order; the residual stream ping-pongs between two buffers so a folded row can
-//     never be folded twice);
+//   * MLP2 (K = 4d) is split over CTAs into K slabs (3 x 4d/3 when that keeps the 8-warp split, else 4 x d): the
+//     partial sums are folded into x, in a fixed order, by the LayerNorm stage that consumes x next (only CTA r
+//     touches row r there, so the fold is in place);
+//   * cross attention streams the unit's contiguous head-major K/V block (encoder.cu ckv_relayout_kernel) with bulk
+//     copies into a per-warp mbarrier ring that aliases the (then dead) activation planes;
 //   * logits: E[V][d] is streamed once through the same MMA path into an L2-resident [R][V] buffer; a second
-//     stage turns it into per-slice (max, sum-exp, top candidates) records, the finish stage is decoder3's.
+//     stage turns it into per-slice (max, sum-exp, top candidates) records (compact code for greedy: this part
+//     runs once per step from a cold instruction cache), then one warp per row finishes.
 // Code size matters: the layer loop must stay inside the instruction cache, so every building block (staging,
 // MMA tile, emit, attention) exists ONCE and the stages are driven by small descriptors (the first version
 // inlined six copies and ran 3x slower than its memory traffic explains).

@@ -55,7 +55,7 @@ Session::Session(Model* model, int64_t max_w, int64_t max_b, int64_t max_text_le
     }
     if (kv == WB_KV_F16) { kc16.alloc((size_t)L * Rmax * t_max * d); vc16.alloc((size_t)L * Rmax * t_max * d); }
     else { kc.alloc((size_t)L * Rmax * t_max * d); vc.alloc((size_t)L * Rmax * t_max * d); }
-    dx.alloc((size_t)Rmax * d); dx2.alloc((size_t)Rmax * d);
+    dx.alloc((size_t)Rmax * d);
     att_pl.alloc(4 * dec5_plane_uint4(d)); hid_pl.alloc(8 * dec5_plane_uint4(d));   // attention + LayerNorm output planes (hi, lo each), MLP hidden planes
     WB_CUDA(cudaMemsetAsync(att_pl.p, 0, 4 * dec5_plane_uint4(d) * sizeof(uint4), st));
     WB_CUDA(cudaMemsetAsync(hid_pl.p, 0, 8 * dec5_plane_uint4(d) * sizeof(uint4), st));
@@ -491,7 +491,7 @@ void Session::launch_v3(int R_, int pos0, int n_steps, int logits_from, bool use
     a.E_tiled = m->tok_emb16_tiled;
     a.lnf_g = m->dec_ln.g; a.lnf_b = m->dec_ln.b; a.lnf_eps = m->dec_ln.eps;
     a.x = dx.p; a.q = dq.p; a.att = datt.p; a.hid = dhid.p;
-    a.x2 = dx2.p; a.ypart = ypart.p; a.lgbuf = logits.p; a.att_pl = att_pl.p; a.hid_pl = hid_pl.p; a.d5 = d5_desc.p; a.ckv_hm = ckv_hm ? 1 : 0;
+    a.ypart = ypart.p; a.lgbuf = logits.p; a.att_pl = att_pl.p; a.hid_pl = hid_pl.p; a.d5 = d5_desc.p; a.ckv_hm = ckv_hm ? 1 : 0;
     a.lg_slices = std::max(1, std::min(16, n_sm / std::max(1, R_)));
     a.kv_half = kv_dtype == WB_KV_F16 ? 1 : 0;
     if (a.kv_half) { a.kc = kc16.p; a.vc = vc16.p; a.ckv = ckv16.p; } else { a.kc = kc.p; a.vc = vc.p; a.ckv = ckv.p; }

@@ -48,7 +48,7 @@ struct Session {
     // ---- device: decode state
     DevBuf<float> kc, vc;  // [L][Rmax][t_max][d] self keys (scaled) / values
     DevBuf<__half> kc16, vc16, ckv16;   // fp16 caches (WB_KV_F16)
-    DevBuf<float> dx, dx2, dq, dhid, logits;
+    DevBuf<float> dx, dq, dhid, logits;
     DevBuf<Dec5Desc> d5_desc;
     DevBuf<uint4> att_pl, hid_pl;   // decoder5.cu activation planes
     DevBuf<float> part_o, part_m, part_l;
