@@ -114,3 +114,40 @@ def test_host_beam_search_matches_oracle(beam_size, quant):
 
         want = o_beam.beam_search([o_beam.BeamNode(seq=[3], log_prob=0.0)], next_fn, lambda s: s[-1] == eot, beam_size, 12)
         assert w_beam.beam_search_table(table, 3, eot, beam_size, 12) == want
+
+
+def test_npy_tree_rejects_malformed_files(tmp_path):
+    """load.rs:19-27 trusts the leading dims; the C++ reader checks them (size mismatch, dtype, magic) and says which file."""
+    from whisper_burn_b200 import npytree, synth
+    dims, w_np = synth.make_weights("test-a", seed=1)
+    npytree.save_npy_tree(tmp_path, dims, w_np)
+    p = tmp_path / "decoder/token_embedding/weight.npy"
+    good = np.load(p)
+    np.save(p, good[:-3])                                   # payload shorter than its leading dims
+    with pytest.raises(ffi.WbError) as e:
+        npytree.probe(tmp_path)
+    assert e.value.code == ffi.WB_ERR_INVALID_ARG and "token_embedding" in e.value.msg
+    np.save(p, good.astype(np.float64))                     # npy::NpyData<f32> (load.rs:19): f32 only
+    with pytest.raises(ffi.WbError) as e:
+        npytree.probe(tmp_path)
+    assert "float32" in e.value.msg
+    p.write_bytes(b"not an npy file")
+    with pytest.raises(ffi.WbError) as e:
+        npytree.probe(tmp_path)
+    assert e.value.code == ffi.WB_ERR_INVALID_ARG
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU port of the reference path): ONE JSON line with the contract's keys, no GPU needed."""
+    import json, subprocess, sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--max-depth", "3",
+                        "--cpu-baseline-windows", "1"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["metric"] == "audio-seconds/sec" and j["unit"] == "audio-s/s" and j["higher_is_better"] is True
+    assert j["value"] > 0 and j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1
+    assert j["e2e"] == {"value": j["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
