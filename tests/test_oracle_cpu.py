@@ -137,3 +137,18 @@ def test_special_mask_only_first_two_steps():
     lp = tr["log_probs"]
     assert np.isneginf(lp[0][0][sp.first_special:]).all() and np.isneginf(lp[1][0][sp.first_special:]).all()
     assert np.isfinite(lp[2][0][sp.first_special:]).all()             # transcribe.rs:271: max_seq_len > 5
+
+
+def test_wide_model_tokens_golden():
+    """The oracle reproduces the committed ids of the batched-decoder test models (tests/golden/make_golden_wide.py): greedy with the
+    fp32 and the fp16 K/V cache, and beam 5."""
+    import json
+    gold = json.loads((G / "tokens_wide.json").read_text())
+    dims, _, w = synth.make_weights("test-c", seed=0)
+    sp = synth.special_tokens(dims)
+    for i in (0, 9):
+        mel = audio.prep_audio(torch.from_numpy(synth.waveform(30000 + 7000 * i, seed=40 + i))[None])
+        assert transcribe.mels_to_tokens(w, dims, sp, mel, beam_size=1, max_depth=14) == gold["test-c_greedy_depth14_f32"][i]
+        assert transcribe.mels_to_tokens(w, dims, sp, mel, beam_size=1, max_depth=14, opts=model.OracleOptions(kv_dtype="f16")) == gold["test-c_greedy_depth14_f16"][i]
+    mel = audio.prep_audio(torch.from_numpy(synth.waveform(42000 + 9000 * 2, seed=62))[None])
+    assert transcribe.mels_to_tokens(w, dims, sp, mel, beam_size=5, max_depth=8) == gold["test-c_beam5_depth8_f32"][2]

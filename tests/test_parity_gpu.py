@@ -299,6 +299,7 @@ def test_batched_tensor_core_decoder_greedy_vs_oracle(wide, kv):
                               kv_dtype=ffi.WB_KV_F16 if kv == "f16" else ffi.WB_KV_F32)
     got = sess.transcribe_windows(waves, sp, is_special_of(sp), beam_size=1, max_depth=14)
     assert sess.last_decoder() == 5
+    assert got == json.loads((G / "tokens_wide.json").read_text())[f"test-c_greedy_depth14_{kv}"]      # committed oracle ids
     opts = o_model.OracleOptions(kv_dtype=kv)
     for g, wv in zip(got, waves):
         want = o_tr.mels_to_tokens(w_t, dims, sp, o_audio.prep_audio(torch.from_numpy(wv)[None]), beam_size=1, max_depth=14, opts=opts)
@@ -318,6 +319,8 @@ def test_batched_tensor_core_decoder_unsplit_cross_attention():
     sess = transcribe.Session(wh, max_windows=20, max_beams=1, max_text_len=4 + 6 + 1)
     got = sess.transcribe_windows(waves, sp, is_special_of(sp), beam_size=1, max_depth=6)
     assert sess.last_decoder() == 5
+    gold = json.loads((G / "tokens_wide.json").read_text())["test-d_greedy_depth6_f32"]
+    assert all(got[int(i)] == t for i, t in gold.items())
     for i in (0, 7, 13, 19):
         want = o_tr.mels_to_tokens(w_t, dims, sp, o_audio.prep_audio(torch.from_numpy(waves[i])[None]), beam_size=1, max_depth=6)
         assert got[i] == want
@@ -332,6 +335,8 @@ def test_batched_tensor_core_decoder_small_en_width():
     sess = transcribe.Session(wh, max_windows=9, max_beams=1, max_text_len=4 + 6 + 1)
     got = sess.transcribe_windows(waves, sp, is_special_of(sp), beam_size=1, max_depth=6)
     assert sess.last_decoder() == 5
+    gold = json.loads((G / "tokens_wide.json").read_text())["test-e_greedy_depth6_f32"]
+    assert all(got[int(i)] == t for i, t in gold.items())
     for i in (0, 4, 8):
         want = o_tr.mels_to_tokens(w_t, dims, sp, o_audio.prep_audio(torch.from_numpy(waves[i])[None]), beam_size=1, max_depth=6)
         assert got[i] == want
@@ -343,6 +348,7 @@ def test_batched_tensor_core_decoder_beams_and_logits(wide):
     sess = transcribe.Session(wh, max_windows=3, max_beams=5, max_text_len=4 + 8 + 1)
     got = sess.transcribe_windows(waves, sp, is_special_of(sp), beam_size=5, max_depth=8)      # 15 rows, ancestry table
     assert sess.last_decoder() == 5
+    assert got == json.loads((G / "tokens_wide.json").read_text())["test-c_beam5_depth8_f32"]
     for g, wv in zip(got, waves):
         assert g == o_tr.mels_to_tokens(w_t, dims, sp, o_audio.prep_audio(torch.from_numpy(wv)[None]), beam_size=5, max_depth=8)
     # stateless forward_decoder (full logits) against the oracle's decoder (mod.rs:131-157)
