@@ -359,6 +359,7 @@ def run_config(args, cfg, ctx):
             "e2e": {"value": e2e_val, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e, "api": "wb_waveforms_to_tokens (windowing + batched decode + overlap merge), pinned host waveforms"},
             "gpu_launches": launches // max(args.steps, 1), "roofline": roof,
+            "wall_ms_each": [round(v, 3) for v in wall_ms], "e2e_ms_each": [round(v, 3) for v in e2e_ms],
             "weights": "fp16-exact synthetic (tensor-core path)" if wh.weights_fp16_exact else "not fp16-exact: fp32 SIMT path",
             "tokens_checksum": int(sum(sum(t) for t in toks) % (1 << 31)),
         }

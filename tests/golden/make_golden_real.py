@@ -3,6 +3,7 @@
 Same status as make_golden.py: oracle outputs (the reference ships no vectors and cannot be built here: "parity unpinned");
 they pin the oracle and give the GPU tests committed ids at the shapes the metric is quoted on:
 
+  tiny.en   seed 0, chunks 0..7 (24 windows), greedy, depth 100, fp32 and fp16 K/V cache (batched cluster decoder)
   small.en  seed 0, chunks 0..7 (24 reference windows), greedy, depth 100, fp32 cache and fp16 K/V cache
             + per-step top-5 ids / log-probs of every window (checked through wb_session_step with a tolerance: the synthetic
             deep models decode to 1-2 distinct tokens, so the continuous log-probs carry the parity evidence)
@@ -43,11 +44,13 @@ def windows_of(chunk_id, dims):
     return chunk, transcribe.window_bounds(len(chunk), 16000, window_len)
 
 
-def decode(w, dims, sp, wave, beam, depth, kv, want_top1=False):
+def decode(w, dims, sp, wave, beam, depth, kv, want_top1=False, want_margins=False):
     mel = audio.prep_audio(torch.from_numpy(np.ascontiguousarray(wave))[None])
     tr = {}
     toks = transcribe.mels_to_tokens(w, dims, sp, mel, beam_size=beam, max_depth=depth, opts=model.OracleOptions(kv_dtype=kv), trace=tr)
     rec = {"tokens": toks, "min_margin": min(margins(tr))}
+    if want_margins:   # top-1 / top-2 log-prob gap at every generated step (greedy): where it is tiny, fp32 rounding decides the id
+        rec["margins"] = [round(g, 7) for g in margins(tr)]
     if want_top1 and beam == 1:   # per generated step: the 5 best ids (ties -> lower id) and their log-probs
         top = []
         for st in tr["log_probs"]:
@@ -70,6 +73,23 @@ def small_en():
             rec["f16"].append(decode(w, dims, sp, chunk[s:e], 1, 100, "f16"))
         out["chunks"].append(rec)
         print("small.en chunk", c, "done", flush=True)
+    out["min_margin_f32"] = min(r["min_margin"] for c in out["chunks"] for r in c["f32"])
+    out["min_margin_f16"] = min(r["min_margin"] for c in out["chunks"] for r in c["f16"])
+    return out
+
+
+def tiny_en():
+    """tiny.en, chunks 0..7 (24 windows): the batched case of the head-fused cluster decoder (decoder6.cu: 24 clusters, 3 n-tiles)."""
+    dims, _, w = synth.make_weights("tiny.en", seed=0)
+    sp = synth.special_tokens(dims)
+    out = {"model": "tiny.en", "seed": 0, "depth": 100, "chunks": []}
+    for c in range(8):
+        chunk, bounds = windows_of(c, dims)
+        rec = {"bounds": bounds, "f32": [], "f16": []}
+        for (s, e) in bounds:
+            rec["f32"].append(decode(w, dims, sp, chunk[s:e], 1, 100, "f32", want_margins=True))
+            rec["f16"].append(decode(w, dims, sp, chunk[s:e], 1, 100, "f16", want_margins=True))
+        out["chunks"].append(rec)
     out["min_margin_f32"] = min(r["min_margin"] for c in out["chunks"] for r in c["f32"])
     out["min_margin_f16"] = min(r["min_margin"] for c in out["chunks"] for r in c["f16"])
     return out
@@ -99,9 +119,9 @@ def large_v2():
 
 def main():
     torch.manual_seed(0)
-    which = sys.argv[1:] or ["small.en", "medium", "large-v2"]
+    which = sys.argv[1:] or ["tiny.en", "small.en", "medium", "large-v2"]
     data = json.loads(OUT.read_text()) if OUT.exists() else {}
-    for name, fn in (("small.en", small_en), ("medium", medium), ("large-v2", large_v2)):
+    for name, fn in (("tiny.en", tiny_en), ("small.en", small_en), ("medium", medium), ("large-v2", large_v2)):
         if name in which:
             t0 = time.time()
             data[name] = fn()

@@ -131,3 +131,62 @@ def test_large_v2_beam5_golden(large_v2, kv):
     got = sess.transcribe_windows([wave], sp, is_special_of(sp), beam_size=5, max_depth=20)[0]
     assert sess.last_decoder() == 5
     assert got == g[kv]["tokens"], f"oracle min margin {g[kv]['min_margin']}"
+
+
+# ---------------------------------------------------------------- tiny.en, the cluster decoder's configurations (decoder6.cu)
+def _tiny_cases(kv, chunks):
+    g = gold()["tiny.en"]
+    waves, recs = [], []
+    for c in chunks:
+        chunk = synth.chunk_waveform(c)
+        for (s, e), r in zip(g["chunks"][c]["bounds"], g["chunks"][c][kv]):
+            waves.append(chunk[s:e])
+            recs.append(r)
+    return waves, recs
+
+
+def _check_ids_where_separated(got, recs, tol=1e-4):
+    """ids identical up to the first step whose ORACLE top-1/top-2 log-prob gap is below tol (there fp32 rounding decides;
+    24 windows x 100 steps of the synthetic tiny.en model contain 4 such steps, smallest gap 3e-6)."""
+    for i, (g, r) in enumerate(zip(got, recs)):
+        want, m = r["tokens"], r["margins"]
+        n = next((4 + s for s, v in enumerate(m) if v < tol), len(want))
+        assert g[:n] == want[:n], f"window {i}: first difference at {next(j for j in range(n) if g[j] != want[j])} (compared {n} ids)"
+        if n == len(want):
+            assert g == want
+
+
+@pytest.fixture(scope="module")
+def tiny_en():
+    dims, w_np, _ = synth.make_weights("tiny.en", seed=0)
+    return dims, synth.special_tokens(dims), model.Whisper(dims, w_np)
+
+
+@pytest.mark.parametrize("kv", ["f32", "f16"])
+@pytest.mark.parametrize("hs", ["1", "2"])
+def test_tiny_en_cluster_decoder_one_chunk(tiny_en, kv, hs, monkeypatch):
+    """BASELINE config 2 through both cluster shapes of decoder6.cu: one CTA per head (6-CTA clusters) and two (12-CTA clusters,
+    keys and MLP slices split, softmax merge on the receiving side)."""
+    dims, sp, wh = tiny_en
+    monkeypatch.setenv("WB200_DEC6_HS", hs)
+    waves, recs = _tiny_cases(kv, [0])
+    sess = transcribe.Session(wh, max_windows=3, max_beams=1, max_text_len=105, kv_dtype=ffi.WB_KV_F16 if kv == "f16" else ffi.WB_KV_F32)
+    got = sess.transcribe_windows(waves, sp, is_special_of(sp), beam_size=1, max_depth=100)
+    assert sess.last_decoder() == 6
+    _check_ids_where_separated(got, recs)
+
+
+@pytest.mark.parametrize("kv", ["f32", "f16"])
+def test_tiny_en_cluster_decoder_8_chunks(tiny_en, kv):
+    """tiny.en, 8 x 30 s chunks = 24 rows in one launch: one cluster per row (rows beyond the co-resident clusters are looped),
+    three n-tiles in the vocabulary projection."""
+    dims, sp, wh = tiny_en
+    waves, recs = _tiny_cases(kv, range(8))
+    sess = transcribe.Session(wh, max_windows=24, max_beams=1, max_text_len=105, kv_dtype=ffi.WB_KV_F16 if kv == "f16" else ffi.WB_KV_F32)
+    got = sess.transcribe_windows(waves, sp, is_special_of(sp), beam_size=1, max_depth=100)
+    assert sess.last_decoder() == 6
+    _check_ids_where_separated(got, recs)
+    # batching invariance: 7 windows (one n-tile, partially filled) give the same ids as inside the batch of 24
+    sess7 = transcribe.Session(wh, max_windows=7, max_beams=1, max_text_len=105, kv_dtype=ffi.WB_KV_F16 if kv == "f16" else ffi.WB_KV_F32)
+    got7 = sess7.transcribe_windows(waves[5:12], sp, is_special_of(sp), beam_size=1, max_depth=100)
+    _check_ids_where_separated(got7, recs[5:12])

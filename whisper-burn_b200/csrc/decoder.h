@@ -246,7 +246,9 @@ struct Dec3Args {
     float *lg_m = nullptr, *lg_s = nullptr, *lg_v = nullptr;
     int* lg_i = nullptr;
     int *pos = nullptr, *n_unfinished = nullptr, *steps_done = nullptr;
-    unsigned int* bar = nullptr;          // [2] arrival count, generation
+    unsigned int* bar = nullptr;          // [4] arrival count, generation / ticket, finish flag (decoder6.cu)
+    const void* d6_pack = nullptr;        // decoder6.cu: packed weight slices [L][CS][PACK] bytes
+    const float* d6_params = nullptr;     // decoder6.cu: parameter blocks [L][CS][PARAMS] floats
     unsigned long long* trace = nullptr;  // optional: stage / barrier timestamps of CTA 0 (ns)
     int trace_cap = 0;
 };
@@ -256,6 +258,17 @@ bool launch_dec4(const Dec3Args& a, bool w_half, cudaStream_t st);
 // batched tensor-core version (decoder5.cu); returns false when the configuration is not covered
 bool launch_dec5(const Dec3Args& a, int n_ctas, bool w_half, cudaStream_t st);
 size_t dec5_plane_uint4(int d);   // uint4 elements of one global activation plane
+// head-fused cluster decoder (decoder6.cu): greedy, d in {128, 384}, <= 24 rows; hs = CTAs per attention head (1 or 2)
+struct Dec6LayerSrc {   // device pointers of one decoder block (fp16 [N][K] weights, fp32 biases / LayerNorm parameters)
+    const __half *Wqkv, *Wo, *Wcq, *Wco, *W1, *W2;
+    const float *bqkv, *bo, *bcq, *bco, *b1, *b2;
+    const float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *ln3_g, *ln3_b;
+    float ln1_eps, ln2_eps, ln3_eps;
+};
+bool dec6_supported(int d, int H);
+int dec6_pick_hs(int d, int R);
+void dec6_build_pack(int d, int hs, const std::vector<Dec6LayerSrc>& layers, DevBuf<uint8_t>& pack, DevBuf<float>& params, cudaStream_t st);
+bool launch_dec6(const Dec3Args& a, int hs, bool w_half, cudaStream_t st);
 
 void launch_dec2_self(const Dec2SelfArgs& a, int H, bool w_half, cudaStream_t st);
 void launch_dec2_cross(const Dec2CrossArgs& a, int H, int S, bool w_half, cudaStream_t st);

@@ -82,8 +82,9 @@ Session::Session(Model* model, int64_t max_w, int64_t max_b, int64_t max_text_le
         n_logit_ctas = 2 * prop.multiProcessorCount;
         // persistent decoder: per-layer pointer table, barrier words, larger split-KV partial buffers
         part_o.alloc((size_t)Rmax * H * 16 * 64); part_m.alloc((size_t)Rmax * H * 16); part_l.alloc((size_t)Rmax * H * 16);
-        datt.alloc((size_t)Rmax * d); steps_done.alloc(1); d3_bar.alloc(2);
-        WB_CUDA(cudaMemsetAsync(d3_bar.p, 0, 2 * sizeof(unsigned int), st));
+        datt.alloc((size_t)Rmax * d); steps_done.alloc(1); d3_bar.alloc(4);
+        WB_CUDA(cudaMemsetAsync(d3_bar.p, 0, 4 * sizeof(unsigned int), st));
+        { const char* e6 = getenv("WB200_DEC6"); use_dec6 = !(e6 && e6[0] == '0'); }
         {
             const bool h16 = m->fp16_exact;
             auto wp = [&](const LinearW& w) -> const void* { return h16 ? (const void*)w.w16 : (const void*)w.w32; };
@@ -512,11 +513,31 @@ void Session::launch_v3(int R_, int pos0, int n_steps, int logits_from, bool use
         a.trace = d3_trace.p;
         a.trace_cap = 1 << 16;
     }
-    WB_CUDA(cudaMemsetAsync(d3_bar.p, 0, 2 * sizeof(unsigned int), st));   // monotonic barrier counter starts at 0
+    WB_CUDA(cudaMemsetAsync(d3_bar.p, 0, 4 * sizeof(unsigned int), st));   // monotonic barrier counters start at 0
     last_decoder = 3;
     if (dec_version == 4) {
-        if (launch_dec4(a, m->fp16_exact, st)) last_decoder = 4;
-        else if (launch_dec5(a, n_sm, m->fp16_exact, st)) last_decoder = 5;
+        // head-fused cluster decoder first (greedy, d = 128 / 384); its packed weight slices are built on first use
+        if (use_dec6 && m->fp16_exact && greedy && k == 1 && !use_cur_tok && a.anc == nullptr && a.logits_out == nullptr && R_ <= 24 && ckv_hm &&
+            t_max <= 128 && dec6_supported(d, H)) {
+            const int hs = dec6_pick_hs(d, R_);
+            if (d6_pack[hs].p == nullptr) {
+                std::vector<Dec6LayerSrc> src((size_t)D.n_text_layer);
+                for (int l = 0; l < D.n_text_layer; ++l) {
+                    const DecBlockW& B = m->dec[(size_t)l];
+                    src[(size_t)l] = Dec6LayerSrc{B.qkv.w16, B.out.w16, B.cq.w16, B.cout.w16, B.mlp1.w16, B.mlp2.w16, B.qkv.b, B.out.b, B.cq.b, B.cout.b,
+                                                  B.mlp1.b, B.mlp2.b, B.attn_ln.g, B.attn_ln.b, B.cross_ln.g, B.cross_ln.b, B.mlp_ln.g, B.mlp_ln.b,
+                                                  B.attn_ln.eps, B.cross_ln.eps, B.mlp_ln.eps};
+                }
+                dec6_build_pack(d, hs, src, d6_pack[hs], d6_params[hs], st);
+            }
+            a.d6_pack = d6_pack[hs].p;
+            a.d6_params = d6_params[hs].p;
+            if (launch_dec6(a, hs, m->fp16_exact, st)) last_decoder = 6;
+        }
+        if (last_decoder == 3) {
+            if (launch_dec4(a, m->fp16_exact, st)) last_decoder = 4;
+            else if (launch_dec5(a, n_sm, m->fp16_exact, st)) last_decoder = 5;
+        }
     }
     if (last_decoder == 3) launch_dec3(a, n_sm, m->fp16_exact, st);
     if (a.trace) {

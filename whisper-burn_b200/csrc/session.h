@@ -74,6 +74,9 @@ struct Session {
                                  // unfused (decoder.cu) / fused-per-layer (decoder2.cu) paths for A/B testing
     int n_sm = 0;
     DevBuf<Dec3Layer> d3_layers;
+    DevBuf<uint8_t> d6_pack[3];     // decoder6.cu packed weight slices, index = CTAs per head (1, 2), built on first use
+    DevBuf<float> d6_params[3];
+    bool use_dec6 = true;           // WB200_DEC6=0 disables the head-fused cluster decoder (A/B against decoder4.cu)
     DevBuf<unsigned int> d3_bar;
     DevBuf<int> steps_done;
     DevBuf<float> datt;
