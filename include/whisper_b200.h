@@ -118,7 +118,8 @@ int wb_forward_decoder(wb_model* m, const int64_t* tokens, int64_t n_batch, int6
 /* ---- KV-cached decoding session -------------------------------------------------------- */
 /* A session holds, for up to max_windows audio windows x max_beams live beams each: encoder
  * output, per-layer cross K/V (computed once per window), per-layer self K/V for
- * max_text_len positions, and all workspaces. */
+ * max_text_len positions, and all workspaces.  max_beams <= 7 and k <= 7 in wb_session_step (the decoders keep 8 candidates per
+ * record; the reference searches with width 5, src/transcribe.rs:232); larger values are rejected with WB_ERR_INVALID_ARG. */
 int wb_session_create(wb_model* m, int64_t max_windows, int64_t max_beams, int64_t max_text_len,
                       int kv_dtype, wb_session** out);
 void wb_session_destroy(wb_session* s);
@@ -157,7 +158,9 @@ int wb_transcribe_windows_dev(wb_session* s, const float* wave_dev, const int64_
                               int64_t n_windows, int beam_size, int max_depth, const wb_special_ids* ids,
                               const uint8_t* is_special, int64_t* tokens_out, int64_t capacity, int64_t* lens_out);
 /* waveform_to_text without detokenisation: windowing (transcribe.rs:114-138), per-window
- * decoding, overlap merge (transcribe.rs:56-63).  Writes the merged ids. */
+ * decoding, overlap merge (transcribe.rs:56-63).  Writes the merged ids.
+ * sample_rate must be 16000 (WB_ERR_INVALID_ARG otherwise): the log-mel tables are the 16 kHz ones the reference's binary
+ * always uses (src/bin/transcribe/main.rs:38-41); wb_prep_audio likewise assumes 16 kHz input. */
 int wb_waveform_to_tokens(wb_session* s, const float* waveform, int64_t n_samples, int64_t sample_rate,
                           int beam_size, int max_depth, const wb_special_ids* ids, const uint8_t* is_special,
                           int64_t* tokens_out, int64_t capacity, int64_t* n_tokens_out);
@@ -192,8 +195,8 @@ int wb_load_wav(const char* path, int strict_16k_mono, float* out, int64_t capac
                 int64_t* sample_rate_out, int* channels_out);
 
 /* ---- measurement ----------------------------------------------------------------------------- */
-/* Diagnostics: which persistent decoder kernel the last decode launch used: 4 = cluster/DSMEM (decoder4.cu), 5 = batched
- * tensor-core (decoder5.cu), 3 = grid-barrier FMA fallback (decoder3.cu), 0 = none yet. */
+/* Diagnostics: which persistent decoder kernel the last decode launch used: 6 = head-fused cluster decoder (decoder6.cu),
+ * 5 = batched tensor-core (decoder5.cu), 4 = cluster/DSMEM (decoder4.cu), 3 = grid-barrier FMA fallback (decoder3.cu), 0 = none yet. */
 int wb_session_last_decoder(const wb_session* s);
 /* kernels launched by this library on this thread's sessions since the last reset */
 int64_t wb_kernel_launch_count(void);

@@ -1,32 +1,34 @@
+"""Stage trace of the persistent decoder: WB200_TRACE=<file> python scripts/trace_decode.py [model] [chunks] [kv] [depth]
+Prints the mean gap between consecutive time stamps of CTA 0 (ns) per stamp index within a position."""
 import os, sys
 from pathlib import Path
-sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
-os.environ["WB200_TRACE"] = "1"
 import numpy as np
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import wb200  # noqa
-from whisper_burn_b200 import model, synth, transcribe
-dims, w_np = synth.make_weights(sys.argv[1] if len(sys.argv) > 1 else "tiny.en")
+from whisper_burn_b200 import audio, ffi, model, synth, transcribe
+
+name = sys.argv[1] if len(sys.argv) > 1 else "tiny.en"
+chunks = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+kv = sys.argv[3] if len(sys.argv) > 3 else "f32"
+depth = int(sys.argv[4]) if len(sys.argv) > 4 else 20
+dims, w = synth.make_weights(name, 0)
 sp = synth.special_tokens(dims)
-wh = model.Whisper(dims, w_np)
-chunk = synth.chunk_waveform(0)
-waves = [chunk[:238559], chunk[190559:429118], chunk[381118:]]
-sess = transcribe.Session(wh, 3, 1, 105)
-sess.transcribe_windows(waves, sp, sp.is_special_bitmap(), beam_size=1, max_depth=100)
-t = np.loadtxt("gpurun_out/d3_trace.txt", dtype=np.uint64).astype(np.int64)
-print("stamps", len(t), "total ms", (t[-1] - t[0]) / 1e6)
-# stamps: start, then per barrier (stage_end, barrier_end)
-L = dims.n_text_layer
-per_step = 2 * (8 * L + 2)
-names = [f"L{l}.{n}" for l in range(L) for n in ("qkv", "self", "out", "cq", "cross", "cout", "mlp1", "mlp2")] + ["logits", "finish"]
-body = t[1:]
-prefill = 3 * 2 * (8 * L)
-steps = body[prefill:]
-n = len(steps) // per_step
-steps = steps[:n * per_step].reshape(n, per_step // 2, 2)
-prev_end = np.concatenate([[body[prefill - 1]], steps[:-1, -1, 1]])
-stage = steps[:, :, 0] - np.concatenate([prev_end[:, None], steps[:, :-1, 1]], axis=1)
-barr = steps[:, :, 1] - steps[:, :, 0]
-print(f"steps {n}; mean step us {(steps[:, -1, 1] - prev_end).mean() / 1e3:.1f}")
-for i, nm in enumerate(names):
-    print(f"{nm:10s} stage {stage[:, i].mean() / 1e3:6.2f} us   barrier {barr[:, i].mean() / 1e3:6.2f} us")
-print("sum stage", stage.mean(0).sum() / 1e3, "sum barrier", barr.mean(0).sum() / 1e3)
+wh = model.Whisper(dims, w)
+bounds = transcribe.window_bounds(480000, 16000, audio.max_waveform_samples(dims.n_audio_ctx - 10))
+waves = [synth.chunk_waveform(c)[s:e] for c in range(chunks) for s, e in bounds]
+sess = transcribe.Session(wh, len(waves), 1, 4 + depth + 1, ffi.WB_KV_F16 if kv == "f16" else ffi.WB_KV_F32)
+isp = (np.arange(dims.n_vocab) >= sp.first_special).astype(np.uint8)
+trace_file = os.environ.pop("WB200_TRACE", None)
+sess.transcribe_windows(waves, sp, isp, 1, depth)       # warm
+if trace_file:
+    os.environ["WB200_TRACE"] = trace_file
+sess.transcribe_windows(waves, sp, isp, 1, depth)
+print("decoder", sess.last_decoder())
+if trace_file:
+    t = np.array([int(x) for x in open(trace_file).read().split()], dtype=np.int64)
+    d = np.diff(t)
+    n_pos = 3 + depth
+    # prefill positions have fewer stamps than logits positions: report the tail (logits positions)
+    per = (len(t) - 1) // n_pos if n_pos else 0
+    print("stamps", len(t), "total us", (t[-1] - t[0]) / 1e3, "per position us", (t[-1] - t[0]) / 1e3 / n_pos)
+    np.save(trace_file + ".npy", t)

@@ -151,3 +151,20 @@ def test_bench_reference_arm_contract():
     assert j["impl"] == "reference" and j["metric"] == "audio-seconds/sec" and j["unit"] == "audio-s/s" and j["higher_is_better"] is True
     assert j["value"] > 0 and j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1
     assert j["e2e"] == {"value": j["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_integration_excerpts_are_literal_and_shim_symbols_exist():
+    """INTEGRATION.md quotes rust/src/lib.rs literally, and every wb_* symbol the Rust shim binds is declared in the header
+    (and therefore exported: test_header_symbols_match_library)."""
+    import re
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    lib = (root / "rust" / "src" / "lib.rs").read_text()
+    md = (root / "INTEGRATION.md").read_text()
+    blocks = re.findall(r"<!-- excerpt:\w+ -->\n```rust\n(.*?)```\n<!-- /excerpt -->", md, flags=re.S)
+    assert len(blocks) == 2
+    for b in blocks:
+        assert b in lib, "INTEGRATION.md excerpt drifted from rust/src/lib.rs"
+    header = (root / "include" / "whisper_b200.h").read_text()
+    for sym in set(re.findall(r"pub fn (wb_\w+)\(", lib)):
+        assert re.search(r"\b" + sym + r"\(", header), f"{sym} bound by the shim but not declared in the header"

@@ -272,7 +272,7 @@ int wb_forward_decoder(wb_model* m, const int64_t* tokens, int64_t n_batch, int6
             }
             WB_CUDA(cudaMemcpyAsync(s.cur_tok.p, tk.data(), tk.size() * sizeof(int), cudaMemcpyHostToDevice, s.st));
             WB_CUDA(cudaStreamSynchronize(s.st));
-            s.step_core(true, 0, 1, false, -1, nullptr);
+            s.step_core(true, 0, 1, false, -1);
             for (int64_t r = 0; r < n_batch; ++r)
                 WB_CUDA(cudaMemcpyAsync(all.p + ((size_t)r * seq_len + p) * V, s.logits.p + (size_t)r * V,
                                         (size_t)V * sizeof(float), cudaMemcpyDeviceToDevice, s.st));
@@ -413,6 +413,9 @@ int wb_window_bounds(int64_t n_samples, int64_t sample_rate, int64_t window_len,
 static void waveforms_to_tokens(wb::Session& S, const float* const* waveforms, const int64_t* n_samples, int64_t n_waveforms,
                                 int64_t sample_rate, int beam_size, int max_depth, const wb_special_ids& ids,
                                 const uint8_t* is_special, std::vector<std::vector<int64_t>>& out) {
+    // the frontend tables (mel filterbank, DFT bins) are the 16 kHz ones: the reference builds them from the caller's rate
+    // (audio.rs:44, 67-143) but its binary only ever passes 16 kHz (src/bin/transcribe/main.rs:38-41 asserts it)
+    WB_REQUIRE(sample_rate == 16000, "waveform_to_tokens: only 16 kHz input is supported (frontend tables are built for 16 kHz)");
     const int64_t window_len = wb_max_waveform_samples(S.m->dims.n_audio_ctx - wb::MEL_PADDING);   // transcribe.rs:32-34
     std::vector<const float*> ptrs;
     std::vector<int64_t> lens;

@@ -1,4 +1,4 @@
-// Argument blocks of the decoder-step kernels (decoder.cu).  Internal.
+// Argument blocks of the persistent decoder kernels.  Internal.
 #pragma once
 #include <stdint.h>
 
@@ -6,177 +6,7 @@
 
 namespace wb {
 
-enum { IN_LN = 0, IN_COPY = 1, IN_ATTN_MERGE = 2 };
-
-struct GemvSeg {          // output columns [begin, next.begin) go to out + r*row_stride + p*pos_stride + (n-begin)
-    int begin;
-    float* out;
-    int64_t row_stride;
-    int64_t pos_stride;   // multiplied by the current position (KV-cache append)
-    float scale;
-};
-
-struct GemvArgs {
-    const void* W = nullptr;     // [N][K] fp16 or fp32
-    const float* bias = nullptr;
-    int N = 0, K = 0, R = 0;
-    int in_mode = IN_COPY;
-    const float* in = nullptr;   // [R][K] for IN_LN / IN_COPY
-    const float* ln_g = nullptr;
-    const float* ln_b = nullptr;
-    float ln_eps = 1e-5f;
-    int eps_outside = 1;
-    const float* part_o = nullptr;   // IN_ATTN_MERGE: [R][H][S][64], [R][H][S], [R][H][S]
-    const float* part_m = nullptr;
-    const float* part_l = nullptr;
-    int n_splits = 1;
-    int act = ACT_NONE;
-    int residual = 0;            // out += value
-    GemvSeg seg[3];
-    int n_seg = 1;
-    const int* pos = nullptr;    // device pointer to the current position (may be null -> 0)
-};
-
-struct DecAttnArgs {
-    const float* q = nullptr;    // [R][q_ld], head h at column h*64
-    int64_t q_ld = 0;
-    const float* K = nullptr;
-    const float* V = nullptr;
-    int64_t kv_ld = 0;           // row stride in elements
-    int is_cross = 0;
-    // cross: per-window geometry
-    const int* row_window = nullptr;      // [R]
-    const int64_t* win_row_off = nullptr; // [W]
-    const int* win_T = nullptr;           // [W]
-    // self: cache geometry
-    const int* anc = nullptr;             // [R][t_max] or null
-    int t_max = 0;
-    const int* pos = nullptr;
-    float* part_o = nullptr;
-    float* part_m = nullptr;
-    float* part_l = nullptr;
-};
-
-struct LogSoftmaxArgs {
-    const float* logits = nullptr;   // [R][V]
-    int V = 0;
-    const uint8_t* is_special = nullptr;
-    int mask_mode = 0;               // 0 never, 1 always, 2 while seq_len <= 5 (transcribe.rs:271)
-    const int* pos = nullptr;
-    int k = 1;
-    int* topk_id = nullptr;          // [R][k]
-    float* topk_lp = nullptr;        // [R][k]
-    float* logprob_out = nullptr;    // optional [R][V]
-    // greedy bookkeeping
-    int greedy = 0;
-    int* tokens = nullptr;           // [R][t_max]
-    int* lengths = nullptr;
-    int* cur_tok = nullptr;
-    int* finished = nullptr;
-    int t_max = 0;
-    int eot = -1;
-};
-
-// ---- fused step, version 2 (decoder2.cu) ----------------------------------------------------------
-constexpr int DEC2_KC = 8;   // top candidates kept per logits CTA and row (>= k + 1)
-
-struct Dec2SelfArgs {
-    float* x = nullptr;            // [R][d] residual stream (complete on entry, updated on exit)
-    int R = 0, d = 0;
-    const float* ln_g = nullptr;
-    const float* ln_b = nullptr;
-    float ln_eps = 1e-5f;
-    int eps_outside = 1;
-    const void* Wqkv = nullptr;    // [3d][d]
-    const float* bqkv = nullptr;
-    const void* Wo = nullptr;      // [d][d]
-    const float* bo = nullptr;
-    float qk_scale = 1.0f;
-    float* kc = nullptr;           // this layer's self K cache [Rmax][t_max][d]
-    float* vc = nullptr;
-    const int* anc = nullptr;      // [R][t_max] or null (identity)
-    int t_max = 0;
-    const int* pos = nullptr;
-    float* ypart = nullptr;        // [H][R][d]
-    unsigned int* counter = nullptr;
-};
-
-struct Dec2CrossArgs {
-    float* x = nullptr;
-    int R = 0, d = 0;
-    const float* ln_g = nullptr;
-    const float* ln_b = nullptr;
-    float ln_eps = 1e-5f;
-    int eps_outside = 1;
-    const void* Wq = nullptr;      // [d][d]
-    const float* bq = nullptr;
-    const void* Wo = nullptr;
-    const float* bo = nullptr;
-    float qk_scale = 1.0f;
-    const float* ckv = nullptr;    // this layer's cross K|V rows [M][2d]
-    const int* row_window = nullptr;
-    const int64_t* win_row_off = nullptr;
-    const int* win_T = nullptr;
-    int kmax = 0;                  // max keys per split
-    float* ypart = nullptr;        // [H][S][R][d]
-    float* part_m = nullptr;       // [H][S][R]
-    float* part_l = nullptr;
-    unsigned int* counter = nullptr;
-};
-
-struct Dec2MlpArgs {
-    float* x = nullptr;
-    int R = 0, d = 0;
-    const float* ln_g = nullptr;
-    const float* ln_b = nullptr;
-    float ln_eps = 1e-5f;
-    int eps_outside = 1;
-    const void* W1 = nullptr;      // [4d][d]
-    const float* b1 = nullptr;
-    const void* W2 = nullptr;      // [d][4d]
-    const float* b2 = nullptr;
-    float* ypart = nullptr;        // [4d/32][R][d]
-    unsigned int* counter = nullptr;
-};
-
-struct Dec2LogitsArgs {
-    const float* x = nullptr;
-    int R = 0, d = 0, V = 0;
-    const float* ln_g = nullptr;
-    const float* ln_b = nullptr;
-    float ln_eps = 1e-5f;
-    int eps_outside = 1;
-    const void* E = nullptr;       // token embedding [V][d]
-    const uint8_t* is_special = nullptr;
-    int mask_mode = 0;
-    const int* pos = nullptr;
-    float* logits_out = nullptr;   // optional [R][V] raw logits (stateless forward_decoder)
-    float* part_m = nullptr;       // [n_ctas][R]
-    float* part_s = nullptr;
-    float* part_v = nullptr;       // [n_ctas][R][KC]
-    int* part_i = nullptr;
-};
-
-struct Dec2FinishArgs {
-    int n_parts = 0;
-    const float* part_m = nullptr;
-    const float* part_s = nullptr;
-    const float* part_v = nullptr;
-    const int* part_i = nullptr;
-    int k = 1;
-    int* topk_id = nullptr;
-    float* topk_lp = nullptr;
-    int greedy = 0;
-    int* tokens = nullptr;
-    int* lengths = nullptr;
-    int* cur_tok = nullptr;
-    int* finished = nullptr;
-    int t_max = 0;
-    int eot = -1;
-    int* pos = nullptr;
-    int* n_unfinished = nullptr;
-    unsigned int* counter = nullptr;
-};
+constexpr int DEC_KC = 8;   // top candidates a persistent decoder keeps per record (k <= 7)
 
 // ---- persistent cooperative decoder (decoder3.cu) ------------------------------------------------------
 struct Dec3Layer {
@@ -270,19 +100,6 @@ int dec6_pick_hs(int d, int R);
 void dec6_build_pack(int d, int hs, const std::vector<Dec6LayerSrc>& layers, DevBuf<uint8_t>& pack, DevBuf<float>& params, cudaStream_t st);
 bool launch_dec6(const Dec3Args& a, int hs, bool w_half, cudaStream_t st);
 
-void launch_dec2_self(const Dec2SelfArgs& a, int H, bool w_half, cudaStream_t st);
-void launch_dec2_cross(const Dec2CrossArgs& a, int H, int S, bool w_half, cudaStream_t st);
-void launch_dec2_mlp(const Dec2MlpArgs& a, bool w_half, cudaStream_t st);
-void launch_dec2_logits(const Dec2LogitsArgs& a, int n_ctas, bool w_half, cudaStream_t st);
-void launch_dec2_finish(const Dec2FinishArgs& a, int R, cudaStream_t st);
-
-void launch_dec_embed(const int* tok, const float* emb, const float* pos_emb, const int* pos_ptr, float* x, int R,
-                      int d, cudaStream_t st);
-void launch_dec_gemv(const GemvArgs& a, bool w_half, cudaStream_t st);
-void launch_dec_attn(const DecAttnArgs& a, int n_head, int R, int n_splits, cudaStream_t st);
-int dec_attn_max_keys_per_split();
-void launch_logsoftmax_topk(const LogSoftmaxArgs& a, int R, cudaStream_t st);
-void launch_dec_advance(int* pos, const int* finished, int R, int* n_unfinished, cudaStream_t st);
 void launch_dec_anc_identity(int* anc, int R, int t_max, cudaStream_t st);
 void launch_dec_reorder(const int* anc_old, int* anc_new, const int* parent, const int* pos_ptr, int R, int t_max,
                         cudaStream_t st);

@@ -2,7 +2,8 @@
 //
 // Same math and single-launch structure as decoder3.cu (TextDecoder::forward src/model/mod.rs:131-157, blocks :345-350,
 // attention :428-533, MLP :376-382, search closure src/transcribe.rs:253-307; prefill + every greedy step in one kernel), but
-// the per-layer chain is cut from 8 cluster-wide stages (decoder4.cu) to THREE exchanges:
+// the per-layer chain is cut from 8 cluster-wide stages (decoder4.cu) to THREE exchanges, and every linear layer runs on the
+// 5th-generation tensor cores:
 //
 //   one thread-block cluster of CS = H * HS CTAs owns one batch row; CTA (h, hs) owns attention head h.
 //   phase 1  x -> LN1 -> q_h | k_h | v_h (192 weight rows) -> causal self attention of head h -> the head's K-slice of the
@@ -16,11 +17,16 @@
 //   in a fixed order, identically in every CTA) and owns a full copy of the residual stream again.  No hardware cluster barrier
 //   inside the step, no cross-thread release/acquire chains: data and its "ready" signal travel together.
 //
-//   Weights do not depend on activations, so they never wait for the chain: a dedicated PRODUCER warp streams the CTA's weight
-//   slices -- pre-packed per (layer, CTA) in exactly the order and register layout the consumers use (dec6_pack_kernel) -- and
-//   the cross K/V block through a 6 x 24 KB shared-memory ring with bulk copies (TMA engine, full/empty mbarriers).  The
-//   8 consumer warps run the dependent chain on on-chip data only: GEMV = one conflict-free 16-byte shared load per lane and
-//   8 FMAs (4 rows x 8 lanes per warp pass, the activation slice in registers), attention = 8 lanes per key.
+//   Linear layers = swap-AB tcgen05.mma (kind::f16, M = 128 weight rows, N = 16, K = 16): the weight slices of this CTA are
+//   pre-packed per (layer, CTA) as 128-row x 64-column slabs in the canonical K-major 128B-swizzled shared-memory image
+//   (dec6_pack_kernel), so a slab is ONE 16 KB bulk copy (TMA engine) into a ring slot and IS the A operand; the activation is
+//   the B operand: 16 rows of which row 0 = fp16(x) and row 1 = fp16((x - hi) * 2048) (the decoder5.cu split: exact products,
+//   fp32 accumulation), the rest zero.  The accumulator [128 lanes][16 columns] lives in TMEM (two of them, ping-pong); thread
+//   `row` of an epilogue warp group reads its lane with tcgen05.ld, combines hi + lo / 2048 and applies bias / scale / GELU.
+//   Weights do not depend on activations, so they never wait for the chain: a PRODUCER warp streams weight slabs and the cross
+//   K/V block through the ring (full / empty mbarriers), an MMA warp (one elected thread) issues the tensor-core instructions
+//   as slabs land and releases the slots with tcgen05.commit; the 8 consumer warps run the dependent chain: LayerNorm,
+//   attention (8 lanes per key), epilogues, the exchange.
 //
 //   Only the vocabulary projection is chip-wide (as in decoder4.cu: bulk-copy ring of contiguous half-tiles of the tied
 //   embedding, mma.sync swap-AB with fp16 hi/lo activation planes, fused mask / online softmax / arg-max), behind ONE grid
@@ -43,23 +49,27 @@ namespace wb {
 namespace {
 
 constexpr int NCW = 8;                    // consumer warps (threads 0..255)
-constexpr int NTH6 = (NCW + 1) * 32;      // + one producer warp
-constexpr int SLOT = 24576;               // bytes per ring slot
-constexpr int NSLOT = 6;
-constexpr int LG_NBUF = 3;                // logits stage: ring slots per warp (aliases the weight ring)
+constexpr int W_PROD = NCW, W_MMA = NCW + 1;
+constexpr int NTH6 = (NCW + 2) * 32;      // + producer warp + MMA warp
+constexpr int SLOT = 16384;               // bytes per ring slot = one 128-row x 64-column fp16 slab
+constexpr int NSLOT = 8;
+constexpr int LG_NBUF = 2;                // logits stage: ring slots per warp (aliases the weight ring)
+constexpr int BX_SLAB = 2048;             // B operand: 16 rows x 128 bytes per 64-column slab
+constexpr uint32_t TMEM_COLS = 32;        // two 16-column accumulators
 
 template <int D, int HS>
 struct Geo {
     static constexpr int H = D / 64, CS = H * HS, NS = 4 * D / CS, SEND = D + 4;
-    // packed weight segments of one (layer, rank), bytes
-    static constexpr int OFF_QKV = 0, OFF_O = OFF_QKV + 192 * D * 2, OFF_CQ = OFF_O + D * 64 * 2, OFF_CO = OFF_CQ + 64 * D * 2,
-                         OFF_W1 = OFF_CO + D * 64 * 2, OFF_W2 = OFF_W1 + NS * D * 2, PACK = OFF_W2 + D * NS * 2;
+    static constexpr int pad128(int n) { return (n + 127) / 128 * 128; }
+    // packed weight segments of one (layer, rank), bytes: [tiles of 128 rows][K / 64 slabs][16 KB]
+    static constexpr int OFF_QKV = 0, OFF_O = OFF_QKV + pad128(192) * D * 2, OFF_CQ = OFF_O + pad128(D) * 64 * 2, OFF_CO = OFF_CQ + pad128(64) * D * 2,
+                         OFF_W1 = OFF_CO + pad128(D) * 64 * 2, OFF_W2 = OFF_W1 + pad128(NS) * D * 2, PACK = OFF_W2 + pad128(D) * NS * 2;
     // parameter block of one (layer, rank), floats
     static constexpr int P_LN1G = 0, P_LN1B = D, P_LN2G = 2 * D, P_LN2B = 3 * D, P_LN3G = 4 * D, P_LN3B = 5 * D, P_BO = 6 * D,
                          P_BCO = 7 * D, P_B2 = 8 * D, P_BQKV = 9 * D, P_BCQ = 9 * D + 192, P_B1 = 9 * D + 256, P_EPS = 9 * D + 256 + NS, PARAMS = 9 * D + 256 + NS + 4;
+    static constexpr int KMAX = D > NS ? D : NS;   // widest B operand
     static_assert(PARAMS % 4 == 0 && SEND % 4 == 0 && NS % 64 == 0 && D % 64 == 0, "layout");
 };
-__host__ __device__ constexpr int rows_per_chunk(int K) { return 32 * ((SLOT / (64 * K)) < 1 ? 1 : (SLOT / (64 * K))); }
 
 // ---- small PTX helpers -------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -91,13 +101,42 @@ __device__ __forceinline__ void bulk_s2peer(void* dst_local, const void* src, ui
     asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(rd), "r"(s32(src)), "r"(bytes), "r"(rb) : "memory");
 }
 __device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-__device__ __forceinline__ void bar_all() { asm volatile("bar.sync 2, 288;" ::: "memory"); }
+__device__ __forceinline__ void bar_all() { asm volatile("bar.sync 2, 320;" ::: "memory"); }
 __device__ __forceinline__ float group8_sum(float v) {   // sum over the 8 lanes that share lane >> 3 (all lanes converged)
     v += __shfl_xor_sync(0xffffffffu, v, 1);
     v += __shfl_xor_sync(0xffffffffu, v, 2);
     v += __shfl_xor_sync(0xffffffffu, v, 4);
     return v;
 }
+// ---- tcgen05 (see gemm_f16.cu for the same descriptors in a GEMM) ------------------------------------------------------------
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_c),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major, SWIZZLE_128B operand tile (rows of 128 bytes, 8-row groups of 1024 bytes)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);         // start address >> 4        bits [0,14)
+    d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major) = 1
+    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset: 8 rows * 128 B    bits [32,46)
+    d |= (uint64_t)1 << 46;                          // descriptor version 1 (sm_100)
+    d |= (uint64_t)2 << 61;                          // layout type SWIZZLE_128B
+    return d;
+}
+// byte offset of element (row, k) inside a K-major 128B-swizzled operand whose 64-column slabs are `slab_bytes` apart
+__device__ __host__ __forceinline__ uint32_t sw128_off(int row, int k, int slab_bytes) {
+    return (uint32_t)((k >> 6) * slab_bytes + row * 128 + ((((k & 63) >> 3) ^ (row & 7)) << 4) + (k & 7) * 2);
+}
+
 // which of the 64 head dims is element i (0..7) of lane l8: two 16-byte chunks (fp32: l8 and l8 + 8) / one (fp16: l8)
 template <typename KVT>
 __device__ __forceinline__ int hdim(int l8, int i) {
@@ -149,34 +188,32 @@ struct Softmax8 {   // online softmax state of one (warp, rg) key slot; o = the 
 };
 
 // ---- weight / parameter packing (once per session) ---------------------------------------------------------------------
-// Segment [N][K] (fp16, row-major source rows n0 + n, columns k0 .. k0 + K of a [.][ldk] matrix) in consumer order: chunks of
-// rows_per_chunk(K) rows; inside a chunk 32-row groups; inside a group warp w owns rows 4w .. 4w+3; lane (rg, l8) of the warp's
-// j-th 512-byte load holds the 8 halves [row 4w + rg][(l8 + 8j) * 8 ..].
+// Segment [N][K] (fp16, source rows n0 + (r / piece) * piece_stride + r % piece, columns k0 .. k0 + K of a [.][ldk] matrix) as
+// tiles of 128 rows (zero-padded), each tile as K / 64 slabs of 16 KB in the K-major 128B-swizzled shared-memory image:
+// 16-byte unit (row r, chunk c) of a slab at r * 128 + ((c ^ (r & 7)) << 4).  A slab is what one bulk copy moves and what one
+// group of four tcgen05.mma (K = 16 each) reads.
 struct PackSeg {
     const __half* src;
     int ldk, n0, k0, N, K;
-    int piece, piece_stride;   // segment row r comes from source row n0 + (r / piece) * piece_stride + r % piece
-    int64_t dst_off;           // bytes
+    int piece, piece_stride;
+    int64_t dst_off;   // bytes
 };
 __global__ void dec6_pack_kernel(const PackSeg* segs, int n_segs, uint8_t* dst) {
     for (int s = blockIdx.y; s < n_segs; s += gridDim.y) {
         const PackSeg g = segs[s];
-        const int JV = g.K / 64, rpc = rows_per_chunk(g.K);
-        const int64_t n16 = (int64_t)g.N * g.K / 8;
+        const int nslab = g.K / 64, ntile = (g.N + 127) / 128;
+        const int64_t n16 = (int64_t)ntile * nslab * 1024;   // 16-byte units
         for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) {
-            // i indexes 16-byte units in destination order
-            const int64_t chunk_units = (int64_t)rpc * g.K / 8;
-            const int c = (int)(i / chunk_units);
-            int64_t u = i % chunk_units;
-            const int lane = (int)(u & 31);
-            u >>= 5;
-            const int j = (int)(u % JV);
-            u /= JV;
-            const int w = (int)(u & 7), grp = (int)(u >> 3);
-            const int row = c * rpc + grp * 32 + w * 4 + (lane >> 3), vec = (lane & 7) + 8 * j;
-            const int srow = g.n0 + (row / g.piece) * g.piece_stride + row % g.piece;
-            const uint4 v = *reinterpret_cast<const uint4*>(g.src + (int64_t)srow * g.ldk + g.k0 + vec * 8);
-            *reinterpret_cast<uint4*>(dst + g.dst_off + i * 16) = v;
+            const int c = (int)(i & 7), r = (int)((i >> 3) & 127);
+            const int64_t ts = i >> 10;
+            const int sl = (int)(ts % nslab), t = (int)(ts / nslab);
+            const int row = t * 128 + r;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (row < g.N) {
+                const int srow = g.n0 + (row / g.piece) * g.piece_stride + row % g.piece;
+                v = *reinterpret_cast<const uint4*>(g.src + (int64_t)srow * g.ldk + g.k0 + sl * 64 + c * 8);
+            }
+            *reinterpret_cast<uint4*>(dst + g.dst_off + ts * SLOT + r * 128 + ((c ^ (r & 7)) << 4)) = v;
         }
     }
 }
@@ -192,63 +229,126 @@ __global__ void dec6_param_kernel(const ParamSeg* segs, int n_segs, float* dst) 
     }
 }
 
-// ---- consumer-side ring access -------------------------------------------------------------------------------------------
-struct Ring {
-    uint8_t* mem;
-    uint64_t *full, *empty;
-    uint32_t n;   // chunks consumed (consumers) / issued (producer) since kernel start
-    __device__ __forceinline__ const uint8_t* wait() {
-        mbar_wait(full + n % NSLOT, (n / NSLOT) & 1);
-        return mem + (n % NSLOT) * SLOT;
-    }
-    __device__ __forceinline__ void release() {   // consumer warp is done with the current chunk
-        __syncwarp();
-        if ((threadIdx.x & 31) == 0) mbar_arrive(empty + n % NSLOT);
-        ++n;
-    }
-    __device__ __forceinline__ void push(const void* src, uint32_t bytes) {   // producer lane
-        const uint32_t slot = n % NSLOT;
-        if (n >= NSLOT) mbar_wait(empty + slot, ((n / NSLOT) - 1) & 1);
-        mbar_expect_tx(full + slot, bytes);
-        bulk_g2s(mem + slot * SLOT, src, bytes, full + slot);
-        ++n;
-    }
-};
+// ---- building blocks of a phase.  Code size is latency here (decoder5.cu, lesson 2): the layer body runs once per layer and
+// position, i.e. mostly from a cold instruction cache, so every block exists ONCE (noinline, runtime shapes) and the phases are
+// short call sequences.
 
-// y[n] = sum_k W[n][k] x[k] for a packed [N][K] segment streamed through the ring; xr = the lane's slice of x
-// (xr[j][e] = x[(l8 + 8j) * 8 + e]); emit(row, sum) runs in the 4 lanes with l8 == 0.
-template <int K, typename Emit>
-__device__ __forceinline__ void gemv_seg(Ring& ring, int N, const float (&xr)[K / 64][8], Emit&& emit) {
-    constexpr int JV = K / 64, RPC = rows_per_chunk(K);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int r0 = 0; r0 < N; r0 += RPC) {
-        const int groups = min(RPC, N - r0) >> 5;
-        const uint8_t* blk = ring.wait();
-#pragma unroll 2
-        for (int g = 0; g < groups; ++g) {
-            const uint4* p = reinterpret_cast<const uint4*>(blk + (size_t)((g * 8 + warp) * JV) * 512) + lane;
-            uint4 raw[JV];
-#pragma unroll
-            for (int j = 0; j < JV; ++j) raw[j] = p[j * 32];
-            float a0 = 0.0f, a1 = 0.0f;
-#pragma unroll
-            for (int j = 0; j < JV; ++j) {
-                float w[8];
-                cvt8(raw[j], w);
-                a0 = fmaf(w[0], xr[j][0], a0); a1 = fmaf(w[1], xr[j][1], a1); a0 = fmaf(w[2], xr[j][2], a0); a1 = fmaf(w[3], xr[j][3], a1);
-                a0 = fmaf(w[4], xr[j][4], a0); a1 = fmaf(w[5], xr[j][5], a1); a0 = fmaf(w[6], xr[j][6], a0); a1 = fmaf(w[7], xr[j][7], a1);
-            }
-            const float s = group8_sum(a0 + a1);
-            if ((lane & 7) == 0) emit(r0 + g * 32 + warp * 4 + (lane >> 3), s);
-        }
-        ring.release();
-    }
+// the B operand of the next linear layer: value v of column k -> fp16 hi in row 0, fp16 (residual * 2048) in row 1
+__device__ __forceinline__ void bx_store(uint8_t* bx, int k, float v) {
+    const __half h = __float2half_rn(v);
+    *reinterpret_cast<__half*>(bx + sw128_off(0, k, BX_SLAB)) = h;
+    *reinterpret_cast<__half*>(bx + sw128_off(1, k, BX_SLAB)) = __float2half_rn((v - __half2float(h)) * 2048.0f);
 }
 
-// LayerNorm (burn 0.9 form, dec_common.cuh stage_ln) of the row x_s[D], every warp for itself; the lane's slice lands in registers
+struct Pipe {        // shared-memory handles of the ring / tensor-core pipeline
+    uint8_t* ring;   // [NSLOT][SLOT]
+    uint64_t *full, *empty;      // per slot
+    uint64_t* b_ready;           // B operand written (consumers -> MMA warp)
+    uint64_t *acc_full, *acc_free;   // [2] accumulator ping-pong (MMA warp <-> epilogue warp groups)
+    uint32_t tmem;               // base of the 32 allocated TMEM columns
+};
+struct Counters {    // progress counters every role keeps in registers (identical sequences by construction)
+    uint32_t n;      // ring chunks consumed / issued
+    uint32_t tile;   // output tiles
+    uint32_t gemv;   // linear layers
+};
+
+enum { EM_PLAIN = 0, EM_QKV = 1, EM_CQ = 2, EM_HID = 3 };
+template <typename KVT>
+struct GemvOut {
+    int mode;
+    const float* bias;
+    float scale;
+    float* out;        // EM_PLAIN: y[n]; EM_QKV: qkv_s[n]; EM_CQ: q2_s[n]; EM_HID: hid_s[n]
+    KVT *kdst, *vdst;  // EM_QKV: this position's 64-element head slice of the self K / V cache
+};
+
+// Consumer side of one linear layer y[n] = sum_k W[n][k] x[k] (n < N, N padded to tiles of 128 rows): the B operand has been
+// written; hand it to the MMA warp, then the warp group (tile & 1) reads accumulator (tile & 1) -- TMEM lane = weight row --
+// and applies the epilogue.  Ends with a barrier of the consumer warps.
+template <typename KVT>
+__device__ __noinline__ Counters gemv_epi6(const Pipe P, Counters c, int N, int n_slabs, const GemvOut<KVT> o) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes of the B operand -> tensor-core (async proxy) reads
+    bar_consumers();
+    if (tid == 0) mbar_arrive(P.b_ready);
+    const int n_tiles = (N + 127) >> 7;
+#pragma unroll 1
+    for (int t = 0; t < n_tiles; ++t) {
+        const uint32_t T = c.tile + (uint32_t)t, g = T & 1;
+        if ((uint32_t)(warp >> 2) != g) continue;
+        mbar_wait(P.acc_full + g, (T >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t r0, r1;
+        const uint32_t taddr = P.tmem + ((uint32_t)((warp & 3) * 32) << 16) + g * 16;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(taddr) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(P.acc_free + g);                 // 4 warps: the accumulator may be overwritten
+        const int row = t * 128 + (warp & 3) * 32 + lane;
+        if (row < N) {
+            const float s = fmaf(__uint_as_float(r1), 1.0f / 2048.0f, __uint_as_float(r0));
+            if (o.mode == EM_PLAIN) {
+                o.out[row] = s;
+            } else if (o.mode == EM_QKV) {       // mod.rs:429-431; q and k carry (d/H)^-0.25 each (:500-503)
+                float v = __fadd_rn(s, o.bias[row]);
+                if (row < 128) v = __fmul_rn(v, o.scale);
+                if (row >= 64) {
+                    const KVT r = (KVT)v;          // fp16 cache: round-to-nearest where the value enters the cache
+                    (row < 128 ? o.kdst : o.vdst)[row & 63] = r;
+                    v = (float)r;
+                }
+                o.out[row] = v;
+            } else if (o.mode == EM_CQ) {        // cross query (mod.rs:483)
+                o.out[row] = __fmul_rn(__fadd_rn(s, o.bias[row]), o.scale);
+            } else {                             // gelu(LN(x) W1 + b1) (mod.rs:377-378)
+                o.out[row] = gelu_erf(__fadd_rn(s, o.bias[row]));
+            }
+        }
+    }
+    c.tile += (uint32_t)n_tiles;
+    c.n += (uint32_t)(n_tiles * n_slabs);
+    c.gemv += 1;
+    bar_consumers();
+    return c;
+}
+
+// MMA warp (one thread): the tensor-core side of the same linear layer
+__device__ __forceinline__ Counters gemv_mma6(const Pipe P, Counters c, int n_tiles, int n_slabs, uint32_t bx_addr) {
+    // instruction descriptor: D = F32 (1 << 4), A = B = F16 (format 0), K-major both, N >> 3 = 2 at bit 17, M >> 4 = 8 at bit 24
+    constexpr uint32_t idesc = (1u << 4) | (2u << 17) | (8u << 24);
+    mbar_wait(P.b_ready, c.gemv & 1);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+    for (int t = 0; t < n_tiles; ++t) {
+        const uint32_t T = c.tile, g = T & 1, u = T >> 1;
+        if (u >= 1) mbar_wait(P.acc_free + g, (u - 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+        for (int s = 0; s < n_slabs; ++s) {
+            const uint32_t slot = c.n % NSLOT;
+            mbar_wait(P.full + slot, (c.n / NSLOT) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t da = make_smem_desc(s32(P.ring + slot * SLOT)), db = make_smem_desc(bx_addr + (uint32_t)s * BX_SLAB);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)   // UMMA_K = 16 halves = 32 bytes -> +2 in the (>> 4) address field
+                umma_f16(P.tmem + g * 16, da + 2 * k, db + 2 * k, idesc, (s | k) != 0 ? 1u : 0u);
+            umma_commit(P.empty + slot);   // the slab may be overwritten when these MMAs have read it
+            ++c.n;
+        }
+        umma_commit(P.acc_full + g);       // accumulator complete
+        ++c.tile;
+    }
+    ++c.gemv;
+    return c;
+}
+
+// LayerNorm (burn 0.9 form, dec_common.cuh stage_ln) of the row x_s[D] by the 8 consumer warps: every warp computes the
+// statistics for itself (no block reduction), thread t normalises elements t, t + 256 and writes them as the B operand.
 template <int D>
-__device__ __forceinline__ void ln_to_regs(const float* x_s, const float* g, const float* b, float eps, int eps_outside, float (&xr)[D / 64][8]) {
-    const int lane = threadIdx.x & 31, l8 = lane & 7;
+__device__ __noinline__ void ln6(const float* x_s, const float* g, const float* b, float eps, int eps_outside, uint8_t* bx) {
+    const int tid = threadIdx.x, lane = tid & 31;
     float v[D / 32];
     float sum = 0.0f;
 #pragma unroll
@@ -261,32 +361,166 @@ __device__ __forceinline__ void ln_to_regs(const float* x_s, const float* g, con
     q = warp_sum(q);
     const float var = __fdiv_rn(q, (float)D);
     const float den = eps_outside ? __fadd_rn(__fsqrt_rn(var), eps) : __fsqrt_rn(__fadd_rn(var, eps));
-#pragma unroll
-    for (int j = 0; j < D / 64; ++j) {
-        const int c = (l8 + 8 * j) * 8;
-#pragma unroll
-        for (int hlf = 0; hlf < 2; ++hlf) {
-            const float4 x4 = *reinterpret_cast<const float4*>(x_s + c + 4 * hlf);
-            const float4 g4 = *reinterpret_cast<const float4*>(g + c + 4 * hlf);
-            const float4 b4 = *reinterpret_cast<const float4*>(b + c + 4 * hlf);
-            xr[j][4 * hlf + 0] = __fadd_rn(__fmul_rn(__fdiv_rn(__fsub_rn(x4.x, mean), den), g4.x), b4.x);
-            xr[j][4 * hlf + 1] = __fadd_rn(__fmul_rn(__fdiv_rn(__fsub_rn(x4.y, mean), den), g4.y), b4.y);
-            xr[j][4 * hlf + 2] = __fadd_rn(__fmul_rn(__fdiv_rn(__fsub_rn(x4.z, mean), den), g4.z), b4.z);
-            xr[j][4 * hlf + 3] = __fadd_rn(__fmul_rn(__fdiv_rn(__fsub_rn(x4.w, mean), den), g4.w), b4.w);
-        }
-    }
+#pragma unroll 1
+    for (int c = tid; c < D; c += 256) bx_store(bx, c, __fadd_rn(__fmul_rn(__fdiv_rn(__fsub_rn(x_s[c], mean), den), g[c]), b[c]));
 }
-template <int K>
-__device__ __forceinline__ void slice_to_regs(const float* v_s, float (&xr)[K / 64][8]) {
-    const int l8 = threadIdx.x & 7;
+
+// merges the 8 per-warp attention records (wm, wl, wo) into the head's un-normalised output, written as the B operand of the
+// out projection, and its (max, sum) record
+__device__ __noinline__ void attn_merge6(const float* wm, const float* wl, const float* wo, uint8_t* bx, float* rec, float active) {
+    const int tid = threadIdx.x;
+    bar_consumers();
+    if (tid < 64) {
+        float M = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < K / 64; ++j) {
-        const float4 a = *reinterpret_cast<const float4*>(v_s + (l8 + 8 * j) * 8), b = *reinterpret_cast<const float4*>(v_s + (l8 + 8 * j) * 8 + 4);
-        xr[j][0] = a.x; xr[j][1] = a.y; xr[j][2] = a.z; xr[j][3] = a.w; xr[j][4] = b.x; xr[j][5] = b.y; xr[j][6] = b.z; xr[j][7] = b.w;
+        for (int w2 = 0; w2 < NCW; ++w2) M = fmaxf(M, wm[w2]);
+        float Ls = 0.0f, o = 0.0f;
+#pragma unroll
+        for (int w2 = 0; w2 < NCW; ++w2) {
+            const float sc = wm[w2] > -INFINITY ? expf(wm[w2] - M) : 0.0f;
+            Ls += sc * wl[w2];
+            o += sc * wo[w2 * 64 + tid];
+        }
+        bx_store(bx, tid, o);
+        if (tid == 0) { rec[0] = M; rec[1] = Ls; rec[2] = active; rec[3] = 0.0f; }
     }
 }
 
 enum { MODE_SUM = 0, MODE_ATTN = 1 };
+
+// x += bias + sum over sources of weight * partial (fixed order, identical in every CTA of the cluster).  pr = the phase's
+// records [CS][D + 4] (y, max, sum, active); MODE_ATTN: softmax merge of the key splits of each head on the receiving side
+// (mod.rs:516-527 computed in pieces); MODE_SUM: plain sum.  Ends with a barrier.
+template <int D, int HS>
+__device__ __noinline__ void combine6(const float* pr, uint64_t* bar, uint32_t parity, int mode, const float* bias, float* x_s, float* wsrc_s) {
+    constexpr int H = D / 64, CS = H * HS, SEND = D + 4;
+    const int tid = threadIdx.x;
+    if (tid == 0) mbar_expect_tx(bar, CS * SEND * 4);
+    mbar_wait(bar, parity);
+    if (tid < CS) {
+        float wgt = 1.0f;
+        if (mode == MODE_ATTN) {
+            const int hh = tid % H;
+            float M = -INFINITY;
+#pragma unroll
+            for (int s = 0; s < HS; ++s)
+                if (pr[(hh + H * s) * SEND + D + 2] != 0.0f) M = fmaxf(M, pr[(hh + H * s) * SEND + D]);
+            float den = 0.0f;
+#pragma unroll
+            for (int s = 0; s < HS; ++s) {
+                const float* rec = pr + (hh + H * s) * SEND + D;
+                if (rec[2] != 0.0f && rec[0] > -INFINITY) den += expf(rec[0] - M) * rec[1];
+            }
+            const float* me = pr + tid * SEND + D;
+            wgt = (me[2] != 0.0f && me[0] > -INFINITY) ? __fdiv_rn(expf(me[0] - M), den) : 0.0f;
+        }
+        wsrc_s[tid] = wgt;
+    }
+    bar_consumers();
+#pragma unroll 1
+    for (int c = tid; c < D; c += 256) {
+        float acc = bias[c];
+#pragma unroll 4
+        for (int s = 0; s < CS; ++s) acc = fmaf(wsrc_s[s], pr[s * SEND + c], acc);
+        x_s[c] = __fadd_rn(x_s[c], acc);
+    }
+    bar_consumers();
+}
+
+// causal self attention of one head over positions 0..p (mod.rs:428-436 with the mask of :535-544 = "keys <= p"): 32 (warp, rg)
+// key slots, 8 lanes per key; keys < p come from the cache (L2), key p from shared memory.  Leaves per-warp records in wm/wl/wo.
+template <typename KVT>
+__device__ __noinline__ void self_attn6(const float* qkv_s, const KVT* kbase, const KVT* vbase, int ld, int p, float* wm, float* wl, float* wo) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, rg = lane >> 3, l8 = lane & 7;
+    float q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q[i] = qkv_s[hdim<KVT>(l8, i)];
+    Softmax8 A;
+    A.init();
+    float kf[4][8], vf[4][8];
+    const int j0 = warp * 4 + rg;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {                          // all loads first (t_max <= 128 -> at most 4 keys per slot)
+        const int j = j0 + 32 * u;
+        if (j < p) {
+            load_row8<KVT>(kbase + (int64_t)j * ld, l8, 0, kf[u], false);
+            load_row8<KVT>(vbase + (int64_t)j * ld, l8, 0, vf[u], false);
+        } else if (j == p) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { kf[u][i] = qkv_s[64 + hdim<KVT>(l8, i)]; vf[u][i] = qkv_s[128 + hdim<KVT>(l8, i)]; }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { kf[u][i] = 0.0f; vf[u][i] = 0.0f; }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        float s = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s = fmaf(q[i], kf[u][i], s);
+        s = group8_sum(s);
+        if (j0 + 32 * u <= p) A.add(s, vf[u]);
+    }
+    A.merge_xor(8);
+    A.merge_xor(16);
+    if (rg == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) wo[warp * 64 + hdim<KVT>(l8, i)] = A.o[i];
+        if (l8 == 0) { wm[warp] = A.m; wl[warp] = A.l; }
+    }
+}
+
+// cross attention of one head over keys [k_begin, k_end) of the window (mod.rs:482-490), the head-major K/V block arriving through
+// the ring in chunks of KPC keys; 8 lanes per key.  A slot is released by the LAST of the 8 warps to finish with it (the slots'
+// empty barriers take one arrival, as tcgen05.commit gives them for weight slabs).  Returns the ring counter.
+template <typename KVT>
+__device__ __noinline__ uint32_t cross_attn6(const Pipe P, uint32_t n, int* slot_cnt, const float* q2_s, int k_begin, int k_end, float* wm, float* wl, float* wo) {
+    constexpr int ROWB = 128 * (int)sizeof(KVT), KPC = SLOT / ROWB;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, rg = lane >> 3, l8 = lane & 7;
+    float q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q[i] = q2_s[hdim<KVT>(l8, i)];
+    Softmax8 A;
+    A.init();
+#pragma unroll 1
+    for (int k0 = k_begin; k0 < k_end; k0 += KPC) {
+        const int nk = min(KPC, k_end - k0);
+        const uint32_t slot = n % NSLOT;
+        mbar_wait(P.full + slot, (n / NSLOT) & 1);
+        const uint8_t* blk = P.ring + slot * SLOT;
+#pragma unroll 2
+        for (int kk = warp * 4 + rg; kk < nk; kk += 32) {
+            const int par = (k0 + kk) & 1;
+            const KVT* rowp = reinterpret_cast<const KVT*>(blk + (size_t)kk * ROWB);
+            float kf[8], vf[8];
+            load_row8<KVT>(rowp, l8, par, kf, true);
+            load_row8<KVT>(rowp + 64, l8, par, vf, true);
+            float s = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s = fmaf(q[i], kf[i], s);
+            const unsigned int gm = 0xffu << (lane & 24);
+            s += __shfl_xor_sync(gm, s, 1);
+            s += __shfl_xor_sync(gm, s, 2);
+            s += __shfl_xor_sync(gm, s, 4);
+            A.add(s, vf);
+        }
+        __syncwarp();
+        if (lane == 0 && atomicAdd(slot_cnt + slot, 1) == NCW - 1) {
+            slot_cnt[slot] = 0;
+            mbar_arrive(P.empty + slot);
+        }
+        ++n;
+    }
+    __syncwarp();
+    A.merge_xor(8);
+    A.merge_xor(16);
+    if (rg == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) wo[warp * 64 + hdim<KVT>(l8, i)] = A.o[i];
+        if (l8 == 0) { wm[warp] = A.m; wl[warp] = A.l; }
+    }
+    return n;
+}
 
 // =====================================================================================================================
 template <int D, int HS, int NT8, typename KVT>
@@ -294,59 +528,82 @@ __global__ void __launch_bounds__(NTH6, 1)
 dec6_kernel(const Dec3Args a) {
     using G = Geo<D, HS>;
     constexpr int H = G::H, CS = G::CS, NS = G::NS, SEND = G::SEND, PARAMS = G::PARAMS;
-    extern __shared__ __align__(128) unsigned char smraw[];
+    constexpr int KPC = SLOT / (128 * (int)sizeof(KVT));   // cross keys per ring chunk
+    constexpr int ROWB = 128 * (int)sizeof(KVT);
+    extern __shared__ __align__(1024) unsigned char smraw_[];
+    uint8_t* smraw = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smraw_) + 1023) & ~(uintptr_t)1023);
     cg::cluster_group cl = cg::this_cluster();
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, rg = lane >> 3, l8 = lane & 7;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rank = (int)cl.block_rank(), h = rank % H, hs = rank / H;
     const int cluster_id = blockIdx.x / CS, n_clusters = gridDim.x / CS;
     const int L = a.L, V = a.V, R = a.R, t_max = a.t_max;
 
-    // ---- shared memory carve-up
+    // ---- shared memory carve-up (ring and B operand 1024-byte aligned: swizzle atoms)
     uint8_t* ring_mem = smraw;                                              // [NSLOT][SLOT]
-    float* params = reinterpret_cast<float*>(ring_mem + NSLOT * SLOT);      // [2][PARAMS]
+    uint8_t* bx = ring_mem + NSLOT * SLOT;                                  // [KMAX / 64][16 rows][128 B]  B operand (rows 0, 1 live)
+    float* params = reinterpret_cast<float*>(bx + (G::KMAX / 64) * BX_SLAB);   // [2][PARAMS]
     float* part = params + 2 * PARAMS;                                      // [2][CS][SEND] partial records of the cluster
     float* y_s = part + 2 * CS * SEND;                                      // [2][SEND]     this CTA's outgoing record
     float* x_s = y_s + 2 * SEND;                                            // [D]           residual stream (own copy)
     float* qkv_s = x_s + D;                                                 // [192]         q_h | k_h | v_h of the current position
     float* q2_s = qkv_s + 192;                                              // [64]
-    float* att_s = q2_s + 64;                                               // [64]          un-normalised attention output of the head
-    float* hid_s = att_s + 64;                                              // [NS]
+    float* hid_s = q2_s + 64;                                               // [NS]          MLP hidden slice
     float* wsrc_s = hid_s + NS;                                             // [16]          merge weights of the sources
     float* wm = wsrc_s + 16;                                                // [8]
     float* wl = wm + 8;                                                     // [8]
     float* wo = wl + 8;                                                     // [8][64]
-    float* ML = wo + 512;                                                   // [4]
-    int* ctl = reinterpret_cast<int*>(ML + 4);                              // [4] stop flag, is_last
-    uint64_t* bars = reinterpret_cast<uint64_t*>(ctl + 4);
+    int* ctl = reinterpret_cast<int*>(wo + 512);                            // [4] stop flag, is_last, tmem base
+    int* slot_cnt = ctl + 4;                                                // [NSLOT] warps done with a K/V chunk
+    uint64_t* bars = reinterpret_cast<uint64_t*>(slot_cnt + NSLOT);
     uint64_t* full = bars;                    // [NSLOT]
     uint64_t* empty = full + NSLOT;           // [NSLOT]
     uint64_t* pfull = empty + NSLOT;          // [2] parameter block landed
     uint64_t* pfree = pfull + 2;              // [2] consumers are done with the parameter block
     uint64_t* pbar = pfree + 2;               // [2] partial records of a phase landed
-    uint64_t* lg_bar = pbar + 2;              // [NCW][LG_NBUF] logits stage
+    uint64_t* b_ready = pbar + 2;             // [1]
+    uint64_t* acc_full = b_ready + 1;         // [2]
+    uint64_t* acc_free = acc_full + 2;        // [2]
+    uint64_t* lg_bar = acc_free + 2;          // [NCW][LG_NBUF] logits stage
     // logits-stage scratch aliases the (then dead) parameter / partial buffers
     uint4* pl_hi = reinterpret_cast<uint4*>(params);                        // [NT8][D/32][32] fp16 hi plane of the LayerNorm rows, fragment order
     uint4* pl_lo = pl_hi + NT8 * (D / 32) * 32;
     float* red = reinterpret_cast<float*>(pl_lo + NT8 * (D / 32) * 32);     // [NCW][8 * NT8][4]
 
     if (tid == 0) {
-        for (int i = 0; i < NSLOT; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, NCW); }
-        for (int i = 0; i < 2; ++i) { mbar_init(pfull + i, 1); mbar_init(pfree + i, NCW); mbar_init(pbar + i, 1); }
+        for (int i = 0; i < NSLOT; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); slot_cnt[i] = 0; }
+        for (int i = 0; i < 2; ++i) { mbar_init(pfull + i, 1); mbar_init(pfree + i, NCW); mbar_init(pbar + i, 1); mbar_init(acc_full + i, 1); mbar_init(acc_free + i, 4); }
+        mbar_init(b_ready, 1);
         for (int i = 0; i < NCW * LG_NBUF; ++i) mbar_init(lg_bar + i, 1);
         ctl[0] = 0; ctl[1] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    cl.sync();   // every CTA's mbarriers exist before any peer signals them
+    for (int i = tid; i < (G::KMAX / 64) * BX_SLAB / 16; i += NTH6) reinterpret_cast<uint4*>(bx)[i] = make_uint4(0, 0, 0, 0);   // rows 2..15 stay zero
+    if (warp == W_MMA) {   // TMEM: two 16-column fp32 accumulators
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(ctl + 2)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cl.sync();   // every CTA's mbarriers exist before any peer signals them; TMEM address published
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    Pipe P;
+    P.ring = ring_mem; P.full = full; P.empty = empty; P.b_ready = b_ready; P.acc_full = acc_full; P.acc_free = acc_free;
+    P.tmem = *reinterpret_cast<volatile uint32_t*>(ctl + 2);
 
     const uint8_t* pack = reinterpret_cast<const uint8_t*>(a.d6_pack);
     const float* gparams = a.d6_params;
-    const int KPC = SLOT / (128 * (int)sizeof(KVT));   // cross keys per ring chunk
-    constexpr int ROWB = 128 * (int)sizeof(KVT);
+    constexpr int T_QKV = 2, T_D = (D + 127) / 128, T_CQ = 1, T_W1 = (NS + 127) / 128;   // tiles of 128 rows per segment
+    constexpr int S_D = D / 64, S_NS = NS / 64;                                           // K slabs
 
-    if (warp == NCW) {
-        // ===================================================== PRODUCER: weights, parameters and cross K/V, in consumer order
-        Ring ring{ring_mem, full, empty, 0};
-        uint32_t pl = 0;   // parameter blocks issued
+    if (warp == W_PROD) {
+        // ===================================================== PRODUCER: weight slabs, parameters and cross K/V, in consumer order
+        uint32_t n = 0, pl = 0;
+        auto push = [&](const void* src, uint32_t bytes) {
+            const uint32_t slot = n % NSLOT;
+            if (n >= NSLOT) mbar_wait(empty + slot, ((n / NSLOT) - 1) & 1);
+            mbar_expect_tx(full + slot, bytes);
+            bulk_g2s(ring_mem + slot * SLOT, src, bytes, full + slot);
+            ++n;
+        };
         for (int step = 0; step < a.n_steps; ++step) {
             if (lane == 0) {
                 for (int row = cluster_id; row < R; row += n_clusters) {
@@ -362,20 +619,19 @@ dec6_kernel(const Dec3Args a) {
                             ++pl;
                         }
                         const uint8_t* base = pack + ((size_t)l * CS + rank) * G::PACK;
-                        auto seg = [&](int off, int N, int K) {
-                            const int rpc = rows_per_chunk(K);
-                            for (int r0 = 0; r0 < N; r0 += rpc) ring.push(base + off + (size_t)r0 * K * 2, (uint32_t)(min(rpc, N - r0) * K * 2));
+                        auto seg = [&](int off, int n_chunks) {
+                            for (int i = 0; i < n_chunks; ++i) push(base + off + (size_t)i * SLOT, SLOT);
                         };
-                        if (hs == 0) { seg(G::OFF_QKV, 192, D); seg(G::OFF_O, D, 64); }
-                        seg(G::OFF_CQ, 64, D);
+                        if (hs == 0) { seg(G::OFF_QKV, T_QKV * S_D); seg(G::OFF_O, T_D * 1); }
+                        seg(G::OFF_CQ, T_CQ * S_D);
                         {
                             const KVT* kv = reinterpret_cast<const KVT*>(a.ckv) + (size_t)l * a.Mcap * 2 * D + __ldg(a.win_row_off + w) * (int64_t)(2 * D) +
                                             ((int64_t)h * T + k_begin) * 128;
-                            for (int k0 = k_begin; k0 < k_end; k0 += KPC) ring.push(kv + (int64_t)(k0 - k_begin) * 128, (uint32_t)(min(KPC, k_end - k0) * ROWB));
+                            for (int k0 = k_begin; k0 < k_end; k0 += KPC) push(kv + (int64_t)(k0 - k_begin) * 128, (uint32_t)(min(KPC, k_end - k0) * ROWB));
                         }
-                        seg(G::OFF_CO, D, 64);
-                        seg(G::OFF_W1, NS, D);
-                        seg(G::OFF_W2, D, NS);
+                        seg(G::OFF_CO, T_D * 1);
+                        seg(G::OFF_W1, T_W1 * S_D);
+                        seg(G::OFF_W2, T_D * S_NS);
                     }
                 }
             }
@@ -383,9 +639,34 @@ dec6_kernel(const Dec3Args a) {
             bar_all();   // the ring is lent to the logits stage until the consumers finish the step
             if (*reinterpret_cast<volatile int*>(ctl) != 0) break;
         }
+    } else if (warp == W_MMA) {
+        // ===================================================== MMA warp: one thread issues every tcgen05.mma of the step
+        Counters c{0, 0, 0};
+        const uint32_t bxa = s32(bx);
+        for (int step = 0; step < a.n_steps; ++step) {
+            if (lane == 0) {
+                for (int row = cluster_id; row < R; row += n_clusters) {
+                    const int w = __ldg(a.row_window + row);
+                    const int T = __ldg(a.win_T + w);
+                    const int per = (T + HS - 1) / HS, k_begin = min(T, hs * per), k_end = min(T, k_begin + per);
+                    const uint32_t n_kv = (uint32_t)((k_end - k_begin + KPC - 1) / KPC);
+                    for (int l = 0; l < L; ++l) {
+                        if (hs == 0) { c = gemv_mma6(P, c, T_QKV, S_D, bxa); c = gemv_mma6(P, c, T_D, 1, bxa); }
+                        c = gemv_mma6(P, c, T_CQ, S_D, bxa);
+                        c.n += n_kv;                       // K/V chunks are consumed by the attention warps
+                        c = gemv_mma6(P, c, T_D, 1, bxa);
+                        c = gemv_mma6(P, c, T_W1, S_D, bxa);
+                        c = gemv_mma6(P, c, T_D, S_NS, bxa);
+                    }
+                }
+            }
+            __syncwarp();
+            bar_all();
+            if (*reinterpret_cast<volatile int*>(ctl) != 0) break;
+        }
     } else {
         // ===================================================== CONSUMERS
-        Ring ring{ring_mem, full, empty, 0};
+        Counters c{0, 0, 0};
         uint32_t pl = 0;     // parameter blocks consumed
         uint32_t ph = 0;     // exchange phases completed (buffer = ph & 1)
         unsigned int gen = 0;
@@ -407,233 +688,85 @@ dec6_kernel(const Dec3Args a) {
                 for (int dst = 0; dst < CS; ++dst) bulk_s2peer(part + (b * CS + rank) * SEND, y_s + b * SEND, SEND * 4, pbar + b, (uint32_t)dst);
             }
         };
-        // x += bias + sum over sources of weight * partial (fixed order, identical in every CTA); completes phase `ph`
         auto combine = [&](int mode, const float* bias) {
-            const uint32_t b = ph & 1;
-            if (tid == 0) mbar_expect_tx(pbar + b, CS * SEND * 4);
-            mbar_wait(pbar + b, (ph >> 1) & 1);
-            const float* pr = part + b * CS * SEND;
-            if (tid < CS) {
-                float wgt = 1.0f;
-                if (mode == MODE_ATTN) {   // softmax merge of the key splits of head tid % H (mod.rs:516-527 computed in pieces)
-                    const int hh = tid % H;
-                    float M = -INFINITY;
-#pragma unroll
-                    for (int s = 0; s < HS; ++s)
-                        if (pr[(hh + H * s) * SEND + D + 2] != 0.0f) M = fmaxf(M, pr[(hh + H * s) * SEND + D]);
-                    float den = 0.0f;
-#pragma unroll
-                    for (int s = 0; s < HS; ++s) {
-                        const float* rec = pr + (hh + H * s) * SEND + D;
-                        if (rec[2] != 0.0f && rec[0] > -INFINITY) den += expf(rec[0] - M) * rec[1];
-                    }
-                    const float* me = pr + tid * SEND + D;
-                    wgt = (me[2] != 0.0f && me[0] > -INFINITY) ? __fdiv_rn(expf(me[0] - M), den) : 0.0f;
-                }
-                wsrc_s[tid] = wgt;
-            }
-            bar_consumers();
-            for (int c = tid; c < D; c += 256) {
-                float acc = bias[c];
-#pragma unroll
-                for (int s = 0; s < CS; ++s) acc = fmaf(wsrc_s[s], pr[s * SEND + c], acc);
-                x_s[c] = __fadd_rn(x_s[c], acc);
-            }
+            combine6<D, HS>(part + (ph & 1) * CS * SEND, pbar + (ph & 1), (ph >> 1) & 1, mode, bias, x_s, wsrc_s);
             ++ph;
-            bar_consumers();
         };
 
+#pragma unroll 1
         for (int step = 0; step < a.n_steps; ++step) {
             const int p = a.pos0 + step;
             const bool want_logits = p >= a.logits_from;
+#pragma unroll 1
             for (int row = cluster_id; row < R; row += n_clusters) {
                 // ---- embed (mod.rs:141-146): every CTA of the cluster builds its own copy of x
                 {
                     const int tok = __ldcg(a.tokens + (int64_t)row * t_max + p);
-                    for (int c = tid; c < D; c += 256) x_s[c] = __fadd_rn(__ldg(a.tok_emb + (int64_t)tok * D + c), __ldg(a.pos_emb + (int64_t)p * D + c));
+                    for (int c2 = tid; c2 < D; c2 += 256) x_s[c2] = __fadd_rn(__ldg(a.tok_emb + (int64_t)tok * D + c2), __ldg(a.pos_emb + (int64_t)p * D + c2));
                 }
                 const int w = __ldg(a.row_window + row);
                 const int T = __ldg(a.win_T + w);
                 const int per = (T + HS - 1) / HS, k_begin = min(T, hs * per), k_end = min(T, k_begin + per);
                 bar_consumers();
                 trace();
+#pragma unroll 1
                 for (int l = 0; l < L; ++l) {
                     KVT* kcl = reinterpret_cast<KVT*>(a.kc) + (size_t)l * a.Rmax * t_max * D;
                     KVT* vcl = reinterpret_cast<KVT*>(a.vc) + (size_t)l * a.Rmax * t_max * D;
                     // ================= phase 1: x += MLP of the previous layer; self attention of head h (mod.rs:346)
-                    const float* prm_prev = params + ((pl + 1) & 1) * PARAMS;   // previous layer's block (bias of its MLP2)
                     if (l > 0) {
-                        combine(MODE_SUM, prm_prev + G::P_B2);
+                        combine(MODE_SUM, params + ((pl + 1) & 1) * PARAMS + G::P_B2);   // previous layer's block: bias of its MLP2
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(pfree + ((pl + 1) & 1));       // previous layer's parameters are dead now
+                        if (lane == 0) mbar_arrive(pfree + ((pl + 1) & 1));               // previous layer's parameters are dead now
                     }
+                    trace();   // [t1] records of the previous phase combined
                     mbar_wait(pfull + (pl & 1), (pl >> 1) & 1);
                     const float* prm = params + (pl & 1) * PARAMS;
                     ++pl;
                     float* ys = y_s + (ph & 1) * SEND;
                     if (hs == 0) {
-                        float xr[D / 64][8];
-                        ln_to_regs<D>(x_s, prm + G::P_LN1G, prm + G::P_LN1B, prm[G::P_EPS + 0], a.eps_outside, xr);
-                        gemv_seg<D>(ring, 192, xr, [&](int n, float s) {
-                            float v = __fadd_rn(s, prm[G::P_BQKV + n]);
-                            if (n < 128) v = __fmul_rn(v, scale);                 // q and k carry (d/H)^-0.25 each (mod.rs:500-503)
-                            if (n >= 64) {
-                                const KVT r = (KVT)v;                             // fp16 cache: round-to-nearest where the value enters the cache
-                                (n < 128 ? kcl : vcl)[((int64_t)row * t_max + p) * D + h * 64 + (n & 63)] = r;
-                                v = (float)r;
-                            }
-                            qkv_s[n] = v;
-                        });
-                        bar_consumers();
-                        // causal self attention over positions 0..p: 32 (warp, rg) key slots, 8 lanes per key
-                        {
-                            float q[8];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) q[i] = qkv_s[hdim<KVT>(l8, i)];
-                            Softmax8 A;
-                            A.init();
-                            float kf[4][8], vf[4][8];
-                            const int j0 = warp * 4 + rg;
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {                          // all loads first (t_max <= 128 -> at most 4 keys per slot)
-                                const int j = j0 + 32 * u;
-                                if (j < p) {
-                                    load_row8<KVT>(kcl + ((int64_t)row * t_max + j) * D + h * 64, l8, 0, kf[u], false);
-                                    load_row8<KVT>(vcl + ((int64_t)row * t_max + j) * D + h * 64, l8, 0, vf[u], false);
-                                } else if (j == p) {
-#pragma unroll
-                                    for (int i = 0; i < 8; ++i) { kf[u][i] = qkv_s[64 + hdim<KVT>(l8, i)]; vf[u][i] = qkv_s[128 + hdim<KVT>(l8, i)]; }
-                                } else {
-#pragma unroll
-                                    for (int i = 0; i < 8; ++i) { kf[u][i] = 0.0f; vf[u][i] = 0.0f; }
-                                }
-                            }
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                float s = 0.0f;
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) s = fmaf(q[i], kf[u][i], s);
-                                s = group8_sum(s);
-                                if (j0 + 32 * u <= p) A.add(s, vf[u]);
-                            }
-                            A.merge_xor(8);
-                            A.merge_xor(16);
-                            if (rg == 0) {
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) wo[warp * 64 + hdim<KVT>(l8, i)] = A.o[i];
-                                if (l8 == 0) { wm[warp] = A.m; wl[warp] = A.l; }
-                            }
-                        }
-                        bar_consumers();
-                        if (tid < 64) {
-                            float M = -INFINITY;
-#pragma unroll
-                            for (int w2 = 0; w2 < NCW; ++w2) M = fmaxf(M, wm[w2]);
-                            float Ls = 0.0f, o = 0.0f;
-#pragma unroll
-                            for (int w2 = 0; w2 < NCW; ++w2) {
-                                const float sc = wm[w2] > -INFINITY ? expf(wm[w2] - M) : 0.0f;
-                                Ls += sc * wl[w2];
-                                o += sc * wo[w2 * 64 + tid];
-                            }
-                            att_s[tid] = o;
-                            if (tid == 0) { ys[D] = M; ys[D + 1] = Ls; ys[D + 2] = 1.0f; ys[D + 3] = 0.0f; }
-                        }
-                        bar_consumers();
-                        {
-                            float xo[1][8];
-                            slice_to_regs<64>(att_s, xo);
-                            gemv_seg<64>(ring, D, xo, [&](int n, float s) { ys[n] = s; });
-                        }
+                        ln6<D>(x_s, prm + G::P_LN1G, prm + G::P_LN1B, prm[G::P_EPS + 0], a.eps_outside, bx);
+                        KVT* kd = kcl + ((int64_t)row * t_max + p) * D + h * 64;
+                        KVT* vd = vcl + ((int64_t)row * t_max + p) * D + h * 64;
+                        c = gemv_epi6<KVT>(P, c, 192, S_D, GemvOut<KVT>{EM_QKV, prm + G::P_BQKV, scale, qkv_s, kd, vd});
+                        trace();   // [t2] q | k | v done
+                        self_attn6<KVT>(qkv_s, kcl + (int64_t)row * t_max * D + h * 64, vcl + (int64_t)row * t_max * D + h * 64, D, p, wm, wl, wo);
+                        attn_merge6(wm, wl, wo, bx, ys + D, 1.0f);
+                        trace();   // [t3] self attention done
+                        c = gemv_epi6<KVT>(P, c, D, 1, GemvOut<KVT>{EM_PLAIN, nullptr, 1.0f, ys, nullptr, nullptr});
                     } else {
-                        for (int c = tid; c < SEND; c += 256) ys[c] = 0.0f;    // inactive in this phase: weight 0, zeros
+                        for (int c2 = tid; c2 < SEND; c2 += 256) ys[c2] = 0.0f;    // inactive in this phase: weight 0, zeros
                     }
+                    trace();   // [t4] out-projection slice done
                     send();
-                    trace();
+                    trace();   // [t5] sent
                     // ================= phase 2: x += self-attention output; cross attention of head h over this CTA's keys (mod.rs:347)
                     combine(MODE_ATTN, prm + G::P_BO);
+                    trace();   // [t6] combined
                     ys = y_s + (ph & 1) * SEND;
-                    {
-                        float xr[D / 64][8];
-                        ln_to_regs<D>(x_s, prm + G::P_LN2G, prm + G::P_LN2B, prm[G::P_EPS + 1], a.eps_outside, xr);
-                        gemv_seg<D>(ring, 64, xr, [&](int n, float s) { q2_s[n] = __fmul_rn(__fadd_rn(s, prm[G::P_BCQ + n]), scale); });
-                    }
-                    bar_consumers();
-                    {
-                        float q[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) q[i] = q2_s[hdim<KVT>(l8, i)];
-                        Softmax8 A;
-                        A.init();
-                        for (int k0 = k_begin; k0 < k_end; k0 += KPC) {
-                            const int nk = min(KPC, k_end - k0);
-                            const uint8_t* blk = ring.wait();
-                            for (int kk = warp * 4 + rg; kk < nk; kk += 32) {
-                                const int par = (k0 + kk) & 1;
-                                const KVT* rowp = reinterpret_cast<const KVT*>(blk + (size_t)kk * ROWB);
-                                float kf[8], vf[8];
-                                load_row8<KVT>(rowp, l8, par, kf, true);
-                                load_row8<KVT>(rowp + 64, l8, par, vf, true);
-                                float s = 0.0f;
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) s = fmaf(q[i], kf[i], s);
-                                const unsigned int gm = 0xffu << (lane & 24);
-                                s += __shfl_xor_sync(gm, s, 1);
-                                s += __shfl_xor_sync(gm, s, 2);
-                                s += __shfl_xor_sync(gm, s, 4);
-                                A.add(s, vf);
-                            }
-                            ring.release();
-                        }
-                        __syncwarp();
-                        A.merge_xor(8);
-                        A.merge_xor(16);
-                        if (rg == 0) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) wo[warp * 64 + hdim<KVT>(l8, i)] = A.o[i];
-                            if (l8 == 0) { wm[warp] = A.m; wl[warp] = A.l; }
-                        }
-                    }
-                    bar_consumers();
-                    if (tid < 64) {
-                        float M = -INFINITY;
-#pragma unroll
-                        for (int w2 = 0; w2 < NCW; ++w2) M = fmaxf(M, wm[w2]);
-                        float Ls = 0.0f, o = 0.0f;
-#pragma unroll
-                        for (int w2 = 0; w2 < NCW; ++w2) {
-                            const float sc = wm[w2] > -INFINITY ? expf(wm[w2] - M) : 0.0f;
-                            Ls += sc * wl[w2];
-                            o += sc * wo[w2 * 64 + tid];
-                        }
-                        att_s[tid] = o;
-                        if (tid == 0) { ys[D] = M; ys[D + 1] = Ls; ys[D + 2] = (k_end > k_begin) ? 1.0f : 0.0f; ys[D + 3] = 0.0f; }
-                    }
-                    bar_consumers();
-                    {
-                        float xo[1][8];
-                        slice_to_regs<64>(att_s, xo);
-                        gemv_seg<64>(ring, D, xo, [&](int n, float s) { ys[n] = s; });
-                    }
+                    ln6<D>(x_s, prm + G::P_LN2G, prm + G::P_LN2B, prm[G::P_EPS + 1], a.eps_outside, bx);
+                    c = gemv_epi6<KVT>(P, c, 64, S_D, GemvOut<KVT>{EM_CQ, prm + G::P_BCQ, scale, q2_s, nullptr, nullptr});
+                    trace();   // [t7] cross query done
+                    c.n = cross_attn6<KVT>(P, c.n, slot_cnt, q2_s, k_begin, k_end, wm, wl, wo);
+                    attn_merge6(wm, wl, wo, bx, ys + D, (k_end > k_begin) ? 1.0f : 0.0f);
+                    trace();   // [t8] cross attention done
+                    c = gemv_epi6<KVT>(P, c, D, 1, GemvOut<KVT>{EM_PLAIN, nullptr, 1.0f, ys, nullptr, nullptr});
+                    trace();   // [t9]
                     send();
-                    trace();
+                    trace();   // [t10]
                     // ================= phase 3: x += cross-attention output; MLP slice (mod.rs:348, :376-382)
                     combine(MODE_ATTN, prm + G::P_BCO);
+                    trace();   // [t11]
                     ys = y_s + (ph & 1) * SEND;
-                    {
-                        float xr[D / 64][8];
-                        ln_to_regs<D>(x_s, prm + G::P_LN3G, prm + G::P_LN3B, prm[G::P_EPS + 2], a.eps_outside, xr);
-                        gemv_seg<D>(ring, NS, xr, [&](int n, float s) { hid_s[n] = gelu_erf(__fadd_rn(s, prm[G::P_B1 + n])); });
-                    }
-                    bar_consumers();
-                    {
-                        float xh[NS / 64][8];
-                        slice_to_regs<NS>(hid_s, xh);
-                        gemv_seg<NS>(ring, D, xh, [&](int n, float s) { ys[n] = s; });
-                        if (tid == 0) { ys[D] = 0.0f; ys[D + 1] = 1.0f; ys[D + 2] = 1.0f; ys[D + 3] = 0.0f; }
-                    }
+                    ln6<D>(x_s, prm + G::P_LN3G, prm + G::P_LN3B, prm[G::P_EPS + 2], a.eps_outside, bx);
+                    c = gemv_epi6<KVT>(P, c, NS, S_D, GemvOut<KVT>{EM_HID, prm + G::P_B1, 1.0f, hid_s, nullptr, nullptr});
+                    for (int c2 = tid; c2 < NS; c2 += 256) bx_store(bx, c2, hid_s[c2]);   // every MMA of the W1 product has completed: the B operand may change
+                    trace();   // [t12] hidden slice done
+                    c = gemv_epi6<KVT>(P, c, D, S_NS, GemvOut<KVT>{EM_PLAIN, nullptr, 1.0f, ys, nullptr, nullptr});
+                    if (tid == 0) { ys[D] = 0.0f; ys[D + 1] = 1.0f; ys[D + 2] = 1.0f; ys[D + 3] = 0.0f; }
+                    trace();   // [t13]
                     send();
-                    trace();
+                    trace();   // [t14]
                 }
                 // ---- x += MLP of the last layer; rank 0 publishes the row for the vocabulary projection
                 combine(MODE_SUM, params + ((pl + 1) & 1) * PARAMS + G::P_B2);
@@ -838,19 +971,32 @@ dec6_kernel(const Dec3Args a) {
                 if (ctl[1]) {
                     __threadfence();
                     for (int r = warp; r < R; r += NCW) {
+                        // <= 160 co-resident CTAs: at most 5 records per lane, every load issued before any use (one L2 round trip)
                         const int NP = gridDim.x;
+                        float rm[5], rs[5], rv[5];
+                        int ri[5];
+#pragma unroll
+                        for (int k = 0; k < 5; ++k) {
+                            const int c = min(lane + 32 * k, NP - 1);
+                            rm[k] = __ldcg(a.lg_m + (int64_t)c * R + r);
+                            rs[k] = __ldcg(a.lg_s + (int64_t)c * R + r);
+                            rv[k] = __ldcg(a.lg_v + (int64_t)c * R + r);
+                            ri[k] = __ldcg(a.lg_i + (int64_t)c * R + r);
+                        }
                         float mx = -INFINITY;
-                        for (int c = lane; c < NP; c += 32) mx = fmaxf(mx, __ldcg(a.lg_m + (int64_t)c * R + r));
+#pragma unroll
+                        for (int k = 0; k < 5; ++k)
+                            if (lane + 32 * k < NP) mx = fmaxf(mx, rm[k]);
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
                         float se = 0.0f, bvv = -INFINITY;
                         int bii = INT_MAX;
-                        for (int c = lane; c < NP; c += 32) {
-                            const float m = __ldcg(a.lg_m + (int64_t)c * R + r);
-                            if (m > -INFINITY) se += __ldcg(a.lg_s + (int64_t)c * R + r) * expf(m - mx);
-                            const float cv = __ldcg(a.lg_v + (int64_t)c * R + r);
-                            const int ci = __ldcg(a.lg_i + (int64_t)c * R + r);
-                            if (ci != INT_MAX && (cv > bvv || (cv == bvv && ci < bii))) { bvv = cv; bii = ci; }
+#pragma unroll
+                        for (int k = 0; k < 5; ++k) {
+                            if (lane + 32 * k < NP) {
+                                if (rm[k] > -INFINITY) se += rs[k] * expf(rm[k] - mx);
+                                if (ri[k] != INT_MAX && (rv[k] > bvv || (rv[k] == bvv && ri[k] < bii))) { bvv = rv[k]; bii = ri[k]; }
+                            }
                         }
                         se = warp_sum(se);
                         const float lse = logf(se);
@@ -903,14 +1049,20 @@ dec6_kernel(const Dec3Args a) {
             }
         }
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     cl.sync();   // no CTA leaves while a peer may still address its shared memory
+    if (warp == W_MMA) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(P.tmem), "n"(TMEM_COLS) : "memory");
+    }
 }
 
 template <int D, int HS, int NT8>
 constexpr size_t dec6_smem() {
     using G = Geo<D, HS>;
-    return (size_t)NSLOT * SLOT + sizeof(float) * ((size_t)2 * G::PARAMS + 2 * G::CS * G::SEND + 2 * G::SEND + D + 192 + 64 + 64 + G::NS + 16 + 8 + 8 + 512 + 4 + 4) +
-           8 * (size_t)(2 * NSLOT + 6 + NCW * LG_NBUF) + 128;
+    return 1024 + (size_t)NSLOT * SLOT + (size_t)(G::KMAX / 64) * BX_SLAB +
+           sizeof(float) * ((size_t)2 * G::PARAMS + 2 * G::CS * G::SEND + 2 * G::SEND + D + 192 + 64 + G::NS + 16 + 8 + 8 + 512 + 4 + NSLOT) +
+           8 * (size_t)(2 * NSLOT + 6 + 5 + NCW * LG_NBUF) + 64;
 }
 
 struct LaunchState {

@@ -12,7 +12,7 @@ constexpr int LN_MAX_PER_LANE = 40;   // d <= 1280
 // One warp per row.  burn 0.9 LayerNorm: mean, biased variance of (x-mean), then
 // (x-mean)/(sqrt(var)+eps) [eps_outside] or (x-mean)/sqrt(var+eps); * gamma + beta as separate ops.
 __global__ void __launch_bounds__(256)
-layernorm_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ y_lo, const float* __restrict__ g,
+layernorm_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ g,
                  const float* __restrict__ b, float eps, int eps_outside, int rows, int d) {
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -46,15 +46,52 @@ layernorm_kernel(const float* __restrict__ x, float* __restrict__ y, float* __re
     for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
         const int c = i * 32 + lane;
         if (c < d) {
+            yr[c] = __fadd_rn(__fmul_rn(__fdiv_rn(v[i], den), g[c]), b[c]);
+        }
+    }
+}
+
+// Same LayerNorm, output as fp16 hi / lo planes (x = hi + lo / 2048, gemm_f16.cu) for the tensor-core GEMM that consumes the row;
+// y (fp32 rows) is written as well when non-null (ln_post: the encoder output returned through the ABI).
+__global__ void __launch_bounds__(256)
+layernorm_f16_kernel(const float* __restrict__ x, float* __restrict__ y, __half* __restrict__ y_hi, __half* __restrict__ y_lo,
+                     const float* __restrict__ g, const float* __restrict__ b, float eps, int eps_outside, int rows, int d) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const float* xr = x + (int64_t)row * d;
+    float v[LN_MAX_PER_LANE];
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+        const int c = i * 32 + lane;
+        v[i] = c < d ? xr[c] : 0.0f;
+        s += v[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = __fdiv_rn(s, (float)d);
+    float q = 0.0f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+        const int c = i * 32 + lane;
+        const float dv = __fsub_rn(v[i], mean);
+        v[i] = dv;
+        if (c < d) q = __fadd_rn(q, __fmul_rn(dv, dv));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float var = __fdiv_rn(q, (float)d);
+    const float den = eps_outside ? __fadd_rn(__fsqrt_rn(var), eps) : __fsqrt_rn(__fadd_rn(var, eps));
+#pragma unroll
+    for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+        const int c = i * 32 + lane;
+        if (c < d) {
             const float o = __fadd_rn(__fmul_rn(__fdiv_rn(v[i], den), g[c]), b[c]);
-            if (y_lo) {   // TF32 hi / lo planes for the tensor-core GEMM that consumes this row
-                uint32_t t;
-                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(o));
-                yr[c] = __uint_as_float(t);
-                y_lo[(int64_t)row * d + c] = __fsub_rn(o, __uint_as_float(t));
-            } else {
-                yr[c] = o;
-            }
+            if (y) y[(int64_t)row * d + c] = o;
+            const __half h = __float2half_rn(o);
+            y_hi[(int64_t)row * d + c] = h;
+            y_lo[(int64_t)row * d + c] = __float2half_rn((o - __half2float(h)) * 2048.0f);
         }
     }
 }
@@ -65,8 +102,7 @@ constexpr int ATT_THREADS = 256;
 constexpr size_t ATT_SMEM = (size_t)4 * 64 * AST * sizeof(float);
 
 __global__ void __launch_bounds__(ATT_THREADS)
-enc_attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, float* __restrict__ out_lo,
-                     const AttnWindow* __restrict__ wins, int d) {
+enc_attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, const AttnWindow* __restrict__ wins, int d) {
     extern __shared__ __align__(16) float sm[];
     float* Qt = sm;                  // [c][q]
     float* Kt = sm + 64 * AST;       // [c][k]
@@ -190,41 +226,33 @@ enc_attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, flo
         const float inv = lrow[i];
         float r[4] = {__fdiv_rn(o[i][0], inv), __fdiv_rn(o[i][1], inv), __fdiv_rn(o[i][2], inv), __fdiv_rn(o[i][3], inv)};
         const int64_t oo = (win.row_off + q) * (int64_t)d + h * DH + tx * 4;
-        if (out_lo) {
-            float l[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                uint32_t t;
-                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(r[j]));
-                l[j] = __fsub_rn(r[j], __uint_as_float(t));
-                r[j] = __uint_as_float(t);
-            }
-            *reinterpret_cast<float4*>(out_lo + oo) = make_float4(l[0], l[1], l[2], l[3]);
-        }
         *reinterpret_cast<float4*>(out + oo) = make_float4(r[0], r[1], r[2], r[3]);
     }
 }
 
 }  // namespace
 
-void launch_layernorm(const float* x, float* y, float* y_lo, const LayerNormW& ln, int rows, int d, int eps_outside,
-                      cudaStream_t st) {
+void launch_layernorm(const float* x, float* y, const LayerNormW& ln, int rows, int d, int eps_outside, cudaStream_t st) {
     WB_REQUIRE(d <= 32 * LN_MAX_PER_LANE, "layernorm: d too large");
     if (rows <= 0) return;
-    layernorm_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, y, y_lo, ln.g, ln.b, ln.eps, eps_outside, rows, d);
+    layernorm_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, y, ln.g, ln.b, ln.eps, eps_outside, rows, d);
     WB_LAUNCH_CHECK();
 }
 
-void launch_encoder_attention(const float* qkv, float* out, float* out_lo, const AttnWindow* win_dev, int n_windows, int max_T,
-                              int d, int n_head, cudaStream_t st) {
+void launch_layernorm_f16(const float* x, float* y, __half* y_hi, __half* y_lo, const LayerNormW& ln, int rows, int d, int eps_outside,
+                          cudaStream_t st) {
+    WB_REQUIRE(d <= 32 * LN_MAX_PER_LANE, "layernorm: d too large");
+    if (rows <= 0) return;
+    layernorm_f16_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, y, y_hi, y_lo, ln.g, ln.b, ln.eps, eps_outside, rows, d);
+    WB_LAUNCH_CHECK();
+}
+
+void launch_encoder_attention(const float* qkv, float* out, const AttnWindow* win_dev, int n_windows, int max_T, int d, int n_head,
+                              cudaStream_t st) {
     WB_REQUIRE(d == n_head * DH, "attention: head dim must be 64");
-    static bool attr_set = false;
-    if (!attr_set) {
-        WB_CUDA(cudaFuncSetAttribute(enc_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
-        attr_set = true;
-    }
+    WB_CUDA(cudaFuncSetAttribute(enc_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));   // per device, cheap: the fp32 path is the fallback
     dim3 grid((max_T + AQ - 1) / AQ, n_head, n_windows);
-    enc_attention_kernel<<<grid, ATT_THREADS, ATT_SMEM, st>>>(qkv, out, out_lo, win_dev, d);
+    enc_attention_kernel<<<grid, ATT_THREADS, ATT_SMEM, st>>>(qkv, out, win_dev, d);
     WB_LAUNCH_CHECK();
 }
 

@@ -178,7 +178,7 @@ void model_finalize(Model& m) {
                 for (int kk = 0; kk < 3; ++kk)
                     s.w[(size_t)o * 3 * c_in + (size_t)kk * c_in + c] = w.second[((size_t)o * c_in + c) * 3 + kk];
         s.b = b.second;
-        return upload_linear(m, s, true, false);
+        return upload_linear(m, s, !exact, exact);
     };
     m.conv1 = conv("encoder/conv1", D.n_mels);
     m.conv2 = conv("encoder/conv2", d);
@@ -193,14 +193,14 @@ void model_finalize(Model& m) {
         add_linear(m, qkv, p + "/attn/query", d, d, true);
         add_linear(m, qkv, p + "/attn/key", d, d, false);
         add_linear(m, qkv, p + "/attn/value", d, d, true);
-        B.qkv = upload_linear(m, qkv, true, false);
+        B.qkv = upload_linear(m, qkv, !exact, exact);   // fp16-exact weights: fp16 storage feeds the tensor-core GEMM (gemm_f16.cu), else fp32 + SIMT
         LinSpec o, m1, m2;
         add_linear(m, o, p + "/attn/out", d, d, true);
         add_linear(m, m1, p + "/mlp/mlp1", d, 4 * d, true);
         add_linear(m, m2, p + "/mlp/mlp2", 4 * d, d, true);
-        B.out = upload_linear(m, o, true, false);
-        B.mlp1 = upload_linear(m, m1, true, false);
-        B.mlp2 = upload_linear(m, m2, true, false);
+        B.out = upload_linear(m, o, !exact, exact);
+        B.mlp1 = upload_linear(m, m1, !exact, exact);
+        B.mlp2 = upload_linear(m, m2, !exact, exact);
     }
     m.ln_post = upload_ln(m, "encoder/ln_post", d);
 
@@ -242,7 +242,7 @@ void model_finalize(Model& m) {
         B.qkv = upload_linear(m, qkv, h32, h16);
         B.out = upload_linear(m, o, h32, h16);
         B.cq = upload_linear(m, cq, h32, h16);
-        B.ckv = upload_linear(m, ckv, true, false);   // applied by the encoder-side GEMM
+        B.ckv = upload_linear(m, ckv, h32, h16);      // applied by the encoder-side GEMM
         B.cout = upload_linear(m, co, h32, h16);
         B.mlp1 = upload_linear(m, m1, h32, h16);
         B.mlp2 = upload_linear(m, m2, h32, h16);

@@ -29,10 +29,8 @@ Session::Session(Model* model, int64_t max_w, int64_t max_b, int64_t max_text_le
     Tcap = (D.n_audio_ctx - 1) / 2 + 1;
     Mcap = (int64_t)max_windows * Tcap;
     const int d = D.n_audio_state, H = D.n_text_head, L = D.n_text_layer, V = D.n_vocab;
-    n_splits = std::max(1, std::min(16, (Tcap + 127) / 128));
-    while ((Tcap + n_splits - 1) / n_splits > dec_attn_max_keys_per_split()) ++n_splits;
-    WB_REQUIRE(t_max <= dec_attn_max_keys_per_split(), "session: max_text_len too large for the attention kernel");
-    kmax = std::max(8, max_beams);
+    WB_REQUIRE(max_beams <= DEC_KC - 1, "session: max_beams must be <= 7 (candidates kept per record by the persistent decoders)");
+    kmax = DEC_KC;
 
     WB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     for (auto& e : ev) WB_CUDA(cudaEventCreate(&e));
@@ -40,18 +38,21 @@ Session::Session(Model* model, int64_t max_w, int64_t max_b, int64_t max_text_le
     d_win_row_off.alloc(max_windows); d_win_T.alloc(max_windows);
     max_slots.alloc(max_windows);
     mel_rows.alloc((size_t)max_windows * TmS * N_MELS);
-    h1.alloc((size_t)max_windows * TmS * d);
-    x.alloc(Mcap * d); xn.alloc(Mcap * d); att.alloc(Mcap * d); qkv.alloc(Mcap * 3 * d); hid.alloc(Mcap * 4 * d);
+    x.alloc(Mcap * d);
     xa.alloc(Mcap * d);
     if (kv == WB_KV_F16) ckv16.alloc((size_t)L * Mcap * 2 * d); else ckv.alloc((size_t)L * Mcap * 2 * d);
-    {
-        const char* e = getenv("WB200_GEMM");
-        use_tc = m->fp16_exact && !(e && std::strcmp(e, "simt") == 0);
-        if (use_tc) {
-            lo_a.alloc(Mcap * d); lo_b.alloc(Mcap * d); lo_b4.alloc(Mcap * 4 * d); xa_hi.alloc(Mcap * d);
-            mel_hi.alloc((size_t)max_windows * TmS * N_MELS); mel_lo.alloc((size_t)max_windows * TmS * N_MELS);
-            h1_lo.alloc((size_t)max_windows * TmS * d);
-        }
+    use_tc = m->fp16_exact;   // fp16-exact weights (released checkpoints): tensor-core encoder on fp16 hi/lo planes; else fp32 CUDA cores
+    if (use_tc) {
+        const size_t nm = (size_t)max_windows * TmS * N_MELS, nh = (size_t)max_windows * TmS * d;
+        mel_h.alloc(nm); mel_l.alloc(nm); h1_h.alloc(nh); h1_l.alloc(nh);
+        xn_h.alloc(Mcap * d); xn_l.alloc(Mcap * d); qkv_h.alloc(Mcap * 3 * d); qkv_l.alloc(Mcap * 3 * d);
+        att_h.alloc(Mcap * d); att_l.alloc(Mcap * d); hid_h.alloc(Mcap * 4 * d); hid_l.alloc(Mcap * 4 * d);
+        xa_h.alloc(Mcap * d); xa_l.alloc(Mcap * d);
+        enc_plans.resize((size_t)2 + 4 * D.n_audio_layer + L);
+        for (auto& pl : enc_plans) pl.reset(new GemmF16Plan());
+    } else {
+        h1.alloc((size_t)max_windows * TmS * d);
+        xn.alloc(Mcap * d); att.alloc(Mcap * d); qkv.alloc(Mcap * 3 * d); hid.alloc(Mcap * 4 * d);
     }
     if (kv == WB_KV_F16) { kc16.alloc((size_t)L * Rmax * t_max * d); vc16.alloc((size_t)L * Rmax * t_max * d); }
     else { kc.alloc((size_t)L * Rmax * t_max * d); vc.alloc((size_t)L * Rmax * t_max * d); }
@@ -61,21 +62,16 @@ Session::Session(Model* model, int64_t max_w, int64_t max_b, int64_t max_text_le
     WB_CUDA(cudaMemsetAsync(hid_pl.p, 0, 8 * dec5_plane_uint4(d) * sizeof(uint4), st));
     dq.alloc((size_t)Rmax * d); dhid.alloc((size_t)Rmax * 4 * d);
     logits.alloc((size_t)Rmax * V);
-    part_o.alloc((size_t)Rmax * H * n_splits * 64); part_m.alloc((size_t)Rmax * H * n_splits);
-    part_l.alloc((size_t)Rmax * H * n_splits);
     tokens.alloc((size_t)Rmax * t_max); lengths.alloc(Rmax); cur_tok.alloc(Rmax); finished.alloc(Rmax);
     row_window.alloc(Rmax); anc0.alloc((size_t)Rmax * t_max); anc1.alloc((size_t)Rmax * t_max); parent.alloc(Rmax);
     pos.alloc(1); n_unfinished.alloc(1);
     topk_id.alloc((size_t)Rmax * kmax); topk_lp.alloc((size_t)Rmax * kmax);
     is_special.alloc(V);
     {
-        const char* e = getenv("WB200_DECODER");
-        if (e && e[0] == '1') dec_version = 1;
-        if (e && e[0] == '2') dec_version = 2;
+        const char* e = getenv("WB200_DECODER");   // "3": force the grid-barrier FMA fallback (decoder3.cu) for A/B runs
         if (e && e[0] == '3') dec_version = 3;
-        if (kv == WB_KV_F16 && dec_version < 3) dec_version = 3;   // the fp16 cache exists in the persistent decoders only
-        ckv_hm = dec_version >= 3;
-        if (ckv_hm) ckv_tmp.alloc(Mcap * 2 * d);
+        ckv_hm = true;                             // cross K/V head-major (encoder.cu ckv_relayout_kernel): what the persistent decoders stream
+        ckv_tmp.alloc(Mcap * 2 * d);
         cudaDeviceProp prop;
         WB_CUDA(cudaGetDeviceProperties(&prop, m->device));
         n_sm = prop.multiProcessorCount;
@@ -132,12 +128,9 @@ Session::Session(Model* model, int64_t max_w, int64_t max_b, int64_t max_text_le
                 WB_CUDA(cudaMemcpy(d5_desc.p, ds.data(), ds.size() * sizeof(Dec5Desc), cudaMemcpyHostToDevice));
             }
         }
-        const size_t n_part = (size_t)std::max(H * n_splits, 4 * d / 32);
-        ypart.alloc(n_part * Rmax * d);
+        ypart.alloc((size_t)4 * Rmax * d);   // decoder5.cu: MLP2 K-slab partial sums
         lg_m.alloc((size_t)n_logit_ctas * Rmax); lg_s.alloc((size_t)n_logit_ctas * Rmax);
-        lg_v.alloc((size_t)n_logit_ctas * Rmax * DEC2_KC); lg_i.alloc((size_t)n_logit_ctas * Rmax * DEC2_KC);
-        tickets.alloc(8);
-        WB_CUDA(cudaMemsetAsync(tickets.p, 0, 8 * sizeof(unsigned int), st));
+        lg_v.alloc((size_t)n_logit_ctas * Rmax * DEC_KC); lg_i.alloc((size_t)n_logit_ctas * Rmax * DEC_KC);
     }
     WB_CUDA(cudaMallocHost((void**)&h_int, sizeof(int) * (4 * (size_t)Rmax + 16 + (size_t)Rmax * kmax)));
     WB_CUDA(cudaMallocHost((void**)&h_float, sizeof(float) * (size_t)Rmax * kmax));
@@ -256,116 +249,135 @@ void Session::load_encoder_output_host(const float* xa_host, int64_t n, int64_t 
     set_geometry(*this, Tm);
     const int d = m->dims.n_audio_state;
     WB_CUDA(cudaMemcpyAsync(xa.p, xa_host, (size_t)n * T * d * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (use_tc) launch_split_f16(xa.p, xa_h.p, xa_l.p, (int64_t)n * T * d, st);
     run_cross_kv();
     encoded = true;
 }
 
 // ---- encoder ------------------------------------------------------------------------------------
-// Plain (ungrouped) GEMM on the tensor cores when the weights are TF32-exact.  p.A must already be the
-// TF32 hi plane and a_lo the lo plane (written by the producing kernel); fp32 CUDA-core GEMM otherwise.
-void Session::gemm(const GemmParams& p, float* a_mut, float* lo_buf) {
-    (void)a_mut;
-    if (use_tc && p.groups == nullptr && p.lda == p.K && gemm_tc_supported(p)) launch_gemm_tc(p, lo_buf, 0, p.max_rows, st);
-    else launch_gemm(p, st);
-}
-
 void Session::run_encoder() {
-    const wb_dims& D = m->dims;
-    const int d = D.n_audio_state;
-    const int M = (int)M_tot;
-    const float qk_scale = (float)std::pow((double)d / (double)D.n_audio_head, -0.25);   // mod.rs:503
-    const bool tc = use_tc;
-    // lo planes (tensor-core path): lo_a = [M][4d] scratch shared by xn / att / hid; conv inputs have their own
-    float* lo = tc ? lo_a.p : nullptr;
-    // halo rows of the conv1 output must read as zero padding
-    WB_CUDA(cudaMemsetAsync(h1.p, 0, (size_t)n_windows * TmS * d * sizeof(float), st));
-    GemmParams p;
-    // conv1 + GELU (mod.rs:243): K = 3*80 over three consecutive token-major mel rows; a conv output row is a
-    // dot product with ONE contiguous 240-vector, so the conv is a GEMM whose A rows overlap (lda = 80 < K)
-    bool conv_tc = tc && conv_tc_ok;
-    if (conv_tc) {
-        try {
-            launch_split_tf32(mel_rows.p, mel_hi.p, mel_lo.p, (int64_t)n_windows * TmS * N_MELS, st);
-            WB_CUDA(cudaMemsetAsync(h1_lo.p, 0, (size_t)n_windows * TmS * d * sizeof(float), st));
-            p = GemmParams{};
-            p.A = mel_hi.p; p.lda = N_MELS; p.B = m->conv1.w32; p.C = h1.p; p.C_lo = h1_lo.p; p.ldc = d; p.N = d; p.K = 3 * N_MELS;
-            p.bias = m->conv1.b; p.act = ACT_GELU; p.groups = d_g1.p; p.n_groups = n_windows; p.max_rows = max_Tm;
-            launch_gemm_tc(p, mel_lo.p, (int64_t)TmS * N_MELS, TmS - 2, st);
-            p = GemmParams{};
-            p.A = h1.p; p.lda = 2 * d; p.B = m->conv2.w32; p.C = x.p; p.ldc = d; p.N = d; p.K = 3 * d;
-            p.bias = m->conv2.b; p.act = ACT_GELU; p.pos = m->enc_pos; p.groups = d_g2.p; p.n_groups = n_windows;
-            p.max_rows = max_T;
-            launch_gemm_tc(p, h1_lo.p, (int64_t)TmS * d, Tcap, st);
-        } catch (const Error& e) {
-            if (e.code != WB_ERR_UNSUPPORTED) throw;
-            conv_tc_ok = false;   // the driver refused the overlapping-row tensor map: CUDA-core path from now on
-            conv_tc = false;
-        }
-    }
-    if (!conv_tc) {
-        p = GemmParams{};
-        p.A = mel_rows.p; p.lda = N_MELS; p.B = m->conv1.w32; p.C = h1.p; p.ldc = d; p.N = d; p.K = 3 * N_MELS;
-        p.bias = m->conv1.b; p.act = ACT_GELU; p.groups = d_g1.p; p.n_groups = n_windows; p.max_rows = max_Tm;
-        launch_gemm(p, st);
-        // conv2 (stride 2) + GELU + transpose + positional embedding (mod.rs:244-252)
-        p = GemmParams{};
-        p.A = h1.p; p.lda = 2 * d; p.B = m->conv2.w32; p.C = x.p; p.ldc = d; p.N = d; p.K = 3 * d;
-        p.bias = m->conv2.b; p.act = ACT_GELU; p.pos = m->enc_pos; p.groups = d_g2.p; p.n_groups = n_windows;
-        p.max_rows = max_T;
-        launch_gemm(p, st);
-    }
-    for (int l = 0; l < D.n_audio_layer; ++l) {
-        const EncBlockW& B = m->enc[(size_t)l];
-        // x = x + attn(attn_ln(x))   (mod.rs:300); LayerNorm writes the TF32 hi/lo planes the GEMM consumes
-        launch_layernorm(x.p, xn.p, lo, B.attn_ln, M, d, m->ln_eps_outside, st);
-        p = GemmParams{};
-        p.A = xn.p; p.lda = d; p.B = B.qkv.w32; p.C = qkv.p; p.ldc = 3 * d; p.N = 3 * d; p.K = d;
-        p.bias = B.qkv.b; p.scale = qk_scale; p.scale_cols = 2 * d; p.max_rows = M;
-        gemm(p, xn.p, lo);
-        launch_encoder_attention(qkv.p, att.p, lo, d_awin.p, n_windows, max_T, d, D.n_audio_head, st);
-        p = GemmParams{};
-        p.A = att.p; p.lda = d; p.B = B.out.w32; p.C = x.p; p.ldc = d; p.N = d; p.K = d;
-        p.bias = B.out.b; p.residual = x.p; p.max_rows = M;
-        gemm(p, att.p, lo);
-        // x = x + mlp(mlp_ln(x))     (mod.rs:301); the MLP1 epilogue (bias + GELU) emits hid as hi/lo planes
-        launch_layernorm(x.p, xn.p, lo, B.mlp_ln, M, d, m->ln_eps_outside, st);
-        p = GemmParams{};
-        p.A = xn.p; p.lda = d; p.B = B.mlp1.w32; p.C = hid.p; p.ldc = 4 * d; p.N = 4 * d; p.K = d;
-        p.bias = B.mlp1.b; p.act = ACT_GELU; p.max_rows = M;
-        const bool mlp_tc = tc && gemm_tc_supported(p);
-        if (mlp_tc) p.C_lo = lo_b4.p;
-        gemm(p, xn.p, lo);
-        p = GemmParams{};
-        p.A = hid.p; p.lda = 4 * d; p.B = B.mlp2.w32; p.C = x.p; p.ldc = d; p.N = d; p.K = 4 * d;
-        p.bias = B.mlp2.b; p.residual = x.p; p.max_rows = M;
-        if (mlp_tc) gemm(p, hid.p, lo_b4.p);
-        else launch_gemm(p, st);
-    }
-    launch_layernorm(x.p, xa.p, nullptr, m->ln_post, M, d, m->ln_eps_outside, st);   // mod.rs:259
+    if (use_tc) run_encoder_f16();
+    else run_encoder_f32();
     run_cross_kv();
     encoded = true;
 }
 
+// Tensor-core encoder (fp16-exact weights): conv stems, attention and MLP GEMMs are tcgen05 GEMMs over fp16 hi/lo planes
+// (gemm_f16.cu), attention is enc_attn_tc.cu; only the residual stream x and the encoder output stay fp32 rows.
+void Session::run_encoder_f16() {
+    const wb_dims& D = m->dims;
+    const int d = D.n_audio_state;
+    const int M = (int)M_tot;
+    const float qk_scale = (float)std::pow((double)d / (double)D.n_audio_head, -0.25);   // mod.rs:503
+    auto run = [&](size_t site, const GemmF16Params& p, int64_t gstride, int rows_per_group) {
+        GemmF16Plan& pl = *enc_plans[site];
+        if (!pl.matches(p.max_rows, p.groups ? p.n_groups : 1)) pl.build(p, gstride, rows_per_group);   // tensor maps once per geometry
+        pl.launch(st);
+    };
+    // halo rows of the conv1 output must read as zero padding
+    WB_CUDA(cudaMemsetAsync(h1_h.p, 0, (size_t)n_windows * TmS * d * sizeof(__half), st));
+    WB_CUDA(cudaMemsetAsync(h1_l.p, 0, (size_t)n_windows * TmS * d * sizeof(__half), st));
+    launch_split_f16(mel_rows.p, mel_h.p, mel_l.p, (int64_t)n_windows * TmS * N_MELS, st);
+    GemmF16Params p;
+    // conv1 + GELU (mod.rs:243): K = 3*80 over three consecutive token-major mel rows; a conv output row is a dot product with
+    // ONE contiguous 240-vector, so the conv is a GEMM whose A rows overlap (lda = 80 < K)
+    p.A_hi = mel_h.p; p.A_lo = mel_l.p; p.lda = N_MELS; p.B = m->conv1.w16; p.P_hi = h1_h.p; p.P_lo = h1_l.p; p.ldc = d; p.N = d; p.K = 3 * N_MELS;
+    p.bias = m->conv1.b; p.act = ACT_GELU; p.groups = d_g1.p; p.n_groups = n_windows; p.max_rows = max_Tm;
+    run(0, p, (int64_t)TmS * N_MELS, TmS - 2);
+    // conv2 (stride 2) + GELU + transpose + positional embedding (mod.rs:244-252)
+    p = GemmF16Params{};
+    p.A_hi = h1_h.p; p.A_lo = h1_l.p; p.lda = 2 * d; p.B = m->conv2.w16; p.C = x.p; p.ldc = d; p.N = d; p.K = 3 * d;
+    p.bias = m->conv2.b; p.act = ACT_GELU; p.pos = m->enc_pos; p.groups = d_g2.p; p.n_groups = n_windows; p.max_rows = max_T;
+    run(1, p, (int64_t)TmS * d, Tcap);
+    for (int l = 0; l < D.n_audio_layer; ++l) {
+        const EncBlockW& B = m->enc[(size_t)l];
+        const size_t site = (size_t)2 + 4 * l;
+        // x = x + attn(attn_ln(x))   (mod.rs:300)
+        launch_layernorm_f16(x.p, nullptr, xn_h.p, xn_l.p, B.attn_ln, M, d, m->ln_eps_outside, st);
+        p = GemmF16Params{};
+        p.A_hi = xn_h.p; p.A_lo = xn_l.p; p.lda = d; p.B = B.qkv.w16; p.P_hi = qkv_h.p; p.P_lo = qkv_l.p; p.ldc = 3 * d; p.N = 3 * d; p.K = d;
+        p.bias = B.qkv.b; p.scale = qk_scale; p.scale_cols = 2 * d; p.max_rows = M;
+        run(site, p, 0, M);
+        launch_encoder_attention_tc(qkv_h.p, qkv_l.p, att_h.p, att_l.p, d_awin.p, n_windows, max_T, d, D.n_audio_head, st);
+        p = GemmF16Params{};
+        p.A_hi = att_h.p; p.A_lo = att_l.p; p.lda = d; p.B = B.out.w16; p.C = x.p; p.ldc = d; p.N = d; p.K = d;
+        p.bias = B.out.b; p.residual = x.p; p.max_rows = M;
+        run(site + 1, p, 0, M);
+        // x = x + mlp(mlp_ln(x))     (mod.rs:301); the MLP1 epilogue (bias + GELU) emits the hidden layer as planes
+        launch_layernorm_f16(x.p, nullptr, xn_h.p, xn_l.p, B.mlp_ln, M, d, m->ln_eps_outside, st);
+        p = GemmF16Params{};
+        p.A_hi = xn_h.p; p.A_lo = xn_l.p; p.lda = d; p.B = B.mlp1.w16; p.P_hi = hid_h.p; p.P_lo = hid_l.p; p.ldc = 4 * d; p.N = 4 * d; p.K = d;
+        p.bias = B.mlp1.b; p.act = ACT_GELU; p.max_rows = M;
+        run(site + 2, p, 0, M);
+        p = GemmF16Params{};
+        p.A_hi = hid_h.p; p.A_lo = hid_l.p; p.lda = 4 * d; p.B = B.mlp2.w16; p.C = x.p; p.ldc = d; p.N = d; p.K = 4 * d;
+        p.bias = B.mlp2.b; p.residual = x.p; p.max_rows = M;
+        run(site + 3, p, 0, M);
+    }
+    launch_layernorm_f16(x.p, xa.p, xa_h.p, xa_l.p, m->ln_post, M, d, m->ln_eps_outside, st);   // mod.rs:259
+}
+
+// fp32 CUDA-core encoder: weights that are not exactly representable in fp16
+void Session::run_encoder_f32() {
+    const wb_dims& D = m->dims;
+    const int d = D.n_audio_state;
+    const int M = (int)M_tot;
+    const float qk_scale = (float)std::pow((double)d / (double)D.n_audio_head, -0.25);   // mod.rs:503
+    WB_CUDA(cudaMemsetAsync(h1.p, 0, (size_t)n_windows * TmS * d * sizeof(float), st));
+    GemmParams p;
+    p.A = mel_rows.p; p.lda = N_MELS; p.B = m->conv1.w32; p.C = h1.p; p.ldc = d; p.N = d; p.K = 3 * N_MELS;
+    p.bias = m->conv1.b; p.act = ACT_GELU; p.groups = d_g1.p; p.n_groups = n_windows; p.max_rows = max_Tm;
+    launch_gemm(p, st);
+    p = GemmParams{};
+    p.A = h1.p; p.lda = 2 * d; p.B = m->conv2.w32; p.C = x.p; p.ldc = d; p.N = d; p.K = 3 * d;
+    p.bias = m->conv2.b; p.act = ACT_GELU; p.pos = m->enc_pos; p.groups = d_g2.p; p.n_groups = n_windows;
+    p.max_rows = max_T;
+    launch_gemm(p, st);
+    for (int l = 0; l < D.n_audio_layer; ++l) {
+        const EncBlockW& B = m->enc[(size_t)l];
+        launch_layernorm(x.p, xn.p, B.attn_ln, M, d, m->ln_eps_outside, st);
+        p = GemmParams{};
+        p.A = xn.p; p.lda = d; p.B = B.qkv.w32; p.C = qkv.p; p.ldc = 3 * d; p.N = 3 * d; p.K = d;
+        p.bias = B.qkv.b; p.scale = qk_scale; p.scale_cols = 2 * d; p.max_rows = M;
+        launch_gemm(p, st);
+        launch_encoder_attention(qkv.p, att.p, d_awin.p, n_windows, max_T, d, D.n_audio_head, st);
+        p = GemmParams{};
+        p.A = att.p; p.lda = d; p.B = B.out.w32; p.C = x.p; p.ldc = d; p.N = d; p.K = d;
+        p.bias = B.out.b; p.residual = x.p; p.max_rows = M;
+        launch_gemm(p, st);
+        launch_layernorm(x.p, xn.p, B.mlp_ln, M, d, m->ln_eps_outside, st);
+        p = GemmParams{};
+        p.A = xn.p; p.lda = d; p.B = B.mlp1.w32; p.C = hid.p; p.ldc = 4 * d; p.N = 4 * d; p.K = d;
+        p.bias = B.mlp1.b; p.act = ACT_GELU; p.max_rows = M;
+        launch_gemm(p, st);
+        p = GemmParams{};
+        p.A = hid.p; p.lda = 4 * d; p.B = B.mlp2.w32; p.C = x.p; p.ldc = d; p.N = d; p.K = 4 * d;
+        p.bias = B.mlp2.b; p.residual = x.p; p.max_rows = M;
+        launch_gemm(p, st);
+    }
+    launch_layernorm(x.p, xa.p, m->ln_post, M, d, m->ln_eps_outside, st);   // mod.rs:259
+}
+
+// cross keys (pre-scaled) | values of every decoder layer, projected once per window (mod.rs:484-485 hoisted out of the step loop)
 void Session::run_cross_kv() {
     const wb_dims& D = m->dims;
     const int d = D.n_text_state;
     const float qk_scale = (float)std::pow((double)d / (double)D.n_text_head, -0.25);
-    bool tc = false;
     for (int l = 0; l < D.n_text_layer; ++l) {
         const DecBlockW& B = m->dec[(size_t)l];
-        GemmParams p;
-        p.A = xa.p; p.lda = d; p.B = B.ckv.w32; p.ldc = 2 * d;
-        if (ckv_hm) p.C = ckv_tmp.p;
-        else if (kv_dtype == WB_KV_F16) p.C16 = ckv16.p + (size_t)l * Mcap * 2 * d; else p.C = ckv.p + (size_t)l * Mcap * 2 * d;
-        p.N = 2 * d; p.K = d; p.bias = B.ckv.b; p.scale = qk_scale; p.scale_cols = d; p.max_rows = (int)M_tot;
-        if (use_tc && gemm_tc_supported(p)) {
-            if (!tc) {   // the encoder output itself stays intact (it is returned through the ABI)
-                launch_split_tf32(xa.p, xa_hi.p, lo_b.p, (int64_t)M_tot * d, st);
-                tc = true;
-            }
-            p.A = xa_hi.p;
-            launch_gemm_tc(p, lo_b.p, 0, (int)M_tot, st);
+        float* c32 = ckv_hm ? ckv_tmp.p : (kv_dtype == WB_KV_F16 ? nullptr : ckv.p + (size_t)l * Mcap * 2 * d);
+        if (use_tc) {
+            GemmF16Params p;
+            p.A_hi = xa_h.p; p.A_lo = xa_l.p; p.lda = d; p.B = B.ckv.w16; p.C = c32; p.ldc = 2 * d;
+            p.N = 2 * d; p.K = d; p.bias = B.ckv.b; p.scale = qk_scale; p.scale_cols = d; p.max_rows = (int)M_tot;
+            GemmF16Plan& pl = *enc_plans[(size_t)2 + 4 * D.n_audio_layer + l];
+            if (!pl.matches(p.max_rows, 1)) pl.build(p, 0, (int)M_tot);
+            pl.launch(st);
         } else {
+            GemmParams p;
+            p.A = xa.p; p.lda = d; p.B = B.ckv.w32; p.ldc = 2 * d;
+            if (c32) p.C = c32; else p.C16 = ckv16.p + (size_t)l * Mcap * 2 * d;
+            p.N = 2 * d; p.K = d; p.bias = B.ckv.b; p.scale = qk_scale; p.scale_cols = d; p.max_rows = (int)M_tot;
             launch_gemm(p, st);
         }
         if (ckv_hm) {
@@ -411,72 +423,12 @@ void Session::begin(const int64_t* prompt, int64_t prompt_len, bool prefill) {
     host_pos = 0;
     // feed prompt[0 .. prompt_len-1): no logits needed
     for (int64_t i = 0; prefill && i + 1 < prompt_len; ++i) {
-        step_core(false, 0, 1, false, -1, nullptr);
+        step_core(false, 0, 1, false, -1);
         std::vector<int> nxt((size_t)R, (int)prompt[i + 1]);
         WB_CUDA(cudaMemcpyAsync(cur_tok.p, nxt.data(), nxt.size() * sizeof(int), cudaMemcpyHostToDevice, st));
         WB_CUDA(cudaStreamSynchronize(st));
     }
     WB_CUDA(cudaStreamSynchronize(st));
-}
-
-// One decoder position, fused kernels (decoder2.cu): embed, 3 kernels per layer, logits + finish.
-void Session::step_core_v2(bool with_logits, int mask_mode, int k, bool greedy, int eot) {
-    const wb_dims& D = m->dims;
-    const int d = D.n_text_state, H = D.n_text_head, L = D.n_text_layer, V = D.n_vocab;
-    const bool h16 = m->fp16_exact;
-    const float qk_scale = (float)std::pow((double)d / (double)H, -0.25);
-    const int* anc = anc_identity ? nullptr : (anc_cur == 0 ? anc0.p : anc1.p);
-    auto wptr = [&](const LinearW& w) -> const void* { return h16 ? (const void*)w.w16 : (const void*)w.w32; };
-    const bool pe = prof && with_logits && (size_t)(4 * prof_n + 3) < prof_ev.size();
-    if (pe) WB_CUDA(cudaEventRecord(prof_ev[(size_t)4 * prof_n + 0], st));
-    launch_dec_embed(cur_tok.p, m->tok_emb32, m->dec_pos, pos.p, dx.p, R, d, st);
-    for (int l = 0; l < L; ++l) {
-        const DecBlockW& B = m->dec[(size_t)l];
-        Dec2SelfArgs sa;
-        sa.x = dx.p; sa.R = R; sa.d = d; sa.ln_g = B.attn_ln.g; sa.ln_b = B.attn_ln.b; sa.ln_eps = B.attn_ln.eps;
-        sa.eps_outside = m->ln_eps_outside; sa.Wqkv = wptr(B.qkv); sa.bqkv = B.qkv.b; sa.Wo = wptr(B.out);
-        sa.bo = B.out.b; sa.qk_scale = qk_scale; sa.kc = kc.p + (size_t)l * Rmax * t_max * d;
-        sa.vc = vc.p + (size_t)l * Rmax * t_max * d; sa.anc = anc; sa.t_max = t_max; sa.pos = pos.p;
-        sa.ypart = ypart.p; sa.counter = tickets.p + 0;
-        launch_dec2_self(sa, H, h16, st);
-        Dec2CrossArgs ca;
-        ca.x = dx.p; ca.R = R; ca.d = d; ca.ln_g = B.cross_ln.g; ca.ln_b = B.cross_ln.b; ca.ln_eps = B.cross_ln.eps;
-        ca.eps_outside = m->ln_eps_outside; ca.Wq = wptr(B.cq); ca.bq = B.cq.b; ca.Wo = wptr(B.cout); ca.bo = B.cout.b;
-        ca.qk_scale = qk_scale; ca.ckv = ckv.p + (size_t)l * Mcap * 2 * d; ca.row_window = row_window.p;
-        ca.win_row_off = d_win_row_off.p; ca.win_T = d_win_T.p; ca.kmax = (Tcap + n_splits - 1) / n_splits;
-        ca.ypart = ypart.p; ca.part_m = part_m.p; ca.part_l = part_l.p; ca.counter = tickets.p + 1;
-        launch_dec2_cross(ca, H, n_splits, h16, st);
-        Dec2MlpArgs ma;
-        ma.x = dx.p; ma.R = R; ma.d = d; ma.ln_g = B.mlp_ln.g; ma.ln_b = B.mlp_ln.b; ma.ln_eps = B.mlp_ln.eps;
-        ma.eps_outside = m->ln_eps_outside; ma.W1 = wptr(B.mlp1); ma.b1 = B.mlp1.b; ma.W2 = wptr(B.mlp2);
-        ma.b2 = B.mlp2.b; ma.ypart = ypart.p; ma.counter = tickets.p + 2;
-        launch_dec2_mlp(ma, h16, st);
-    }
-    if (with_logits) {
-        Dec2LogitsArgs la;
-        la.x = dx.p; la.R = R; la.d = d; la.V = V; la.ln_g = m->dec_ln.g; la.ln_b = m->dec_ln.b;
-        la.ln_eps = m->dec_ln.eps; la.eps_outside = m->ln_eps_outside;
-        la.E = h16 ? (const void*)m->tok_emb16 : (const void*)m->tok_emb32;
-        la.is_special = have_special ? is_special.p : nullptr; la.mask_mode = mask_mode; la.pos = pos.p;
-        la.logits_out = full_logits ? logits.p : nullptr;
-        la.part_m = lg_m.p; la.part_s = lg_s.p; la.part_v = lg_v.p; la.part_i = lg_i.p;
-        if (pe) WB_CUDA(cudaEventRecord(prof_ev[(size_t)4 * prof_n + 1], st));
-        launch_dec2_logits(la, n_logit_ctas, h16, st);
-        if (pe) WB_CUDA(cudaEventRecord(prof_ev[(size_t)4 * prof_n + 2], st));
-        Dec2FinishArgs fa;
-        fa.n_parts = n_logit_ctas; fa.part_m = lg_m.p; fa.part_s = lg_s.p; fa.part_v = lg_v.p; fa.part_i = lg_i.p;
-        fa.k = k; fa.topk_id = topk_id.p; fa.topk_lp = topk_lp.p; fa.greedy = greedy ? 1 : 0; fa.tokens = tokens.p;
-        fa.lengths = lengths.p; fa.cur_tok = cur_tok.p; fa.finished = finished.p; fa.t_max = t_max; fa.eot = eot;
-        fa.pos = pos.p; fa.n_unfinished = n_unfinished.p; fa.counter = tickets.p + 3;
-        launch_dec2_finish(fa, R, st);
-    } else {
-        launch_dec_advance(pos.p, nullptr, R, n_unfinished.p, st);
-    }
-    if (pe) {
-        WB_CUDA(cudaEventRecord(prof_ev[(size_t)4 * prof_n + 3], st));
-        ++prof_n;
-    }
-    ++host_pos;
 }
 
 // One cooperative launch of the persistent decoder: n_steps positions starting at pos0.
@@ -544,7 +496,7 @@ void Session::launch_v3(int R_, int pos0, int n_steps, int logits_from, bool use
         std::vector<unsigned long long> h(1 << 16);
         WB_CUDA(cudaStreamSynchronize(st));
         WB_CUDA(cudaMemcpy(h.data(), d3_trace.p, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-        FILE* f = fopen("gpurun_out/d3_trace.txt", "w");
+        FILE* f = fopen(getenv("WB200_TRACE"), "w");   // debugging aid: WB200_TRACE=<file> receives the stage time stamps of CTA 0
         if (f) {
             for (size_t i = 0; i < h.size() && h[i]; ++i) fprintf(f, "%llu\n", h[i]);
             fclose(f);
@@ -552,141 +504,32 @@ void Session::launch_v3(int R_, int pos0, int n_steps, int logits_from, bool use
     }
 }
 
-void Session::step_core(bool with_logits, int mask_mode, int k, bool greedy, int eot, float* logprob_out) {
-    if (kv_dtype == WB_KV_F16 && k > 7) fail(WB_ERR_UNSUPPORTED, "fp16 K/V cache supports k <= 7");
-    if (dec_version >= 3 && k <= 7) {
-        launch_v3(R, host_pos, 1, with_logits ? 0 : INT_MAX, true, mask_mode, k, greedy, eot);
-        ++host_pos;
-        return;
-    }
-    if (ckv_hm) fail(WB_ERR_UNSUPPORTED, "k > 7 candidates per row needs the per-op decoder (WB200_DECODER=1): the persistent decoders keep the cross K/V head-major");
-    if (dec_version == 2 && k <= DEC2_KC - 1) {
-        step_core_v2(with_logits, mask_mode, k, greedy, eot);
-        return;
-    }
-    const wb_dims& D = m->dims;
-    const int d = D.n_text_state, H = D.n_text_head, L = D.n_text_layer, V = D.n_vocab;
-    const bool h16 = m->fp16_exact;
-    const float qk_scale = (float)std::pow((double)d / (double)H, -0.25);
-    const int* anc = anc_identity ? nullptr : (anc_cur == 0 ? anc0.p : anc1.p);
-    const bool pe = prof && with_logits && (size_t)(4 * prof_n + 3) < prof_ev.size();
-    if (pe) WB_CUDA(cudaEventRecord(prof_ev[(size_t)4 * prof_n + 0], st));
-    launch_dec_embed(cur_tok.p, m->tok_emb32, m->dec_pos, pos.p, dx.p, R, d, st);
-    auto wptr = [&](const LinearW& w) -> const void* { return h16 ? (const void*)w.w16 : (const void*)w.w32; };
-    for (int l = 0; l < L; ++l) {
-        const DecBlockW& B = m->dec[(size_t)l];
-        float* kcl = kc.p + (size_t)l * Rmax * t_max * d;
-        float* vcl = vc.p + (size_t)l * Rmax * t_max * d;
-        // ---- self attention (mod.rs:346)
-        GemvArgs g;
-        g.W = wptr(B.qkv); g.bias = B.qkv.b; g.N = 3 * d; g.K = d; g.R = R; g.in_mode = IN_LN; g.in = dx.p;
-        g.ln_g = B.attn_ln.g; g.ln_b = B.attn_ln.b; g.ln_eps = B.attn_ln.eps; g.eps_outside = m->ln_eps_outside;
-        g.n_seg = 3; g.pos = pos.p;
-        g.seg[0] = GemvSeg{0, dq.p, d, 0, qk_scale};
-        g.seg[1] = GemvSeg{d, kcl, (int64_t)t_max * d, d, qk_scale};
-        g.seg[2] = GemvSeg{2 * d, vcl, (int64_t)t_max * d, d, 1.0f};
-        launch_dec_gemv(g, h16, st);
-        DecAttnArgs a;
-        a.q = dq.p; a.q_ld = d; a.K = kcl; a.V = vcl; a.kv_ld = d; a.is_cross = 0; a.anc = anc; a.t_max = t_max;
-        a.pos = pos.p; a.part_o = part_o.p; a.part_m = part_m.p; a.part_l = part_l.p;
-        launch_dec_attn(a, H, R, 1, st);
-        g = GemvArgs{};
-        g.W = wptr(B.out); g.bias = B.out.b; g.N = d; g.K = d; g.R = R; g.in_mode = IN_ATTN_MERGE;
-        g.part_o = part_o.p; g.part_m = part_m.p; g.part_l = part_l.p; g.n_splits = 1; g.residual = 1;
-        g.seg[0] = GemvSeg{0, dx.p, d, 0, 1.0f};
-        launch_dec_gemv(g, h16, st);
-        // ---- cross attention (mod.rs:347)
-        g = GemvArgs{};
-        g.W = wptr(B.cq); g.bias = B.cq.b; g.N = d; g.K = d; g.R = R; g.in_mode = IN_LN; g.in = dx.p;
-        g.ln_g = B.cross_ln.g; g.ln_b = B.cross_ln.b; g.ln_eps = B.cross_ln.eps; g.eps_outside = m->ln_eps_outside;
-        g.seg[0] = GemvSeg{0, dq.p, d, 0, qk_scale};
-        launch_dec_gemv(g, h16, st);
-        a = DecAttnArgs{};
-        const float* ckvl = ckv.p + (size_t)l * Mcap * 2 * d;
-        a.q = dq.p; a.q_ld = d; a.K = ckvl; a.V = ckvl + d; a.kv_ld = 2 * d; a.is_cross = 1;
-        a.row_window = row_window.p; a.win_row_off = d_win_row_off.p; a.win_T = d_win_T.p; a.pos = pos.p;
-        a.part_o = part_o.p; a.part_m = part_m.p; a.part_l = part_l.p;
-        launch_dec_attn(a, H, R, n_splits, st);
-        g = GemvArgs{};
-        g.W = wptr(B.cout); g.bias = B.cout.b; g.N = d; g.K = d; g.R = R; g.in_mode = IN_ATTN_MERGE;
-        g.part_o = part_o.p; g.part_m = part_m.p; g.part_l = part_l.p; g.n_splits = n_splits; g.residual = 1;
-        g.seg[0] = GemvSeg{0, dx.p, d, 0, 1.0f};
-        launch_dec_gemv(g, h16, st);
-        // ---- MLP (mod.rs:348)
-        g = GemvArgs{};
-        g.W = wptr(B.mlp1); g.bias = B.mlp1.b; g.N = 4 * d; g.K = d; g.R = R; g.in_mode = IN_LN; g.in = dx.p;
-        g.ln_g = B.mlp_ln.g; g.ln_b = B.mlp_ln.b; g.ln_eps = B.mlp_ln.eps; g.eps_outside = m->ln_eps_outside;
-        g.act = ACT_GELU;
-        g.seg[0] = GemvSeg{0, dhid.p, 4 * d, 0, 1.0f};
-        launch_dec_gemv(g, h16, st);
-        g = GemvArgs{};
-        g.W = wptr(B.mlp2); g.bias = B.mlp2.b; g.N = d; g.K = 4 * d; g.R = R; g.in_mode = IN_COPY; g.in = dhid.p;
-        g.residual = 1;
-        g.seg[0] = GemvSeg{0, dx.p, d, 0, 1.0f};
-        launch_dec_gemv(g, h16, st);
-    }
-    if (with_logits) {
-        GemvArgs g;
-        g.W = h16 ? (const void*)m->tok_emb16 : (const void*)m->tok_emb32;
-        g.bias = nullptr; g.N = V; g.K = d; g.R = R; g.in_mode = IN_LN; g.in = dx.p;
-        g.ln_g = m->dec_ln.g; g.ln_b = m->dec_ln.b; g.ln_eps = m->dec_ln.eps; g.eps_outside = m->ln_eps_outside;
-        g.seg[0] = GemvSeg{0, logits.p, V, 0, 1.0f};
-        if (pe) WB_CUDA(cudaEventRecord(prof_ev[(size_t)4 * prof_n + 1], st));
-        launch_dec_gemv(g, h16, st);
-        if (pe) WB_CUDA(cudaEventRecord(prof_ev[(size_t)4 * prof_n + 2], st));
-        LogSoftmaxArgs s;
-        s.logits = logits.p; s.V = V; s.is_special = have_special ? is_special.p : nullptr; s.mask_mode = mask_mode;
-        s.pos = pos.p; s.k = k; s.topk_id = topk_id.p; s.topk_lp = topk_lp.p; s.logprob_out = logprob_out;
-        s.greedy = greedy ? 1 : 0; s.tokens = tokens.p; s.lengths = lengths.p; s.cur_tok = cur_tok.p;
-        s.finished = finished.p; s.t_max = t_max; s.eot = eot;
-        launch_logsoftmax_topk(s, R, st);
-    }
-    launch_dec_advance(pos.p, greedy ? finished.p : nullptr, R, n_unfinished.p, st);
-    if (pe) {
-        WB_CUDA(cudaEventRecord(prof_ev[(size_t)4 * prof_n + 3], st));
-        ++prof_n;
-    }
+void Session::step_core(bool with_logits, int mask_mode, int k, bool greedy, int eot) {
+    WB_REQUIRE(k >= 1 && k <= DEC_KC - 1, "step: k must be in [1, 7]");
+    launch_v3(R, host_pos, 1, with_logits ? 0 : INT_MAX, true, mask_mode, k, greedy, eot);
     ++host_pos;
 }
 
 void Session::profile_decode(const int64_t* prompt, int64_t prompt_len, int n_steps, int64_t eot, float* logits_ms,
                              float* step_ms) {
     WB_REQUIRE(n_steps >= 1 && prompt_len + n_steps <= t_max, "profile: n_steps out of range");
-    while (prof_ev.size() < (size_t)4 * n_steps) {
+    while (prof_ev.size() < 2) {
         cudaEvent_t e;
         WB_CUDA(cudaEventCreate(&e));
         prof_ev.push_back(e);
     }
-    if (dec_version >= 3) {
-        // the whole decode is ONE kernel: time the launch (prefill + n_steps greedy steps) and report per step
-        begin(prompt, prompt_len, false);
-        const int total = (int)prompt_len - 1 + n_steps;
-        WB_CUDA(cudaEventRecord(prof_ev[0], st));
-        launch_v3(R, 0, total, (int)prompt_len - 1, false, 2, 1, true, -1 /* never stop early */);
-        WB_CUDA(cudaEventRecord(prof_ev[1], st));
-        WB_CUDA(cudaStreamSynchronize(st));
-        float t = 0.f;
-        WB_CUDA(cudaEventElapsedTime(&t, prof_ev[0], prof_ev[1]));
-        *logits_ms = t / (float)total;
-        *step_ms = t / (float)total;
-        return;
-    }
-    begin(prompt, prompt_len);
-    prof = true;
-    prof_n = 0;
-    for (int i = 0; i < n_steps; ++i) step_core(true, 2, 1, true, (int)eot, nullptr);
-    prof = false;
+    // the whole decode is ONE kernel: time the launch (prefill + n_steps greedy steps) and report per position
+    begin(prompt, prompt_len, false);
+    const int total = (int)prompt_len - 1 + n_steps;
+    WB_CUDA(cudaEventRecord(prof_ev[0], st));
+    launch_v3(R, 0, total, (int)prompt_len - 1, false, 2, 1, true, -1 /* never stop early */);
+    WB_CUDA(cudaEventRecord(prof_ev[1], st));
     WB_CUDA(cudaStreamSynchronize(st));
-    double a = 0.0, b = 0.0;
-    for (int i = 0; i < prof_n; ++i) {
-        float t = 0.f;
-        WB_CUDA(cudaEventElapsedTime(&t, prof_ev[(size_t)4 * i + 1], prof_ev[(size_t)4 * i + 2]));
-        a += t;
-        WB_CUDA(cudaEventElapsedTime(&t, prof_ev[(size_t)4 * i + 0], prof_ev[(size_t)4 * i + 3]));
-        b += t;
-    }
-    *logits_ms = (float)(a / std::max(prof_n, 1));
-    *step_ms = (float)(b / std::max(prof_n, 1));
+    float t = 0.f;
+    WB_CUDA(cudaEventElapsedTime(&t, prof_ev[0], prof_ev[1]));
+    (void)eot;
+    *logits_ms = t / (float)total;
+    *step_ms = t / (float)total;
 }
 
 void Session::step_beams(int64_t n_rows, const int32_t* window_of_row, const int32_t* parent_row, const int64_t* token,
@@ -722,7 +565,7 @@ void Session::step_beams(int64_t n_rows, const int32_t* window_of_row, const int
         launch_dec_reorder(cur, nxt, parent.p, pos.p, R, t_max, st);
         anc_cur ^= 1;
     }
-    step_core(true, apply_mask ? 1 : 0, k, false, -1, nullptr);
+    step_core(true, apply_mask ? 1 : 0, k, false, -1);
     int* hid_ = h_int + 4 * Rmax + 16;
     WB_CUDA(cudaMemcpyAsync(hid_, topk_id.p, sizeof(int) * n_rows * k, cudaMemcpyDeviceToHost, st));
     WB_CUDA(cudaMemcpyAsync(h_float, topk_lp.p, sizeof(float) * n_rows * k, cudaMemcpyDeviceToHost, st));
@@ -736,41 +579,18 @@ void Session::step_beams(int64_t n_rows, const int32_t* window_of_row, const int
 void Session::greedy_decode(const int64_t* prompt, int64_t prompt_len, int max_depth, int64_t eot,
                             std::vector<std::vector<int64_t>>& out) {
     WB_REQUIRE(prompt_len + max_depth <= t_max, "greedy: prompt + max_depth exceeds the session's max_text_len");
-    if (dec_version >= 3) {
-        // one cooperative launch: prompt prefill + every greedy step, early exit inside the kernel
-        begin(prompt, prompt_len, /*prefill=*/false);
-        const int n_steps = (int)prompt_len - 1 + max_depth;
-        if (max_depth > 0) launch_v3(R, 0, n_steps, (int)prompt_len - 1, false, 2, 1, true, (int)eot);
-        std::vector<int> tk((size_t)R * t_max), len((size_t)R);
-        int sd = 0;
-        WB_CUDA(cudaMemcpyAsync(tk.data(), tokens.p, tk.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
-        WB_CUDA(cudaMemcpyAsync(len.data(), lengths.p, len.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
-        if (max_depth > 0) WB_CUDA(cudaMemcpyAsync(&sd, steps_done.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-        WB_CUDA(cudaStreamSynchronize(st));
-        last_steps = max_depth > 0 ? sd - ((int)prompt_len - 1) : 0;
-        host_pos = (int)prompt_len - 1 + (int)last_steps;
-        out.assign((size_t)R, {});
-        for (int r = 0; r < R; ++r)
-            for (int i = 0; i < len[(size_t)r]; ++i) out[(size_t)r].push_back(tk[(size_t)r * t_max + i]);
-        return;
-    }
-    begin(prompt, prompt_len);
-    // beam_search with beam_size 1 (beam.rs:9-37): stop when the (only) beam ends in EOT or after max_depth steps
-    int done_steps = 0;
-    const int poll = 16;
-    while (done_steps < max_depth) {
-        const int n = std::min(poll, max_depth - done_steps);
-        for (int i = 0; i < n; ++i) step_core(true, 2, 1, true, (int)eot, nullptr);
-        done_steps += n;
-        WB_CUDA(cudaMemcpyAsync(h_int, n_unfinished.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-        WB_CUDA(cudaStreamSynchronize(st));
-        if (h_int[0] == 0) break;
-    }
-    last_steps = done_steps;
+    // one launch: prompt prefill + every greedy step, early exit inside the kernel
+    begin(prompt, prompt_len, /*prefill=*/false);
+    const int n_steps = (int)prompt_len - 1 + max_depth;
+    if (max_depth > 0) launch_v3(R, 0, n_steps, (int)prompt_len - 1, false, 2, 1, true, (int)eot);
     std::vector<int> tk((size_t)R * t_max), len((size_t)R);
+    int sd = 0;
     WB_CUDA(cudaMemcpyAsync(tk.data(), tokens.p, tk.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
     WB_CUDA(cudaMemcpyAsync(len.data(), lengths.p, len.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (max_depth > 0) WB_CUDA(cudaMemcpyAsync(&sd, steps_done.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     WB_CUDA(cudaStreamSynchronize(st));
+    last_steps = max_depth > 0 ? sd - ((int)prompt_len - 1) : 0;
+    host_pos = (int)prompt_len - 1 + (int)last_steps;
     out.assign((size_t)R, {});
     for (int r = 0; r < R; ++r)
         for (int i = 0; i < len[(size_t)r]; ++i) out[(size_t)r].push_back(tk[(size_t)r * t_max + i]);

@@ -1,5 +1,6 @@
 // Decoding session: all device state between prep_audio and the emitted token ids.  Internal.
 #pragma once
+#include <memory>
 #include <vector>
 
 #include "decoder.h"
@@ -17,8 +18,7 @@ struct Session {
     int TmS = 0;         // rows per window in the token-major mel / conv1 buffers (n_audio_ctx + 2 halo rows)
     int Tcap = 0;        // max encoder positions per window
     int64_t Mcap = 0;    // max packed encoder rows
-    int n_splits = 1;    // split-KV factor of the cross attention
-    int kmax = 8;        // max top-k
+    int kmax = 8;        // candidates per row the step API can return (k <= 7)
 
     // ---- geometry of the windows currently encoded (host mirrors)
     int n_windows = 0;
@@ -37,14 +37,18 @@ struct Session {
     // ---- device: frontend + encoder activations
     DevBuf<float> wave;
     DevBuf<int> max_slots;
-    DevBuf<float> mel_rows, h1, x, xn, att, qkv, hid, xa;
-    DevBuf<float> lo_a, lo_b, lo_b4, xa_hi, mel_hi, mel_lo, h1_lo;   // TF32 planes of the GEMM inputs (tensor-core path)
+    DevBuf<float> mel_rows, x, xa;           // token-major log-mel rows, residual stream, encoder output
+    DevBuf<float> h1, xn, att, qkv, hid;     // fp32 activations of the CUDA-core encoder (weights that are not fp16-exact)
+    // tensor-core path (fp16-exact weights): every GEMM input travels as a pair of fp16 planes (gemm_f16.cu)
+    DevBuf<__half> mel_h, mel_l, h1_h, h1_l, xn_h, xn_l, qkv_h, qkv_l, att_h, att_l, hid_h, hid_l, xa_h, xa_l;
+    std::vector<std::unique_ptr<GemmF16Plan>> enc_plans;   // conv1, conv2, per encoder layer qkv / out / mlp1 / mlp2, per decoder layer cross K|V
     bool conv_tc_ok = true;            // cleared if the driver rejects the overlapping-row tensor maps of the conv stems
     bool use_tc = true;                // WB200_GEMM=simt forces the fp32 CUDA-core GEMM
-    void gemm(const GemmParams& p, float* a_mut, float* lo_buf);   // tensor-core when possible
+    void run_encoder_f16();            // tensor-core encoder
+    void run_encoder_f32();            // fp32 CUDA-core encoder (weights that are not fp16-exact)
     DevBuf<float> ckv;     // [L][Mcap][2d]  cross keys (scaled) | values, projected once per window
     DevBuf<float> ckv_tmp; // [Mcap][2d] one layer's projection in GEMM (row-major) order, before the head-major re-layout
-    bool ckv_hm = false;   // cross K/V stored head-major (persistent decoders); the per-op decoders (WB200_DECODER=1|2) read it row-major
+    bool ckv_hm = true;    // cross K/V stored head-major (what the persistent decoders stream)
     // ---- device: decode state
     DevBuf<float> kc, vc;  // [L][Rmax][t_max][d] self keys (scaled) / values
     DevBuf<__half> kc16, vc16, ckv16;   // fp16 caches (WB_KV_F16)
@@ -67,11 +71,8 @@ struct Session {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float last_ms[4] = {0, 0, 0, 0};
     int64_t last_steps = 0;
-    // fused decoder step (decoder2.cu): partial buffers, tickets, switches
-    int last_decoder = 0;        // which persistent decoder the last launch used (3, 4 or 5); 0 = none yet / per-op path
-    int dec_version = 4;         // 4 = cluster/DSMEM kernel (decoder4.cu, small batches) / batched tensor-core kernel (decoder5.cu), fallback 3 = grid-barrier
-                                 // persistent kernel (decoder3.cu); WB200_DECODER=1|2|3 select the older paths:
-                                 // unfused (decoder.cu) / fused-per-layer (decoder2.cu) paths for A/B testing
+    int last_decoder = 0;        // which persistent decoder the last launch used (6, 5, 4 or 3); 0 = none yet
+    int dec_version = 4;         // 4 = best persistent decoder for the shape (decoder6 / decoder5 / decoder4), 3 = force the grid-barrier fallback (WB200_DECODER=3)
     int n_sm = 0;
     DevBuf<Dec3Layer> d3_layers;
     DevBuf<uint8_t> d6_pack[3];     // decoder6.cu packed weight slices, index = CTAs per head (1, 2), built on first use
@@ -87,12 +88,7 @@ struct Session {
     int n_logit_ctas = 0;
     DevBuf<float> ypart, lg_m, lg_s, lg_v;
     DevBuf<int> lg_i;
-    DevBuf<unsigned int> tickets;
-    void step_core_v2(bool with_logits, int mask_mode, int k, bool greedy, int eot);
-    // optional per-kernel profiling (wb_session_profile_decode)
-    bool prof = false;
-    std::vector<cudaEvent_t> prof_ev;   // 4 per step: step begin, logits begin, logits end, step end
-    int prof_n = 0;
+    std::vector<cudaEvent_t> prof_ev;   // wb_session_profile_decode: launch begin / end
     void profile_decode(const int64_t* prompt, int64_t prompt_len, int n_steps, int64_t eot, float* logits_ms, float* step_ms);
 
     Session(Model* model, int64_t max_windows, int64_t max_beams, int64_t max_text_len, int kv_dtype);
@@ -112,7 +108,7 @@ struct Session {
     void set_special(const uint8_t* is_special_host);
     void begin(const int64_t* prompt, int64_t prompt_len, bool prefill = true);
     // one decoder position for R rows; tokens come from cur_tok
-    void step_core(bool with_logits, int mask_mode, int k, bool greedy, int eot, float* logprob_out);
+    void step_core(bool with_logits, int mask_mode, int k, bool greedy, int eot);
     void step_beams(int64_t n_rows, const int32_t* window_of_row, const int32_t* parent_row, const int64_t* token,
                     int apply_mask, int k, int64_t* topk_ids_out, float* topk_lp_out);
     // greedy loop on the device; returns per-window token lists

@@ -157,7 +157,6 @@ struct GemmParams {
     const float* B = nullptr;      // [N][K]
     float* C = nullptr;
     __half* C16 = nullptr;         // optional: store fp16-rounded results here instead of C (fp16 K/V cache)
-    float* C_lo = nullptr;         // optional (tensor-core path): C gets the TF32 hi plane, C_lo the lo plane
     int64_t ldc = 0;
     int N = 0, K = 0;
     const float* bias = nullptr;   // [N] or null
@@ -171,10 +170,44 @@ struct GemmParams {
     int max_rows = 0;                 // max rows over groups
 };
 void launch_gemm(const GemmParams& p, cudaStream_t st);
-// tensor-core path (gemm_tc.cu): p.A is the TF32 hi plane, a_lo the lo plane of the same geometry
-bool gemm_tc_supported(const GemmParams& p);
-void launch_split_tf32(const float* src, float* hi, float* lo, int64_t n, cudaStream_t st);
-void launch_gemm_tc(const GemmParams& p, const float* a_lo, int64_t a_group_stride, int a_rows_total_per_group, cudaStream_t st);
+
+// ---- tensor-core GEMM on fp16 hi/lo planes (gemm_f16.cu) ----------------------------------------------------
+// A = A_hi + A_lo / 2048 (fp16 planes, row-major [rows][lda]), B = fp16 [N][K] (exact weights); see gemm_f16.cu.
+struct GemmF16Params {
+    const __half *A_hi = nullptr, *A_lo = nullptr;
+    int64_t lda = 0;
+    const __half* B = nullptr;        // [N][K]
+    float* C = nullptr;               // fp32 result rows, or null
+    __half *P_hi = nullptr, *P_lo = nullptr;   // fp16 planes of the result, or null
+    int64_t ldc = 0;
+    int N = 0, K = 0;
+    const float* bias = nullptr;
+    int act = ACT_NONE;
+    float scale = 1.0f;
+    int scale_cols = 0;
+    const float* residual = nullptr;
+    const float* pos = nullptr;
+    const GemmGroup* groups = nullptr;
+    int n_groups = 1;
+    int max_rows = 0;
+};
+bool gemm_f16_supported(const GemmF16Params& p);
+// Tensor maps and launch geometry of one GEMM site, built once per (site, geometry) instead of per launch
+class GemmF16Plan {
+public:
+    GemmF16Plan();
+    ~GemmF16Plan();
+    GemmF16Plan(const GemmF16Plan&) = delete;
+    GemmF16Plan& operator=(const GemmF16Plan&) = delete;
+    void build(const GemmF16Params& p, int64_t a_group_stride, int a_rows_total_per_group);
+    void launch(cudaStream_t st) const;
+    bool matches(int max_rows, int n_groups) const { return impl != nullptr && key_rows == max_rows && key_groups == n_groups; }
+private:
+    struct Impl;
+    Impl* impl = nullptr;
+    int key_rows = -1, key_groups = -1;
+};
+void launch_split_f16(const float* src, __half* hi, __half* lo, int64_t n, cudaStream_t st);
 
 // ---- frontend (logmel.cu) ---------------------------------------------------------------------
 struct LogMelWindow {
@@ -193,18 +226,22 @@ void launch_rows_to_chan(const float* rows, float* chan, int n_frames, cudaStrea
 void launch_chan_to_rows(const float* chan, float* rows, int n_frames, int64_t chan_stride, cudaStream_t st);
 
 // ---- encoder pieces (encoder.cu) -----------------------------------------------------------------
-// y_lo != null: y receives the TF32 hi plane of LayerNorm(x) and y_lo the lo plane (prologue of a tensor-core GEMM)
 // head-major re-layout of one layer's cross K|V rows (see encoder.cu)
 void launch_ckv_relayout(const float* src, void* dst, bool dst_half, const int64_t* win_row_off, const int* win_T, int n_windows,
                          int64_t M, int d, cudaStream_t st);
-void launch_layernorm(const float* x, float* y, float* y_lo, const LayerNormW& ln, int rows, int d, int eps_outside,
-                      cudaStream_t st);
+void launch_layernorm(const float* x, float* y, const LayerNormW& ln, int rows, int d, int eps_outside, cudaStream_t st);
 struct AttnWindow {
     int64_t row_off;   // first packed row of the window
     int T;
 };
 // non-causal multi-head attention over packed rows; qkv [rows][3d] (q,k pre-scaled), out [rows][d]
-void launch_encoder_attention(const float* qkv, float* out, float* out_lo, const AttnWindow* win_dev, int n_windows, int max_T,
-                              int d, int n_head, cudaStream_t st);
+void launch_encoder_attention(const float* qkv, float* out, const AttnWindow* win_dev, int n_windows, int max_T, int d, int n_head,
+                              cudaStream_t st);
+// tensor-core version on fp16 hi/lo planes (enc_attn_tc.cu): q | k | v planes [rows][3d] -> output planes [rows][d]
+void launch_encoder_attention_tc(const __half* qkv_hi, const __half* qkv_lo, __half* out_hi, __half* out_lo, const AttnWindow* win_dev,
+                                 int n_windows, int max_T, int d, int n_head, cudaStream_t st);
+// LayerNorm whose output leaves as fp16 hi/lo planes (and optionally as fp32 rows too: y may be null)
+void launch_layernorm_f16(const float* x, float* y, __half* y_hi, __half* y_lo, const LayerNormW& ln, int rows, int d, int eps_outside,
+                          cudaStream_t st);
 
 }  // namespace wb
