@@ -366,3 +366,19 @@ def test_launch_counter_counts_kernels(small):
     sess = transcribe.Session(wh, 1, 1, 16)
     sess.transcribe_windows([synth.waveform(16000, seed=1)], sp, is_special_of(sp), beam_size=1, max_depth=4)
     assert ffi.lib().wb_kernel_launch_count() > 20     # log-mel 2 + encoder ~27 + cross K/V + 1 persistent decoder launch
+
+
+@pytest.mark.parametrize("beam_size", [1, 5])
+def test_batched_decoder_row_groups(wide, beam_size):
+    """More rows than one launch of decoder5.cu takes (the shape of BASELINE configs[4]: beams of many windows per GPU): the session
+    runs row groups of 32, one launch each; greedy 40 windows = 2 groups, beam 5 x 9 windows = 45 rows = 2 groups with the ancestry
+    table addressing absolute cache rows."""
+    dims, _, w_t, sp, wh = wide
+    n = 40 if beam_size == 1 else 9
+    waves = [synth.waveform(28000 + 1500 * i, seed=200 + i) for i in range(n)]
+    sess = transcribe.Session(wh, max_windows=n, max_beams=beam_size, max_text_len=4 + 8 + 1)
+    got = sess.transcribe_windows(waves, sp, is_special_of(sp), beam_size=beam_size, max_depth=8)
+    assert sess.last_decoder() == 5
+    for i in (range(0, n, 7) if beam_size == 1 else range(n)):
+        want = o_tr.mels_to_tokens(w_t, dims, sp, o_audio.prep_audio(torch.from_numpy(waves[i])[None]), beam_size=beam_size, max_depth=8)
+        assert got[i] == want, f"window {i}"

@@ -55,6 +55,7 @@ struct Dec3Args {
     const void* ckv = nullptr;            // [L][Mcap][2d]
     int ckv_hm = 0;                       // 1: head-major cross K/V (encoder.cu ckv_relayout_kernel), 0: GEMM row-major order
     int kv_half = 0;
+    int kv_row0 = 0;                      // decoder5.cu row groups: local row r of this launch is cache row r + kv_row0 (ancestry entries are absolute)
     const int* row_window = nullptr;
     const int64_t* win_row_off = nullptr;
     const int* win_T = nullptr;

@@ -27,7 +27,8 @@
 // Code size matters: the layer loop must stay inside the instruction cache, so every building block (staging,
 // MMA tile, emit, attention) exists ONCE and the stages are driven by small descriptors (the first version
 // inlined six copies and ran 3x slower than its memory traffic explains).
-// Requirements: fp16-exact weights, d % 256 == 0, d <= 1280, R <= 32.  Everything else falls back to decoder3.cu.
+// Requirements: fp16-exact weights, d % 256 == 0, d <= 1280, R <= 32 per launch (the session runs larger batches -- beams of many
+// windows -- as row groups of 32, one launch each, a.kv_row0 = first cache row of the group).  Everything else falls back to decoder3.cu.
 #include <cooperative_groups.h>
 #include <cuda_fp16.h>
 
@@ -269,12 +270,12 @@ dec5_kernel(const Dec3Args a) {
                         const int voff = a.ckv_hm ? 64 : d;
                         auto kp = [&](int j) -> const KVT* {
                             if (is_cross) return kbase + j * ld;
-                            const int rr = (anc && j < p) ? __ldcg(anc + j) : r;
+                            const int rr = (anc && j < p) ? __ldcg(anc + j) : r + a.kv_row0;
                             return kcl + ((int64_t)rr * t_max + j) * d + h * 64;
                         };
                         auto vp = [&](int j) -> const KVT* {
                             if (is_cross) return kbase + j * ld + voff;
-                            const int rr = (anc && j < p) ? __ldcg(anc + j) : r;
+                            const int rr = (anc && j < p) ? __ldcg(anc + j) : r + a.kv_row0;
                             return vcl + ((int64_t)rr * t_max + j) * d + h * 64;
                         };
                         AttnAcc A;
@@ -443,8 +444,8 @@ dec5_kernel(const Dec3Args a) {
                                             case EM_QKV:      // mod.rs:429-431; q and k carry the (d/H)^-0.25 scale (:500-503)
                                                 if (n < 2 * d) v = __fmul_rn(v, scale);
                                                 if (n < d) a.q[(int64_t)r * d + n] = v;
-                                                else if (n < 2 * d) kcl[((int64_t)r * t_max + p) * d + (n - d)] = (KVT)v;   // fp16 cache: round-to-nearest
-                                                else vcl[((int64_t)r * t_max + p) * d + (n - 2 * d)] = (KVT)v;
+                                                else if (n < 2 * d) kcl[((int64_t)(r + a.kv_row0) * t_max + p) * d + (n - d)] = (KVT)v;   // fp16 cache: round-to-nearest
+                                                else vcl[((int64_t)(r + a.kv_row0) * t_max + p) * d + (n - 2 * d)] = (KVT)v;
                                                 break;
                                             case EM_RESID:    // x += out-projection (mod.rs:346-347)
                                                 x[(int64_t)r * d + n] = __fadd_rn(prev[e], v);

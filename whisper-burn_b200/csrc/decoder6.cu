@@ -49,8 +49,10 @@ namespace wb {
 namespace {
 
 constexpr int NCW = 8;                    // consumer warps (threads 0..255)
-constexpr int W_PROD = NCW, W_MMA = NCW + 1;
-constexpr int NTH6 = (NCW + 2) * 32;      // + producer warp + MMA warp
+constexpr int NPROD = 3;                  // producer warps: bulk copies of ONE issuing thread complete one after the other (measured ~0.45 us per 16 KB,
+                                          // i.e. 35 GB/s per SM whatever the ring depth); copies of different warps overlap
+constexpr int W_PROD = NCW, W_MMA = NCW + NPROD;
+constexpr int NTH6 = (NCW + NPROD + 1) * 32;      // + producer warps + MMA warp
 constexpr int SLOT = 16384;               // bytes per ring slot = one 128-row x 64-column fp16 slab
 constexpr int NSLOT = 8;
 constexpr int LG_NBUF = 2;                // logits stage: ring slots per warp (aliases the weight ring)
@@ -101,7 +103,7 @@ __device__ __forceinline__ void bulk_s2peer(void* dst_local, const void* src, ui
     asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(rd), "r"(s32(src)), "r"(bytes), "r"(rb) : "memory");
 }
 __device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-__device__ __forceinline__ void bar_all() { asm volatile("bar.sync 2, 320;" ::: "memory"); }
+__device__ __forceinline__ void bar_all() { asm volatile("bar.sync 2, %0;" ::"n"(NTH6) : "memory"); }
 __device__ __forceinline__ float group8_sum(float v) {   // sum over the 8 lanes that share lane >> 3 (all lanes converged)
     v += __shfl_xor_sync(0xffffffffu, v, 1);
     v += __shfl_xor_sync(0xffffffffu, v, 2);
@@ -315,10 +317,11 @@ __device__ __noinline__ Counters gemv_epi6(const Pipe P, Counters c, int N, int 
 }
 
 // MMA warp (one thread): the tensor-core side of the same linear layer
-__device__ __forceinline__ Counters gemv_mma6(const Pipe P, Counters c, int n_tiles, int n_slabs, uint32_t bx_addr) {
+__device__ __forceinline__ Counters gemv_mma6(const Pipe P, Counters c, int n_tiles, int n_slabs, uint32_t bx_addr, unsigned long long* tr, int& tn, int tcap) {
     // instruction descriptor: D = F32 (1 << 4), A = B = F16 (format 0), K-major both, N >> 3 = 2 at bit 17, M >> 4 = 8 at bit 24
     constexpr uint32_t idesc = (1u << 4) | (2u << 17) | (8u << 24);
     mbar_wait(P.b_ready, c.gemv & 1);
+    if (tr && tn < tcap) tr[tn++] = (gtime() << 2) | 1ull;   // debug trace: B operand ready
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
     for (int t = 0; t < n_tiles; ++t) {
@@ -329,6 +332,7 @@ __device__ __forceinline__ Counters gemv_mma6(const Pipe P, Counters c, int n_ti
         for (int s = 0; s < n_slabs; ++s) {
             const uint32_t slot = c.n % NSLOT;
             mbar_wait(P.full + slot, (c.n / NSLOT) & 1);
+            if (tr && tn < tcap) tr[tn++] = (gtime() << 2) | 2ull;   // debug trace: slab landed
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint64_t da = make_smem_desc(s32(P.ring + slot * SLOT)), db = make_smem_desc(bx_addr + (uint32_t)s * BX_SLAB);
 #pragma unroll
@@ -594,14 +598,18 @@ dec6_kernel(const Dec3Args a) {
     constexpr int T_QKV = 2, T_D = (D + 127) / 128, T_CQ = 1, T_W1 = (NS + 127) / 128;   // tiles of 128 rows per segment
     constexpr int S_D = D / 64, S_NS = NS / 64;                                           // K slabs
 
-    if (warp == W_PROD) {
-        // ===================================================== PRODUCER: weight slabs, parameters and cross K/V, in consumer order
+    if (warp >= W_PROD && warp < W_MMA) {
+        // ===================================================== PRODUCERS: weight slabs, parameters and cross K/V, in consumer order;
+        // producer warp pw issues chunks n with n % NPROD == pw (every producer walks the whole schedule)
+        const uint32_t pw = (uint32_t)(warp - W_PROD);
         uint32_t n = 0, pl = 0;
         auto push = [&](const void* src, uint32_t bytes) {
-            const uint32_t slot = n % NSLOT;
-            if (n >= NSLOT) mbar_wait(empty + slot, ((n / NSLOT) - 1) & 1);
-            mbar_expect_tx(full + slot, bytes);
-            bulk_g2s(ring_mem + slot * SLOT, src, bytes, full + slot);
+            if (n % NPROD == pw) {
+                const uint32_t slot = n % NSLOT;
+                if (n >= NSLOT) mbar_wait(empty + slot, ((n / NSLOT) - 1) & 1);
+                mbar_expect_tx(full + slot, bytes);
+                bulk_g2s(ring_mem + slot * SLOT, src, bytes, full + slot);
+            }
             ++n;
         };
         for (int step = 0; step < a.n_steps; ++step) {
@@ -611,13 +619,13 @@ dec6_kernel(const Dec3Args a) {
                     const int T = __ldg(a.win_T + w);
                     const int per = (T + HS - 1) / HS, k_begin = min(T, hs * per), k_end = min(T, k_begin + per);
                     for (int l = 0; l < L; ++l) {
-                        {
+                        if (pw == 0) {
                             const uint32_t b = pl & 1, u = pl >> 1;
                             if (u >= 1) mbar_wait(pfree + b, (u - 1) & 1);
                             mbar_expect_tx(pfull + b, PARAMS * 4);
                             bulk_g2s(params + b * PARAMS, gparams + ((size_t)l * CS + rank) * PARAMS, PARAMS * 4, pfull + b);
-                            ++pl;
                         }
+                        ++pl;
                         const uint8_t* base = pack + ((size_t)l * CS + rank) * G::PACK;
                         auto seg = [&](int off, int n_chunks) {
                             for (int i = 0; i < n_chunks; ++i) push(base + off + (size_t)i * SLOT, SLOT);
@@ -643,6 +651,9 @@ dec6_kernel(const Dec3Args a) {
         // ===================================================== MMA warp: one thread issues every tcgen05.mma of the step
         Counters c{0, 0, 0};
         const uint32_t bxa = s32(bx);
+        unsigned long long* mtr = (a.trace && blockIdx.x == 0) ? a.trace + a.trace_cap / 2 : nullptr;   // second half of the trace buffer
+        int mtn = 0;
+        const int mcap = a.trace_cap / 2;
         for (int step = 0; step < a.n_steps; ++step) {
             if (lane == 0) {
                 for (int row = cluster_id; row < R; row += n_clusters) {
@@ -651,12 +662,12 @@ dec6_kernel(const Dec3Args a) {
                     const int per = (T + HS - 1) / HS, k_begin = min(T, hs * per), k_end = min(T, k_begin + per);
                     const uint32_t n_kv = (uint32_t)((k_end - k_begin + KPC - 1) / KPC);
                     for (int l = 0; l < L; ++l) {
-                        if (hs == 0) { c = gemv_mma6(P, c, T_QKV, S_D, bxa); c = gemv_mma6(P, c, T_D, 1, bxa); }
-                        c = gemv_mma6(P, c, T_CQ, S_D, bxa);
+                        if (hs == 0) { c = gemv_mma6(P, c, T_QKV, S_D, bxa, mtr, mtn, mcap); c = gemv_mma6(P, c, T_D, 1, bxa, mtr, mtn, mcap); }
+                        c = gemv_mma6(P, c, T_CQ, S_D, bxa, mtr, mtn, mcap);
                         c.n += n_kv;                       // K/V chunks are consumed by the attention warps
-                        c = gemv_mma6(P, c, T_D, 1, bxa);
-                        c = gemv_mma6(P, c, T_W1, S_D, bxa);
-                        c = gemv_mma6(P, c, T_D, S_NS, bxa);
+                        c = gemv_mma6(P, c, T_D, 1, bxa, mtr, mtn, mcap);
+                        c = gemv_mma6(P, c, T_W1, S_D, bxa, mtr, mtn, mcap);
+                        c = gemv_mma6(P, c, T_D, S_NS, bxa, mtr, mtn, mcap);
                     }
                 }
             }
@@ -676,7 +687,7 @@ dec6_kernel(const Dec3Args a) {
         const int gw = blockIdx.x * NCW + warp, n_gw = gridDim.x * NCW;
 
         auto trace = [&]() {
-            if (a.trace && blockIdx.x == 0 && tid == 0 && tr_n < a.trace_cap) a.trace[tr_n++] = gtime();
+            if (a.trace && blockIdx.x == 0 && tid == 0 && tr_n < a.trace_cap / 2) a.trace[tr_n++] = gtime();
         };
         // sends y_s[ph & 1] (D values + max, sum, active) to every CTA of the cluster
         auto send = [&]() {
@@ -778,6 +789,41 @@ dec6_kernel(const Dec3Args a) {
             }
             int stop = 0;
             if (want_logits) {
+                // ---- vocabulary tiles of this warp.  CTAs of clusters without a row have nothing to do until the rows are published:
+                // they take the first LG_NBUF half-tiles into their ring BEFORE the grid barrier (the embedding matrix does not depend on
+                // the activations), and their warps get `na` extra tiles each (stage A) so that the stream that remains after the
+                // barrier is spread evenly (stage B: round robin over all warps).
+                const int lg_g = lane >> 2, lg_t = lane & 3;
+                constexpr int KH = D / 2, NCH = KH / 32;
+                constexpr uint32_t BLKB = 16 * KH * 2;
+                constexpr int RINGW = NSLOT * SLOT / NCW;
+                static_assert(LG_NBUF * (int)BLKB <= RINGW, "logits ring");
+                const __half* Et = reinterpret_cast<const __half*>(a.E_tiled);
+                const int v_tiles = (V + 15) / 16;
+                const bool idle_cta = cluster_id >= R;
+                const int n_idle_w = max(0, n_clusters - R) * CS * NCW;
+                const int na = (n_idle_w > 0 && 2 * n_idle_w <= v_tiles) ? 2 : 0;
+                const int tiles_a = na * n_idle_w, tiles_b = v_tiles - tiles_a;
+                const int iw = ((cluster_id - R) * CS + rank) * NCW + warp;                 // index among the idle warps
+                const int my_a = idle_cta ? na : 0;
+                const int my_tiles = my_a + (gw < tiles_b ? (tiles_b - gw + n_gw - 1) / n_gw : 0);
+                const int total = my_tiles * 2;
+                auto tile_of = [&](int i) { return i < my_a ? iw + i * n_idle_w : tiles_a + gw + (i - my_a) * n_gw; };
+                uint8_t* wring = ring_mem + (size_t)warp * RINGW;
+                uint64_t* wbar = lg_bar + warp * LG_NBUF;
+                auto issue = [&](int it) {
+                    if (it < total && lane == 0) {
+                        const int vt = tile_of(it >> 1);
+                        const int slot = (int)((lg_count + (unsigned int)it) % LG_NBUF);
+                        mbar_expect_tx(wbar + slot, BLKB);
+                        bulk_g2s(wring + (size_t)slot * BLKB, Et + ((int64_t)vt * 2 + (it & 1)) * 16 * KH, BLKB, wbar + slot);
+                    }
+                };
+                if (idle_cta) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < LG_NBUF; ++j) issue(j);
+                }
                 // ---- the one grid barrier of the step: every row's x is published
                 trace();
                 if (tid == 0) {
@@ -795,7 +841,6 @@ dec6_kernel(const Dec3Args a) {
                 trace();
                 // ================= logits (all CTAs): LN(x) tok_emb^T + mask + online softmax + arg-max (mod.rs:155-156, transcribe.rs:271-276)
                 const bool use_mask = a.is_special != nullptr && (a.mask_mode == 1 || (a.mask_mode == 2 && p + 1 <= 5));
-                const __half* Et = reinterpret_cast<const __half*>(a.E_tiled);
                 // LayerNorm rows straight into fp16 hi / lo planes in MMA fragment order (decoder5.cu); rows >= R are zero
                 for (int r = warp; r < 8 * NT8; r += NCW) {
                     constexpr int NV = D / 128;   // float4 per lane
@@ -840,38 +885,21 @@ dec6_kernel(const Dec3Args a) {
                     // Swap-AB tensor-core product (decoder4.cu): a warp owns tiles of 16 vocabulary rows (M), 8 batch rows per n-tile
                     // (N), K = D; the matrix is streamed as contiguous half-tiles [16][D/2] (one bulk copy each) through this warp's
                     // share of the ring, LG_NBUF - 1 copies in flight.
-                    const int g = lane >> 2, t = lane & 3;
-                    constexpr int KH = D / 2, NCH = KH / 32;
-                    constexpr uint32_t BLKB = 16 * KH * 2;
-                    constexpr int RINGW = NSLOT * SLOT / NCW;
-                    static_assert(LG_NBUF * (int)BLKB <= RINGW, "logits ring");
-                    const int v_tiles = (V + 15) / 16;
-                    const int my_tiles = gw < v_tiles ? (v_tiles - gw + n_gw - 1) / n_gw : 0;
-                    const int total = my_tiles * 2;
-                    uint8_t* wring = ring_mem + (size_t)warp * RINGW;
-                    uint64_t* wbar = lg_bar + warp * LG_NBUF;
-                    auto issue = [&](int it) {
-                        if (it < total && lane == 0) {
-                            const int vt = gw + (it >> 1) * n_gw;
-                            const int slot = (int)((lg_count + (unsigned int)it) % LG_NBUF);
-                            mbar_expect_tx(wbar + slot, BLKB);
-                            bulk_g2s(wring + (size_t)slot * BLKB, Et + ((int64_t)vt * 2 + (it & 1)) * 16 * KH, BLKB, wbar + slot);
-                        }
-                    };
+                    const int g = lg_g, t = lg_t;
                     float m_run[NT8][2], s_run[NT8][2], bv[NT8][2];
                     int bi[NT8][2];
 #pragma unroll
                     for (int j = 0; j < NT8; ++j)
 #pragma unroll
                         for (int e = 0; e < 2; ++e) { m_run[j][e] = -INFINITY; s_run[j][e] = 0.0f; bv[j][e] = -INFINITY; bi[j][e] = INT_MAX; }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the ring was last written by bulk copies and read through the generic proxy
+                    if (!idle_cta) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the ring was last written by bulk copies and read through the generic proxy
 #pragma unroll
-                    for (int j = 0; j < LG_NBUF - 1; ++j) issue(j);
+                        for (int j = 0; j < LG_NBUF; ++j) issue(j);
+                    }
                     float ah[NT8][4], al[NT8][4];
 #pragma unroll 1
                     for (int it = 0; it < total; ++it) {
-                        __syncwarp();
-                        issue(it + LG_NBUF - 1);
                         const unsigned int cnt = lg_count + (unsigned int)it;
                         const int slot = (int)(cnt % LG_NBUF);
                         mbar_wait(wbar + slot, (cnt / LG_NBUF) & 1);
@@ -900,7 +928,7 @@ dec6_kernel(const Dec3Args a) {
                         }
                         if (half == 1) {
                             // C fragment: c0,c1 -> (vocabulary row g, batch rows 2t, 2t+1), c2,c3 -> (row g+8, same batch rows)
-                            const int n0 = (gw + (it >> 1) * n_gw) * 16;
+                            const int n0 = tile_of(it >> 1) * 16;
 #pragma unroll
                             for (int j = 0; j < NT8; ++j)
 #pragma unroll
@@ -917,6 +945,8 @@ dec6_kernel(const Dec3Args a) {
                                     }
                                 }
                         }
+                        __syncwarp();                 // every lane is done with the slot
+                        issue(it + LG_NBUF);
                     }
                     lg_count += (unsigned int)total;
                     trace();

@@ -64,7 +64,7 @@ Session::Session(Model* model, int64_t max_w, int64_t max_b, int64_t max_text_le
     logits.alloc((size_t)Rmax * V);
     tokens.alloc((size_t)Rmax * t_max); lengths.alloc(Rmax); cur_tok.alloc(Rmax); finished.alloc(Rmax);
     row_window.alloc(Rmax); anc0.alloc((size_t)Rmax * t_max); anc1.alloc((size_t)Rmax * t_max); parent.alloc(Rmax);
-    pos.alloc(1); n_unfinished.alloc(1);
+    pos.alloc(1); n_unfinished.alloc(128);
     topk_id.alloc((size_t)Rmax * kmax); topk_lp.alloc((size_t)Rmax * kmax);
     is_special.alloc(V);
     {
@@ -78,7 +78,7 @@ Session::Session(Model* model, int64_t max_w, int64_t max_b, int64_t max_text_le
         n_logit_ctas = 2 * prop.multiProcessorCount;
         // persistent decoder: per-layer pointer table, barrier words, larger split-KV partial buffers
         part_o.alloc((size_t)Rmax * H * 16 * 64); part_m.alloc((size_t)Rmax * H * 16); part_l.alloc((size_t)Rmax * H * 16);
-        datt.alloc((size_t)Rmax * d); steps_done.alloc(1); d3_bar.alloc(4);
+        datt.alloc((size_t)Rmax * d); steps_done.alloc(128); d3_bar.alloc(4);
         WB_CUDA(cudaMemsetAsync(d3_bar.p, 0, 4 * sizeof(unsigned int), st));
         { const char* e6 = getenv("WB200_DEC6"); use_dec6 = !(e6 && e6[0] == '0'); }
         {
@@ -467,6 +467,7 @@ void Session::launch_v3(int R_, int pos0, int n_steps, int logits_from, bool use
     }
     WB_CUDA(cudaMemsetAsync(d3_bar.p, 0, 4 * sizeof(unsigned int), st));   // monotonic barrier counters start at 0
     last_decoder = 3;
+    last_groups = 1;
     if (dec_version == 4) {
         // head-fused cluster decoder first (greedy, d = 128 / 384); its packed weight slices are built on first use
         if (use_dec6 && m->fp16_exact && greedy && k == 1 && !use_cur_tok && a.anc == nullptr && a.logits_out == nullptr && R_ <= 24 && ckv_hm &&
@@ -489,6 +490,32 @@ void Session::launch_v3(int R_, int pos0, int n_steps, int logits_from, bool use
         if (last_decoder == 3) {
             if (launch_dec4(a, m->fp16_exact, st)) last_decoder = 4;
             else if (launch_dec5(a, n_sm, m->fp16_exact, st)) last_decoder = 5;
+            else if (R_ > 32 && m->fp16_exact && d % 256 == 0 && d <= 1280 && k <= DEC_KC) {
+                // more rows than one launch of the batched tensor-core decoder takes (beams of many windows, BASELINE configs[4]:
+                // 48 windows x 5 beams per GPU): row groups of 32, one launch each on the session stream; rows are independent,
+                // ancestry entries stay absolute cache rows (a.kv_row0 = first cache row of the group)
+                bool ok = true;
+                int gi = 0;
+                for (int r0 = 0; r0 < R_ && ok; r0 += 32, ++gi) {
+                    const int Rg = std::min(32, R_ - r0);
+                    Dec3Args g = a;
+                    g.R = Rg; g.kv_row0 = r0;
+                    g.x += (int64_t)r0 * d; g.q += (int64_t)r0 * d; g.att += (int64_t)r0 * d; g.hid += (int64_t)r0 * 4 * d;
+                    g.row_window += r0;
+                    if (g.anc) g.anc += (int64_t)r0 * t_max;
+                    g.tokens += (int64_t)r0 * t_max; g.cur_tok += r0; g.lengths += r0; g.finished += r0;
+                    g.topk_id += (int64_t)r0 * k; g.topk_lp += (int64_t)r0 * k;
+                    if (g.logits_out) { g.logits_out += (int64_t)r0 * D.n_vocab; g.lgbuf = g.logits_out; }
+                    g.lg_slices = std::max(1, std::min(16, n_sm / std::max(1, Rg)));
+                    g.n_splits = std::max(1, std::min(16, n_sm / std::max(1, Rg * H)));
+                    g.steps_done = steps_done.p + std::min(gi, 127); g.n_unfinished = n_unfinished.p + std::min(gi, 127);
+                    WB_CUDA(cudaMemsetAsync(d3_bar.p, 0, 4 * sizeof(unsigned int), st));
+                    ok = launch_dec5(g, n_sm, true, st);
+                }
+                if (!ok) fail(WB_ERR_UNSUPPORTED, "decoder5 rejected a row group");
+                last_decoder = 5;
+                last_groups = gi;
+            }
         }
     }
     if (last_decoder == 3) launch_dec3(a, n_sm, m->fp16_exact, st);
@@ -498,7 +525,8 @@ void Session::launch_v3(int R_, int pos0, int n_steps, int logits_from, bool use
         WB_CUDA(cudaMemcpy(h.data(), d3_trace.p, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         FILE* f = fopen(getenv("WB200_TRACE"), "w");   // debugging aid: WB200_TRACE=<file> receives the stage time stamps of CTA 0
         if (f) {
-            for (size_t i = 0; i < h.size() && h[i]; ++i) fprintf(f, "%llu\n", h[i]);
+            for (size_t i = 0; i < h.size(); ++i)
+                if (h[i]) fprintf(f, "%llu\n", h[i]);   // decoder6.cu: first half = consumer stage stamps, second half = MMA-warp stamps (time << 2 | kind)
             fclose(f);
         }
     }
@@ -584,11 +612,13 @@ void Session::greedy_decode(const int64_t* prompt, int64_t prompt_len, int max_d
     const int n_steps = (int)prompt_len - 1 + max_depth;
     if (max_depth > 0) launch_v3(R, 0, n_steps, (int)prompt_len - 1, false, 2, 1, true, (int)eot);
     std::vector<int> tk((size_t)R * t_max), len((size_t)R);
-    int sd = 0;
+    int sdv[128] = {0};
     WB_CUDA(cudaMemcpyAsync(tk.data(), tokens.p, tk.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
     WB_CUDA(cudaMemcpyAsync(len.data(), lengths.p, len.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
-    if (max_depth > 0) WB_CUDA(cudaMemcpyAsync(&sd, steps_done.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (max_depth > 0) WB_CUDA(cudaMemcpyAsync(sdv, steps_done.p, sizeof(int) * std::min(last_groups, 128), cudaMemcpyDeviceToHost, st));
     WB_CUDA(cudaStreamSynchronize(st));
+    int sd = 0;
+    for (int g = 0; g < std::min(last_groups, 128); ++g) sd = std::max(sd, sdv[g]);   // row groups stop on their own
     last_steps = max_depth > 0 ? sd - ((int)prompt_len - 1) : 0;
     host_pos = (int)prompt_len - 1 + (int)last_steps;
     out.assign((size_t)R, {});

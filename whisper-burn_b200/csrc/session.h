@@ -71,6 +71,7 @@ struct Session {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float last_ms[4] = {0, 0, 0, 0};
     int64_t last_steps = 0;
+    int last_groups = 1;         // row groups (launches) of the last decode
     int last_decoder = 0;        // which persistent decoder the last launch used (6, 5, 4 or 3); 0 = none yet
     int dec_version = 4;         // 4 = best persistent decoder for the shape (decoder6 / decoder5 / decoder4), 3 = force the grid-barrier fallback (WB200_DECODER=3)
     int n_sm = 0;
