@@ -169,6 +169,7 @@ def test_tiny_en_cluster_decoder_one_chunk(tiny_en, kv, hs, monkeypatch):
     keys and MLP slices split, softmax merge on the receiving side)."""
     dims, sp, wh = tiny_en
     monkeypatch.setenv("WB200_DEC6_HS", hs)
+    monkeypatch.setenv("WB200_DEC6", "force")     # 3 rows are decoder4.cu's range by default
     waves, recs = _tiny_cases(kv, [0])
     sess = transcribe.Session(wh, max_windows=3, max_beams=1, max_text_len=105, kv_dtype=ffi.WB_KV_F16 if kv == "f16" else ffi.WB_KV_F32)
     got = sess.transcribe_windows(waves, sp, is_special_of(sp), beam_size=1, max_depth=100)
@@ -186,7 +187,8 @@ def test_tiny_en_cluster_decoder_8_chunks(tiny_en, kv):
     got = sess.transcribe_windows(waves, sp, is_special_of(sp), beam_size=1, max_depth=100)
     assert sess.last_decoder() == 6
     _check_ids_where_separated(got, recs)
-    # batching invariance: 7 windows (one n-tile, partially filled) give the same ids as inside the batch of 24
-    sess7 = transcribe.Session(wh, max_windows=7, max_beams=1, max_text_len=105, kv_dtype=ffi.WB_KV_F16 if kv == "f16" else ffi.WB_KV_F32)
-    got7 = sess7.transcribe_windows(waves[5:12], sp, is_special_of(sp), beam_size=1, max_depth=100)
-    _check_ids_where_separated(got7, recs[5:12])
+    # batching invariance: 9 windows (two n-tiles, the second partially filled) give the same ids as inside the batch of 24
+    sess9 = transcribe.Session(wh, max_windows=9, max_beams=1, max_text_len=105, kv_dtype=ffi.WB_KV_F16 if kv == "f16" else ffi.WB_KV_F32)
+    got9 = sess9.transcribe_windows(waves[5:14], sp, is_special_of(sp), beam_size=1, max_depth=100)
+    assert sess9.last_decoder() == 6
+    _check_ids_where_separated(got9, recs[5:14])

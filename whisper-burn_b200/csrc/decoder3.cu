@@ -423,14 +423,14 @@ template <typename WT, int RC, int KC, typename KVT>
 void launch_t(const Dec3Args& a, int n_ctas, cudaStream_t st) {
     const size_t smem = dec3_smem_bytes(a.d, a.H, a.n_splits, RC, KC);
     auto k = dec3_kernel<WT, RC, KC, KVT>;
-    static size_t configured = 0;   // per instantiation
-    if (configured != smem) {
+    static PerDeviceConfig cfg;   // per instantiation
+    cfg.ensure(smem, [&] {
         WB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
         WB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, NT, smem));
         if (per_sm < 1) fail(WB_ERR_UNSUPPORTED, "decoder megakernel does not fit on an SM");
-        configured = smem;
-    }
+        return true;
+    });
     void* args[] = {(void*)&a};
     WB_CUDA(cudaLaunchCooperativeKernel((void*)k, dim3(n_ctas), dim3(NT), args, smem, st));
     WB_LAUNCH_CHECK();

@@ -18,6 +18,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 
 #include "dec_common.cuh"
 
@@ -679,43 +680,69 @@ size_t dec4_smem() {
            (size_t)NW * std::max(LG_NBUF * LG_RB * D * 2, KV_STG * 8 * 128 * 4) + NW * LG_NBUF * 8 + NW * KV_STG * 8 + (size_t)2 * (D / 32) * 32 * 16 + 16;
 }
 
+struct LaunchState4 {
+    int clusters = 0;        // 0 unknown, > 0 co-resident clusters to launch, -1 unsupported
+    bool cooperative = true; // cooperative + cluster launch: the driver enforces the co-residency the grid barriers need
+};
+std::mutex g_mu4;
+
 template <int D, int RC, typename KVT>
 bool launch4_t(const Dec3Args& a, cudaStream_t st) {
     auto k = dec4_kernel<D, RC, KVT>;
     const size_t smem = dec4_smem<D, RC>();
-    static int state = 0;   // 0 unknown, >0 = number of co-resident clusters to launch, -1 unsupported
+    static LaunchState4 states[16];   // per device ordinal
+    int dev = 0;
+    WB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 16) return false;
+    std::lock_guard<std::mutex> lock(g_mu4);
+    LaunchState4& S = states[dev];
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((state > 0 ? state : 8) * CS);
     cfg.blockDim = dim3(NT);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CS;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeCooperative;
+    attr[1].val.cooperative = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    if (state == 0) {
+    if (S.clusters == 0) {
         if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
             cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
             cudaGetLastError();
-            state = -1;
+            S.clusters = -1;
             return false;
         }
         int n_clusters = 0;
+        cfg.gridDim = dim3(CS);
+        cfg.numAttrs = 1;
         const cudaError_t oe = cudaOccupancyMaxActiveClusters(&n_clusters, k, &cfg);
         if (getenv("WB200_VERBOSE")) fprintf(stderr, "[wb] dec4<D=%d,RC=%d>: smem %zu B, max active clusters %d (%s)\n", D, RC, smem, n_clusters, cudaGetErrorString(oe));
         if (oe != cudaSuccess || n_clusters < 1) {
             cudaGetLastError();
-            state = -1;
+            S.clusters = -1;
             return false;
         }
-        state = std::min(n_clusters, 8);   // every launched cluster must be co-resident (grid barriers); B200: 7 of size 16
-        cfg.gridDim = dim3(state * CS);
+        S.clusters = std::min(n_clusters, 8);   // every launched cluster must be co-resident (grid barriers); B200: 7 of size 16
     }
-    if (state < 0 || a.R > state) return false;
-    WB_CUDA(cudaLaunchKernelEx(&cfg, k, a));
+    if (S.clusters < 0 || a.R > S.clusters) return false;
+    cfg.gridDim = dim3(S.clusters * CS);
+    cudaError_t e = cudaErrorUnknown;
+    if (S.cooperative) {
+        cfg.numAttrs = 2;
+        e = cudaLaunchKernelEx(&cfg, k, a);
+        if (e != cudaSuccess) {   // cooperative + cluster rejected by this driver: plain cluster launch (co-residency from the occupancy query)
+            cudaGetLastError();
+            S.cooperative = false;
+        }
+    }
+    if (!S.cooperative) {
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, k, a);
+    }
+    WB_CUDA(e);
     WB_LAUNCH_CHECK();
     return true;
 }

@@ -845,17 +845,17 @@ template <int NT8, typename KVT>
 bool launch5_t(const Dec3Args& a, int n_ctas, cudaStream_t st) {
     const size_t smem = dec5_smem_bytes(a.d, NT8, a.L);
     auto k = dec5_kernel<NT8, KVT>;
-    static size_t configured = 0;   // per instantiation
-    if (configured != smem) {
+    static PerDeviceConfig cfg;   // per instantiation
+    const bool fits = cfg.ensure(smem, [&] {
         if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
             cudaGetLastError();
             return false;
         }
         int per_sm = 0;
         WB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, NT, smem));
-        if (per_sm < 1) return false;
-        configured = smem;
-    }
+        return per_sm >= 1;
+    });
+    if (!fits) return false;
     void* args[] = {(void*)&a};
     WB_CUDA(cudaLaunchCooperativeKernel((void*)k, dim3(n_ctas), dim3(NT), args, smem, st));
     WB_LAUNCH_CHECK();

@@ -49,8 +49,8 @@ namespace wb {
 namespace {
 
 constexpr int NCW = 8;                    // consumer warps (threads 0..255)
-constexpr int NPROD = 3;                  // producer warps: bulk copies of ONE issuing thread complete one after the other (measured ~0.45 us per 16 KB,
-                                          // i.e. 35 GB/s per SM whatever the ring depth); copies of different warps overlap
+constexpr int NPROD = 1;                  // producer warps (more than one issuing warp does not raise the stream rate: the tensor cores' shared-memory
+                                          // A-operand read, ~0.3 us per 16 KB slab, is what paces the ring; measured, profiles/r02_dec6_mma_trace.txt)
 constexpr int W_PROD = NCW, W_MMA = NCW + NPROD;
 constexpr int NTH6 = (NCW + NPROD + 1) * 32;      // + producer warps + MMA warp
 constexpr int SLOT = 16384;               // bytes per ring slot = one 128-row x 64-column fp16 slab
@@ -63,9 +63,10 @@ template <int D, int HS>
 struct Geo {
     static constexpr int H = D / 64, CS = H * HS, NS = 4 * D / CS, SEND = D + 4;
     static constexpr int pad128(int n) { return (n + 127) / 128 * 128; }
-    // packed weight segments of one (layer, rank), bytes: [tiles of 128 rows][K / 64 slabs][16 KB]
-    static constexpr int OFF_QKV = 0, OFF_O = OFF_QKV + pad128(192) * D * 2, OFF_CQ = OFF_O + pad128(D) * 64 * 2, OFF_CO = OFF_CQ + pad128(64) * D * 2,
-                         OFF_W1 = OFF_CO + pad128(D) * 64 * 2, OFF_W2 = OFF_W1 + pad128(NS) * D * 2, PACK = OFF_W2 + pad128(D) * NS * 2;
+    // packed weight segments of one (layer, rank), bytes: [tiles of 128 rows (the last one 64 rows when N % 128 == 64)][K / 64 slabs][rows x 128 B]
+    static constexpr int OFF_QKV = 0, OFF_O = OFF_QKV + 192 * D * 2, OFF_CQ = OFF_O + D * 64 * 2, OFF_CO = OFF_CQ + 64 * D * 2,
+                         OFF_W1 = OFF_CO + D * 64 * 2, OFF_W2 = OFF_W1 + NS * D * 2, PACK = OFF_W2 + D * NS * 2;
+    static_assert(D % 128 == 0 && NS % 128 == 0, "only the 192- and 64-row segments end in a 64-row tile");
     // parameter block of one (layer, rank), floats
     static constexpr int P_LN1G = 0, P_LN1B = D, P_LN2G = 2 * D, P_LN2B = 3 * D, P_LN3G = 4 * D, P_LN3B = 5 * D, P_BO = 6 * D,
                          P_BCO = 7 * D, P_B2 = 8 * D, P_BQKV = 9 * D, P_BCQ = 9 * D + 192, P_B1 = 9 * D + 256, P_EPS = 9 * D + 256 + NS, PARAMS = 9 * D + 256 + NS + 4;
@@ -113,6 +114,38 @@ __device__ __forceinline__ float group8_sum(float v) {   // sum over the 8 lanes
 // ---- tcgen05 (see gemm_f16.cu for the same descriptors in a GEMM) ------------------------------------------------------------
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
+}
+// the MMA thread polls without reading the clock on every probe (a probe of a pending barrier suspends the thread for a while
+// in hardware, so 2^26 failed probes are many seconds): fail loudly instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait_lean(uint64_t* bar, uint32_t parity) {
+    const uint32_t b = s32(bar);
+#pragma unroll 1
+    for (int i = 0; i < (1 << 26); ++i) {
+        uint32_t done;
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(b), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void umma_f16_first(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {   // D = A * B
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, 0, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_c),
+        "l"(desc_a), "l"(desc_b), "r"(idesc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_acc(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {     // D += A * B
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.eq.b32 p, 0, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_c),
+        "l"(desc_a), "l"(desc_b), "r"(idesc)
+        : "memory");
 }
 __device__ __forceinline__ void umma_f16(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -191,9 +224,9 @@ struct Softmax8 {   // online softmax state of one (warp, rg) key slot; o = the 
 
 // ---- weight / parameter packing (once per session) ---------------------------------------------------------------------
 // Segment [N][K] (fp16, source rows n0 + (r / piece) * piece_stride + r % piece, columns k0 .. k0 + K of a [.][ldk] matrix) as
-// tiles of 128 rows (zero-padded), each tile as K / 64 slabs of 16 KB in the K-major 128B-swizzled shared-memory image:
-// 16-byte unit (row r, chunk c) of a slab at r * 128 + ((c ^ (r & 7)) << 4).  A slab is what one bulk copy moves and what one
-// group of four tcgen05.mma (K = 16 each) reads.
+// tiles of 128 rows (a last tile of 64 rows when N % 128 == 64), each tile as K / 64 slabs of rows x 128 B in the K-major
+// 128B-swizzled shared-memory image: 16-byte unit (row r, chunk c) of a slab at r * 128 + ((c ^ (r & 7)) << 4).  A slab is what
+// one bulk copy moves and what one group of four tcgen05.mma (M = 128 or 64, K = 16 each) reads.
 struct PackSeg {
     const __half* src;
     int ldk, n0, k0, N, K;
@@ -203,20 +236,19 @@ struct PackSeg {
 __global__ void dec6_pack_kernel(const PackSeg* segs, int n_segs, uint8_t* dst) {
     for (int s = blockIdx.y; s < n_segs; s += gridDim.y) {
         const PackSeg g = segs[s];
-        const int nslab = g.K / 64, ntile = (g.N + 127) / 128;
-        const int64_t n16 = (int64_t)ntile * nslab * 1024;   // 16-byte units
+        const int nslab = g.K / 64;
+        const int64_t n16 = (int64_t)g.N * g.K / 8;   // 16-byte units; N is a multiple of 64
         for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) {
-            const int c = (int)(i & 7), r = (int)((i >> 3) & 127);
-            const int64_t ts = i >> 10;
-            const int sl = (int)(ts % nslab), t = (int)(ts / nslab);
-            const int row = t * 128 + r;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (row < g.N) {
-                const int srow = g.n0 + (row / g.piece) * g.piece_stride + row % g.piece;
-                v = *reinterpret_cast<const uint4*>(g.src + (int64_t)srow * g.ldk + g.k0 + sl * 64 + c * 8);
-            }
-            *reinterpret_cast<uint4*>(dst + g.dst_off + ts * SLOT + r * 128 + ((c ^ (r & 7)) << 4)) = v;
+            // source order: unit i = (row, column chunk)
+            const int row = (int)(i / (g.K / 8)), cc = (int)(i % (g.K / 8));
+            const int t = row >> 7, r = row & 127, sl = cc >> 3, c = cc & 7;
+            const int trows = min(128, g.N - t * 128);                       // rows of this tile: 128 or 64
+            const int64_t tile_base = (int64_t)t * 128 * g.K * 2;            // full tiles precede
+            const int srow = g.n0 + (row / g.piece) * g.piece_stride + row % g.piece;
+            const uint4 v = *reinterpret_cast<const uint4*>(g.src + (int64_t)srow * g.ldk + g.k0 + cc * 8);
+            *reinterpret_cast<uint4*>(dst + g.dst_off + tile_base + (int64_t)sl * trows * 128 + r * 128 + ((c ^ (r & 7)) << 4)) = v;
         }
+        (void)nslab;
     }
 }
 struct ParamSeg {
@@ -288,8 +320,10 @@ __device__ __noinline__ Counters gemv_epi6(const Pipe P, Counters c, int N, int 
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(P.acc_free + g);                 // 4 warps: the accumulator may be overwritten
-        const int row = t * 128 + (warp & 3) * 32 + lane;
-        if (row < N) {
+        // M = 128: TMEM lane = tile row; M = 64 (last tile of a 192- / 64-row segment): the 64 rows sit in lanes 0..15 of each quadrant
+        const bool half_tile = N - t * 128 < 128;
+        const int row = t * 128 + (half_tile ? (warp & 3) * 16 + lane : (warp & 3) * 32 + lane);
+        if (row < N && (!half_tile || lane < 16)) {
             const float s = fmaf(__uint_as_float(r1), 1.0f / 2048.0f, __uint_as_float(r0));
             if (o.mode == EM_PLAIN) {
                 o.out[row] = s;
@@ -317,27 +351,32 @@ __device__ __noinline__ Counters gemv_epi6(const Pipe P, Counters c, int N, int 
 }
 
 // MMA warp (one thread): the tensor-core side of the same linear layer
-__device__ __forceinline__ Counters gemv_mma6(const Pipe P, Counters c, int n_tiles, int n_slabs, uint32_t bx_addr, unsigned long long* tr, int& tn, int tcap) {
-    // instruction descriptor: D = F32 (1 << 4), A = B = F16 (format 0), K-major both, N >> 3 = 2 at bit 17, M >> 4 = 8 at bit 24
-    constexpr uint32_t idesc = (1u << 4) | (2u << 17) | (8u << 24);
-    mbar_wait(P.b_ready, c.gemv & 1);
+__device__ __forceinline__ Counters gemv_mma6(const Pipe P, Counters c, int N, int n_slabs, uint32_t bx_addr, unsigned long long* tr, int& tn, int tcap) {
+    // instruction descriptor: D = F32 (1 << 4), A = B = F16 (format 0), K-major both, N >> 3 = 2 at bit 17, M >> 4 at bit 24
+    const int n_tiles = (N + 127) >> 7;
+    const uint64_t desc_ring0 = make_smem_desc(s32(P.ring)), desc_bx0 = make_smem_desc(bx_addr);
+    mbar_wait_lean(P.b_ready, c.gemv & 1);
     if (tr && tn < tcap) tr[tn++] = (gtime() << 2) | 1ull;   // debug trace: B operand ready
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
     for (int t = 0; t < n_tiles; ++t) {
         const uint32_t T = c.tile, g = T & 1, u = T >> 1;
-        if (u >= 1) mbar_wait(P.acc_free + g, (u - 1) & 1);
+        const uint32_t idesc = (1u << 4) | (2u << 17) | ((uint32_t)(min(128, N - t * 128) >> 4) << 24);
+        if (u >= 1) mbar_wait_lean(P.acc_free + g, (u - 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
         for (int s = 0; s < n_slabs; ++s) {
             const uint32_t slot = c.n % NSLOT;
-            mbar_wait(P.full + slot, (c.n / NSLOT) & 1);
+            mbar_wait_lean(P.full + slot, (c.n / NSLOT) & 1);
             if (tr && tn < tcap) tr[tn++] = (gtime() << 2) | 2ull;   // debug trace: slab landed
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint64_t da = make_smem_desc(s32(P.ring + slot * SLOT)), db = make_smem_desc(bx_addr + (uint32_t)s * BX_SLAB);
-#pragma unroll
-            for (int k = 0; k < 4; ++k)   // UMMA_K = 16 halves = 32 bytes -> +2 in the (>> 4) address field
-                umma_f16(P.tmem + g * 16, da + 2 * k, db + 2 * k, idesc, (s | k) != 0 ? 1u : 0u);
+            // descriptors: ring slots are SLOT apart, B slabs BX_SLAB apart (address field = bytes >> 4)
+            const uint64_t da = desc_ring0 + (uint64_t)(slot * (SLOT >> 4)), db = desc_bx0 + (uint64_t)(s * (BX_SLAB >> 4));
+            const uint32_t acc = P.tmem + g * 16;
+            if (s == 0) umma_f16_first(acc, da, db, idesc); else umma_f16_acc(acc, da, db, idesc);
+            umma_f16_acc(acc, da + 2, db + 2, idesc);   // UMMA_K = 16 halves = 32 bytes -> +2 in the (>> 4) address field
+            umma_f16_acc(acc, da + 4, db + 4, idesc);
+            umma_f16_acc(acc, da + 6, db + 6, idesc);
             umma_commit(P.empty + slot);   // the slab may be overwritten when these MMAs have read it
             ++c.n;
         }
@@ -476,7 +515,9 @@ __device__ __noinline__ void self_attn6(const float* qkv_s, const KVT* kbase, co
 
 // cross attention of one head over keys [k_begin, k_end) of the window (mod.rs:482-490), the head-major K/V block arriving through
 // the ring in chunks of KPC keys; 8 lanes per key.  A slot is released by the LAST of the 8 warps to finish with it (the slots'
-// empty barriers take one arrival, as tcgen05.commit gives them for weight slabs).  Returns the ring counter.
+// empty barriers take one arrival, as tcgen05.commit gives them for weight slabs).  (Waiting for several chunks at once to batch
+// the per-key latency chains was measured SLOWER, 6 -> 12 us per layer: the chunks arrive one per ~0.3 us and the batch waits for
+// the last one.)  Returns the ring counter.
 template <typename KVT>
 __device__ __noinline__ uint32_t cross_attn6(const Pipe P, uint32_t n, int* slot_cnt, const float* q2_s, int k_begin, int k_end, float* wm, float* wl, float* wo) {
     constexpr int ROWB = 128 * (int)sizeof(KVT), KPC = SLOT / ROWB;
@@ -595,8 +636,7 @@ dec6_kernel(const Dec3Args a) {
 
     const uint8_t* pack = reinterpret_cast<const uint8_t*>(a.d6_pack);
     const float* gparams = a.d6_params;
-    constexpr int T_QKV = 2, T_D = (D + 127) / 128, T_CQ = 1, T_W1 = (NS + 127) / 128;   // tiles of 128 rows per segment
-    constexpr int S_D = D / 64, S_NS = NS / 64;                                           // K slabs
+    constexpr int S_D = D / 64, S_NS = NS / 64;   // K slabs of a linear layer
 
     if (warp >= W_PROD && warp < W_MMA) {
         // ===================================================== PRODUCERS: weight slabs, parameters and cross K/V, in consumer order;
@@ -627,19 +667,23 @@ dec6_kernel(const Dec3Args a) {
                         }
                         ++pl;
                         const uint8_t* base = pack + ((size_t)l * CS + rank) * G::PACK;
-                        auto seg = [&](int off, int n_chunks) {
-                            for (int i = 0; i < n_chunks; ++i) push(base + off + (size_t)i * SLOT, SLOT);
+                        auto seg = [&](int off, int N, int K) {   // tiles of 128 rows (last one 64), K / 64 slabs each, one bulk copy per slab
+                            const uint8_t* src = base + off;
+                            for (int r0 = 0; r0 < N; r0 += 128) {
+                                const uint32_t bytes = (uint32_t)min(128, N - r0) * 128;
+                                for (int sl = 0; sl < K / 64; ++sl, src += bytes) push(src, bytes);
+                            }
                         };
-                        if (hs == 0) { seg(G::OFF_QKV, T_QKV * S_D); seg(G::OFF_O, T_D * 1); }
-                        seg(G::OFF_CQ, T_CQ * S_D);
+                        if (hs == 0) { seg(G::OFF_QKV, 192, D); seg(G::OFF_O, D, 64); }
+                        seg(G::OFF_CQ, 64, D);
                         {
                             const KVT* kv = reinterpret_cast<const KVT*>(a.ckv) + (size_t)l * a.Mcap * 2 * D + __ldg(a.win_row_off + w) * (int64_t)(2 * D) +
                                             ((int64_t)h * T + k_begin) * 128;
                             for (int k0 = k_begin; k0 < k_end; k0 += KPC) push(kv + (int64_t)(k0 - k_begin) * 128, (uint32_t)(min(KPC, k_end - k0) * ROWB));
                         }
-                        seg(G::OFF_CO, T_D * 1);
-                        seg(G::OFF_W1, T_W1 * S_D);
-                        seg(G::OFF_W2, T_D * S_NS);
+                        seg(G::OFF_CO, D, 64);
+                        seg(G::OFF_W1, NS, D);
+                        seg(G::OFF_W2, D, NS);
                     }
                 }
             }
@@ -662,12 +706,12 @@ dec6_kernel(const Dec3Args a) {
                     const int per = (T + HS - 1) / HS, k_begin = min(T, hs * per), k_end = min(T, k_begin + per);
                     const uint32_t n_kv = (uint32_t)((k_end - k_begin + KPC - 1) / KPC);
                     for (int l = 0; l < L; ++l) {
-                        if (hs == 0) { c = gemv_mma6(P, c, T_QKV, S_D, bxa, mtr, mtn, mcap); c = gemv_mma6(P, c, T_D, 1, bxa, mtr, mtn, mcap); }
-                        c = gemv_mma6(P, c, T_CQ, S_D, bxa, mtr, mtn, mcap);
+                        if (hs == 0) { c = gemv_mma6(P, c, 192, S_D, bxa, mtr, mtn, mcap); c = gemv_mma6(P, c, D, 1, bxa, mtr, mtn, mcap); }
+                        c = gemv_mma6(P, c, 64, S_D, bxa, mtr, mtn, mcap);
                         c.n += n_kv;                       // K/V chunks are consumed by the attention warps
-                        c = gemv_mma6(P, c, T_D, 1, bxa, mtr, mtn, mcap);
-                        c = gemv_mma6(P, c, T_W1, S_D, bxa, mtr, mtn, mcap);
-                        c = gemv_mma6(P, c, T_D, S_NS, bxa, mtr, mtn, mcap);
+                        c = gemv_mma6(P, c, D, 1, bxa, mtr, mtn, mcap);
+                        c = gemv_mma6(P, c, NS, S_D, bxa, mtr, mtn, mcap);
+                        c = gemv_mma6(P, c, D, S_NS, bxa, mtr, mtn, mcap);
                     }
                 }
             }
@@ -693,10 +737,9 @@ dec6_kernel(const Dec3Args a) {
         auto send = [&]() {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             bar_consumers();
-            if (tid == 0) {
+            if (tid < CS) {   // one issuing thread per destination
                 const uint32_t b = ph & 1;
-#pragma unroll 1
-                for (int dst = 0; dst < CS; ++dst) bulk_s2peer(part + (b * CS + rank) * SEND, y_s + b * SEND, SEND * 4, pbar + b, (uint32_t)dst);
+                bulk_s2peer(part + (b * CS + rank) * SEND, y_s + b * SEND, SEND * 4, pbar + b, (uint32_t)tid);
             }
         };
         auto combine = [&](int mode, const float* bias) {
@@ -791,7 +834,7 @@ dec6_kernel(const Dec3Args a) {
             if (want_logits) {
                 // ---- vocabulary tiles of this warp.  CTAs of clusters without a row have nothing to do until the rows are published:
                 // they take the first LG_NBUF half-tiles into their ring BEFORE the grid barrier (the embedding matrix does not depend on
-                // the activations), and their warps get `na` extra tiles each (stage A) so that the stream that remains after the
+                // the activations), and their warps get `na` extra tile each (stage A) so that the stream that remains after the
                 // barrier is spread evenly (stage B: round robin over all warps).
                 const int lg_g = lane >> 2, lg_t = lane & 3;
                 constexpr int KH = D / 2, NCH = KH / 32;
@@ -802,7 +845,7 @@ dec6_kernel(const Dec3Args a) {
                 const int v_tiles = (V + 15) / 16;
                 const bool idle_cta = cluster_id >= R;
                 const int n_idle_w = max(0, n_clusters - R) * CS * NCW;
-                const int na = (n_idle_w > 0 && 2 * n_idle_w <= v_tiles) ? 2 : 0;
+                const int na = (n_idle_w > 0 && 2 * n_idle_w <= v_tiles) ? 1 : 0;   // = what an idle warp has in its ring when the barrier opens
                 const int tiles_a = na * n_idle_w, tiles_b = v_tiles - tiles_a;
                 const int iw = ((cluster_id - R) * CS + rank) * NCW + warp;                 // index among the idle warps
                 const int my_a = idle_cta ? na : 0;
@@ -1234,7 +1277,9 @@ int dec6_pick_hs(int d, int R) {
     const char* e = getenv("WB200_DEC6_HS");
     if (e && (e[0] == '1' || e[0] == '2')) return e[0] - '0';
     (void)d;
-    return R <= 8 ? 2 : 1;   // few rows: two CTAs per head (keys and MLP slices split), more SMs per row
+    (void)R;
+    return 1;   // one CTA per head; WB200_DEC6_HS=2 selects the two-CTAs-per-head shape (keys and MLP slices split) for <= 8 rows:
+                // measured 150 vs 178 us per position at 3 rows, both behind decoder4.cu's 131 us, which therefore keeps <= 7 rows
 }
 
 void dec6_build_pack(int d, int hs, const std::vector<Dec6LayerSrc>& layers, DevBuf<uint8_t>& pack, DevBuf<float>& params, cudaStream_t st) {

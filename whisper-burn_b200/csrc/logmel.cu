@@ -193,11 +193,11 @@ __global__ void chan_to_rows_kernel(const float* __restrict__ chan, float* __res
 
 void launch_logmel(const Model& m, const float* wave, const LogMelWindow* win_dev, int n_windows, int max_frames,
                    float* mel_rows, int* max_slots, int n_slots, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceConfig cfg;
+    cfg.ensure(LOGMEL_SMEM, [&] {
         WB_CUDA(cudaFuncSetAttribute(logmel_raw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LOGMEL_SMEM));
-        attr_set = true;
-    }
+        return true;
+    });
     WB_CUDA(cudaMemsetAsync(max_slots, 0x80, sizeof(int) * n_slots, st));   // very negative ordered key
     dim3 grid((max_frames + FR - 1) / FR, n_windows);
     logmel_raw_kernel<<<grid, LOGMEL_THREADS, LOGMEL_SMEM, st>>>(wave, win_dev, m.basis_t, m.mel_filt, m.mel_range,

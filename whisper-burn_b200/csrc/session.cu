@@ -80,7 +80,7 @@ Session::Session(Model* model, int64_t max_w, int64_t max_b, int64_t max_text_le
         part_o.alloc((size_t)Rmax * H * 16 * 64); part_m.alloc((size_t)Rmax * H * 16); part_l.alloc((size_t)Rmax * H * 16);
         datt.alloc((size_t)Rmax * d); steps_done.alloc(128); d3_bar.alloc(4);
         WB_CUDA(cudaMemsetAsync(d3_bar.p, 0, 4 * sizeof(unsigned int), st));
-        { const char* e6 = getenv("WB200_DEC6"); use_dec6 = !(e6 && e6[0] == '0'); }
+        { const char* e6 = getenv("WB200_DEC6"); use_dec6 = !(e6 && e6[0] == '0'); force_dec6 = e6 && e6[0] == 'f'; }
         {
             const bool h16 = m->fp16_exact;
             auto wp = [&](const LinearW& w) -> const void* { return h16 ? (const void*)w.w16 : (const void*)w.w32; };
@@ -469,8 +469,11 @@ void Session::launch_v3(int R_, int pos0, int n_steps, int logits_from, bool use
     last_decoder = 3;
     last_groups = 1;
     if (dec_version == 4) {
-        // head-fused cluster decoder first (greedy, d = 128 / 384); its packed weight slices are built on first use
-        if (use_dec6 && m->fp16_exact && greedy && k == 1 && !use_cur_tok && a.anc == nullptr && a.logits_out == nullptr && R_ <= 24 && ckv_hm &&
+        // <= 7 rows: the cluster/DSMEM decoder (decoder4.cu, 131 us per position at 3 rows); 8..24 rows (batched chunks of the small
+        // models): the head-fused tcgen05 cluster decoder (decoder6.cu), whose packed weight slices are built on first use.
+        // WB200_DEC6=force sends the small batches through decoder6.cu too (tests, A/B runs).
+        if (!force_dec6 && launch_dec4(a, m->fp16_exact, st)) last_decoder = 4;
+        if (last_decoder == 3 && use_dec6 && m->fp16_exact && greedy && k == 1 && !use_cur_tok && a.anc == nullptr && a.logits_out == nullptr && R_ <= 24 && ckv_hm &&
             t_max <= 128 && dec6_supported(d, H)) {
             const int hs = dec6_pick_hs(d, R_);
             if (d6_pack[hs].p == nullptr) {

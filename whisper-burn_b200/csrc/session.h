@@ -78,7 +78,8 @@ struct Session {
     DevBuf<Dec3Layer> d3_layers;
     DevBuf<uint8_t> d6_pack[3];     // decoder6.cu packed weight slices, index = CTAs per head (1, 2), built on first use
     DevBuf<float> d6_params[3];
-    bool use_dec6 = true;           // WB200_DEC6=0 disables the head-fused cluster decoder (A/B against decoder4.cu)
+    bool use_dec6 = true;           // WB200_DEC6=0 disables the head-fused cluster decoder
+    bool force_dec6 = false;        // WB200_DEC6=force: also for <= 7 rows (decoder4.cu's range)
     DevBuf<unsigned int> d3_bar;
     DevBuf<int> steps_done;
     DevBuf<float> datt;

@@ -7,6 +7,7 @@
 #include <stdint.h>
 
 #include <map>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -44,6 +45,25 @@ extern thread_local int64_t g_launch_count;
         ++::wb::g_launch_count;               \
         WB_CUDA(cudaPeekAtLastError());       \
     } while (0)
+
+// ---- per-device launch configuration cache -----------------------------------------------------
+// cudaFuncSetAttribute / occupancy results belong to a DEVICE: one slot per device ordinal, guarded by a mutex
+// (a process may create models on several devices and sessions from several host threads).
+struct PerDeviceConfig {
+    std::mutex mu;
+    size_t value[16] = {};
+    // runs configure() when the current device has not been configured for `want` yet; returns what configure() returned
+    template <typename F>
+    bool ensure(size_t want, F&& configure) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return configure();
+        std::lock_guard<std::mutex> lock(mu);
+        if (value[dev] == want) return true;
+        if (!configure()) return false;
+        value[dev] = want;
+        return true;
+    }
+};
 
 // ---- device buffer ----------------------------------------------------------------------
 template <typename T>
