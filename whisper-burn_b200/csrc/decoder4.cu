@@ -161,18 +161,31 @@ __device__ __forceinline__ void bcast(cg::cluster_group& cl, float* local, float
 // LayerNorm of one row held in shared memory (burn 0.9 form) by the whole CTA: thread t owns elements t, t+NT.
 // If delta != null the row is first updated in place (x += delta).  gamma/beta are fetched before the
 // reductions so their latency is hidden.  red: [2*NW] floats of scratch.  Ends with a __syncthreads().
+// gamma / beta of the LayerNorm that follows the NEXT cluster barrier: fetched before the barrier like the weight rows (the
+// barrier flushes L1, so afterwards they would cost an L2 round trip on the critical path)
 template <int D>
-__device__ __forceinline__ void ln_block(float* x_s, const float* delta_s, float* out_s, const float* __restrict__ g,
-                                         const float* __restrict__ b, float eps, int eps_outside, float* red) {
+struct LnRegs {
+    float g[(D + NT - 1) / NT], b[(D + NT - 1) / NT];
+    float eps;
+};
+template <int D>
+__device__ __forceinline__ void ln_prefetch(const float* __restrict__ g, const float* __restrict__ b, float eps, LnRegs<D>& r) {
+#pragma unroll
+    for (int i = 0; i < (D + NT - 1) / NT; ++i) {
+        const int c = threadIdx.x + i * NT;
+        r.g[i] = c < D ? __ldg(g + c) : 0.0f;
+        r.b[i] = c < D ? __ldg(b + c) : 0.0f;
+    }
+    r.eps = eps;
+}
+template <int D>
+__device__ __forceinline__ void ln_block(float* x_s, const float* delta_s, float* out_s, const LnRegs<D>& P, int eps_outside, float* red) {
     constexpr int PT = (D + NT - 1) / NT;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    float xv[PT], gv[PT], bv[PT];
-#pragma unroll
-    for (int i = 0; i < PT; ++i) {
-        const int c = tid + i * NT;
-        gv[i] = c < D ? __ldg(g + c) : 0.0f;
-        bv[i] = c < D ? __ldg(b + c) : 0.0f;
-    }
+    const float eps = P.eps;
+    float xv[PT];
+    const float (&gv)[PT] = P.g;
+    const float (&bv)[PT] = P.b;
     float s = 0.0f;
 #pragma unroll
     for (int i = 0; i < PT; ++i) {
@@ -279,13 +292,15 @@ dec4_kernel(const Dec3Args a) {
             for (int c = tid; c < D; c += NT) x_s[c] = __fadd_rn(__ldg(a.tok_emb + (int64_t)tok * D + c), __ldg(a.pos_emb + (int64_t)p * D + c));
             RowRegs<NR_QKV, VPL> w_qkv;
             load_rows<NR_QKV, VPL>(reinterpret_cast<const __half*>(a.layers[0].Wqkv), a.layers[0].bqkv, D, rank * (3 * D / CS) + warp, NW, w_qkv);
+            LnRegs<D> ln1;
+            ln_prefetch<D>(a.layers[0].ln1_g, a.layers[0].ln1_b, a.layers[0].ln1_eps, ln1);
             __syncthreads();
             for (int l = 0; l < L; ++l) {
                 const Dec3Layer& W = a.layers[l];
                 KVT* kcl = reinterpret_cast<KVT*>(a.kc) + (size_t)l * a.Rmax * t_max * D;
                 KVT* vcl = reinterpret_cast<KVT*>(a.vc) + (size_t)l * a.Rmax * t_max * D;
                 // ================= S1: q | k | v = LN1(x) Wqkv + b
-                ln_block<D>(x_s, l > 0 ? dl_s : nullptr, xn_s, W.ln1_g, W.ln1_b, W.ln1_eps, a.eps_outside, wm);   // l > 0: += MLP2 of the previous layer
+                ln_block<D>(x_s, l > 0 ? dl_s : nullptr, xn_s, ln1, a.eps_outside, wm);   // l > 0: += MLP2 of the previous layer
                 {
                     float acc[NR_QKV];
                     dot_rows1<NR_QKV, VPL, false>(w_qkv, xn_s, D, acc);
@@ -338,10 +353,12 @@ dec4_kernel(const Dec3Args a) {
                 }
                 RowRegs<NR_D, VPL> w_cq;
                 load_rows<NR_D, VPL>(reinterpret_cast<const __half*>(W.Wcq), W.bcq, D, rank * (D / CS) + warp, NW, w_cq);
+                LnRegs<D> ln23;
+                ln_prefetch<D>(W.ln2_g, W.ln2_b, W.ln2_eps, ln23);
                 cl.sync();
                 WB_TRACE();
                 // ================= S4: x += delta; cross query = LN2(x) Wcq + b
-                ln_block<D>(x_s, dl_s, xn_s, W.ln2_g, W.ln2_b, W.ln2_eps, a.eps_outside, wm);
+                ln_block<D>(x_s, dl_s, xn_s, ln23, a.eps_outside, wm);
                 {
                     float acc[NR_D];
                     dot_rows1<NR_D, VPL>(w_cq, xn_s, D, acc);
@@ -435,10 +452,11 @@ dec4_kernel(const Dec3Args a) {
                 }
                 RowRegs<NR_H, VPL> w_1;
                 load_rows<NR_H, VPL>(reinterpret_cast<const __half*>(W.W1), W.b1, D, rank * (4 * D / CS) + warp, NW, w_1);
+                ln_prefetch<D>(W.ln3_g, W.ln3_b, W.ln3_eps, ln23);
                 cl.sync();
                 WB_TRACE();
                 // ================= S7: x += delta; hid = gelu(LN3(x) W1 + b1)
-                ln_block<D>(x_s, dl_s, xn_s, W.ln3_g, W.ln3_b, W.ln3_eps, a.eps_outside, wm);
+                ln_block<D>(x_s, dl_s, xn_s, ln23, a.eps_outside, wm);
                 {
                     float acc[NR_H];
                     dot_rows1<NR_H, VPL, false>(w_1, xn_s, D, acc);
@@ -465,8 +483,10 @@ dec4_kernel(const Dec3Args a) {
                         bcast(cl, dl_s + n, __fadd_rn(acc[i], w_2.bias[i]));
                     }
                 }
-                if (l + 1 < L)
+                if (l + 1 < L) {
                     load_rows<NR_QKV, VPL>(reinterpret_cast<const __half*>(a.layers[l + 1].Wqkv), a.layers[l + 1].bqkv, D, rank * (3 * D / CS) + warp, NW, w_qkv);
+                    ln_prefetch<D>(a.layers[l + 1].ln1_g, a.layers[l + 1].ln1_b, a.layers[l + 1].ln1_eps, ln1);
+                }
                 cl.sync();
                 WB_TRACE();
             }

@@ -14,7 +14,7 @@
 //
 // Kernel shape (one 128 x BN output tile per CTA, 192 threads):
 //   warp 0      TMA producer: cp.async.bulk.tensor (3-D maps: k, row, window) of A_hi, A_lo (128 x 64 halves each) and B
-//               (BN x 64) into a 4-stage 128B-swizzled ring, mbarrier expect_tx / complete_tx
+//               (BN x 64) into a 2-stage 128B-swizzled ring, mbarrier expect_tx / complete_tx (two CTAs per SM: four stages in flight)
 //   warp 1      TMEM allocation (2 * BN columns) + single-thread tcgen05.mma issue (UMMA 128 x BN x 16, 4 + 4 per k-block),
 //               tcgen05.commit releases ring slots and finally signals the epilogue
 //   warps 2-5   epilogue: tcgen05.ld (32 lanes x 16 columns, both accumulators) -> bias / GELU / q,k scale / pos-emb /
@@ -33,7 +33,8 @@ namespace wb {
 
 namespace {
 
-constexpr int F_BM = 128, F_BK = 64, F_STAGES = 4;
+constexpr int F_BM = 128, F_BK = 64, F_STAGES = 2;   // 2 stages x 48 KB: TWO CTAs per SM (2 x 256 TMEM columns), so one tile's epilogue
+                                                     // (TMEM -> registers -> GELU -> global) overlaps the other's TMA / MMA main loop
 constexpr int F_THREADS = 192;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -106,7 +107,7 @@ struct F16Args {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(F_THREADS, 1)
+__global__ void __launch_bounds__(F_THREADS, 2)
 gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                    const __grid_constant__ CUtensorMap map_b, const F16Args g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
