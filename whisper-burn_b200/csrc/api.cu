@@ -1,7 +1,9 @@
 // extern "C" boundary (include/whisper_b200.h).  No exceptions cross it: every entry point maps
 // wb::Error / std::exception to a status code and a thread-local message.
 #include <cstring>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <new>
 
 #include "../host/beam.hpp"
@@ -9,6 +11,18 @@
 
 struct wb_model {
     wb::Model impl;
+    // the stateless entry points (wb_forward_encoder / wb_forward_decoder) keep ONE session between calls instead of paying
+    // dozens of cudaMalloc per call; it is rebuilt only when a call needs more windows or positions than it holds
+    std::mutex fwd_mu;
+    std::unique_ptr<wb::Session> fwd;
+    wb::Session& forward_session(int64_t n_windows, int64_t text_len) {
+        if (!fwd || fwd->max_windows < n_windows || fwd->t_max < text_len) {
+            fwd.reset();
+            fwd.reset(new wb::Session(&impl, std::max<int64_t>(n_windows, 1), 1, std::max<int64_t>(text_len, 2), WB_KV_F32));
+        }
+        return *fwd;
+    }
+    ~wb_model() { fwd.reset(); }   // sessions die before their model
 };
 struct wb_session {
     std::unique_ptr<wb::Session> impl;
@@ -89,7 +103,7 @@ void prep_audio_device(wb::Model& model, const float* wave_dev, int64_t n_batch,
     if (n_frames_out) *n_frames_out = F;
 }
 
-// a throw-away model holding only the frontend tables (prep_audio needs no weights)
+// a model holding only the frontend tables (prep_audio needs no weights); one per device, uploaded on first use
 struct FrontendOnly {
     wb::Model m;
     explicit FrontendOnly(int device) {
@@ -110,6 +124,15 @@ struct FrontendOnly {
         m.mel_range = (int*)up(rng.data(), rng.size() * sizeof(int));
     }
 };
+
+FrontendOnly& frontend_for(int device) {
+    static std::mutex mu;
+    static std::map<int, std::unique_ptr<FrontendOnly>> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    auto& slot = cache[device];
+    if (!slot) slot.reset(new FrontendOnly(device));
+    return *slot;
+}
 
 }  // namespace
 
@@ -139,7 +162,7 @@ int wb_prep_audio(int device, const float* wave, int64_t n_batch, int64_t n_samp
         WB_REQUIRE(n_batch >= 1, "prep_audio: n_batch must be >= 1");
         WB_REQUIRE(n_samples >= wb::N_FFT, "prep_audio: waveform shorter than n_fft (audio.rs:292)");
         require_device(device);
-        FrontendOnly fe(device);
+        FrontendOnly& fe = frontend_for(device);
         const int64_t F = n_samples / wb::HOP;
         wb::DevBuf<float> dw, dm;
         dw.alloc((size_t)(n_batch * n_samples));
@@ -155,7 +178,7 @@ int wb_prep_audio_dev(int device, const float* wave_dev, int64_t n_batch, int64_
     return guarded([&] {
         WB_REQUIRE(wave_dev && mel_out_dev, "prep_audio: null pointer");
         require_device(device);
-        FrontendOnly fe(device);
+        FrontendOnly& fe = frontend_for(device);
         prep_audio_device(fe.m, wave_dev, n_batch, n_samples, mel_out_dev, n_frames_out, nullptr);
     });
 }
@@ -235,7 +258,8 @@ int wb_forward_encoder(wb_model* m, const float* mel, int64_t n_batch, int64_t n
     return guarded([&] {
         WB_REQUIRE(m && mel && out, "forward_encoder: null pointer");
         WB_REQUIRE(n_batch >= 1, "forward_encoder: n_batch must be >= 1");
-        wb::Session s(&m->impl, n_batch, 1, 2, WB_KV_F32);
+        std::lock_guard<std::mutex> lock(m->fwd_mu);
+        wb::Session& s = m->forward_session(n_batch, 2);
         s.encode_mels_host(mel, n_batch, n_mels, n_ctx);
         const int d = m->impl.dims.n_audio_state;
         WB_CUDA(cudaMemcpy(out, s.xa.p, (size_t)s.M_tot * d * sizeof(float), cudaMemcpyDeviceToHost));
@@ -250,9 +274,10 @@ int wb_forward_decoder(wb_model* m, const int64_t* tokens, int64_t n_batch, int6
         WB_REQUIRE(n_batch >= 1 && seq_len >= 1, "forward_decoder: empty input");
         WB_REQUIRE(seq_len <= D.n_text_ctx, "Token sequence length must not exceed n_text_ctx (mod.rs:134-139)");
         const int V = D.n_vocab;
-        wb::Session s(&m->impl, n_batch, 1, std::min<int64_t>(D.n_text_ctx, std::max<int64_t>(seq_len, 2)), WB_KV_F32);
+        std::lock_guard<std::mutex> lock(m->fwd_mu);
+        wb::Session& s = m->forward_session(n_batch, std::min<int64_t>(D.n_text_ctx, std::max<int64_t>(seq_len, 2)));
         s.load_encoder_output_host(encoder_output, n_batch, n_enc_ctx);
-        s.full_logits = true;
+        struct FullLogits { wb::Session& s; explicit FullLogits(wb::Session& x) : s(x) { s.full_logits = true; } ~FullLogits() { s.full_logits = false; } } full_guard(s);
         // position by position through the cached step; logits of every position are kept
         wb::DevBuf<float> all;
         all.alloc((size_t)n_batch * seq_len * V);

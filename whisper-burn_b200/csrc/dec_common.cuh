@@ -63,7 +63,7 @@ __device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int& gen) 
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
         long long t0 = clock64();
         while (ld_acquire(bar) < target) {
-            if (clock64() - t0 > 4000000000LL) __trap();   // ~2 s: fail loudly instead of hanging the GPU
+            if (clock64() - t0 > 40000000000LL) __trap();   // ~20 s of SM clocks (profilers and sanitizers slow a launch down a lot): fail loudly instead of hanging the GPU
         }
     }
     __syncthreads();
@@ -334,6 +334,49 @@ __device__ __forceinline__ float pick_row(const float (&acc)[RC], int rr) {
 struct AttnAcc {
     float m, l, o[16];
 };
+// One key per 4-lane group, held in registers (lane l4 of the group owns dims l4*16 .. +16): score, online-softmax update.
+__device__ __forceinline__ void attn_regs_step(const float (&q)[16], const float4 (&kk)[4], const float4 (&vv)[4], bool ok, AttnAcc& A) {
+    float s = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        s = fmaf(q[c * 4], kk[c].x, s); s = fmaf(q[c * 4 + 1], kk[c].y, s);
+        s = fmaf(q[c * 4 + 2], kk[c].z, s); s = fmaf(q[c * 4 + 3], kk[c].w, s);
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if (ok) {
+        const float mn = fmaxf(A.m, s);
+        const float corr = expf(A.m - mn);
+        const float e = expf(s - mn);
+        A.l = A.l * corr + e;
+        A.m = mn;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            A.o[c * 4] = fmaf(e, vv[c].x, A.o[c * 4] * corr);
+            A.o[c * 4 + 1] = fmaf(e, vv[c].y, A.o[c * 4 + 1] * corr);
+            A.o[c * 4 + 2] = fmaf(e, vv[c].z, A.o[c * 4 + 2] * corr);
+            A.o[c * 4 + 3] = fmaf(e, vv[c].w, A.o[c * 4 + 3] * corr);
+        }
+    }
+}
+// merge the 8 key sub-groups of a warp (all lanes end with the warp's m, l and their 16 dims of o)
+__device__ __forceinline__ void attn_merge_subs(AttnAcc& A) {
+#pragma unroll
+    for (int off = 4; off < 32; off <<= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, A.m, off);
+        const float l2 = __shfl_xor_sync(0xffffffffu, A.l, off);
+        const float mn = fmaxf(A.m, m2);
+        const float c1 = A.m > -INFINITY ? expf(A.m - mn) : 0.0f;
+        const float c2 = m2 > -INFINITY ? expf(m2 - mn) : 0.0f;
+        A.l = A.l * c1 + l2 * c2;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const float o2 = __shfl_xor_sync(0xffffffffu, A.o[c], off);
+            A.o[c] = A.o[c] * c1 + o2 * c2;
+        }
+        A.m = mn;
+    }
+}
 // swz >= 0: the keys come from the head-major cross K/V layout (encoder.cu ckv_relayout_kernel), whose 16-byte chunks are
 // XOR-4 swizzled on odd positions (swz = absolute position of key 0); the lane then finds its 16 dims one block over.
 template <typename KF, typename VF>
@@ -386,46 +429,9 @@ __device__ __forceinline__ void attn_warp(const float* q_smem, int n_keys, int f
             }
         }
 #pragma unroll
-        for (int u = 0; u < UK; ++u) {
-            float s = 0.0f;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                s = fmaf(q[c * 4], kk[u][c].x, s); s = fmaf(q[c * 4 + 1], kk[u][c].y, s);
-                s = fmaf(q[c * 4 + 2], kk[u][c].z, s); s = fmaf(q[c * 4 + 3], kk[u][c].w, s);
-            }
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            if (ok[u]) {
-                const float mn = fmaxf(A.m, s);
-                const float corr = expf(A.m - mn);
-                const float e = expf(s - mn);
-                A.l = A.l * corr + e;
-                A.m = mn;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    A.o[c * 4] = fmaf(e, vv[u][c].x, A.o[c * 4] * corr);
-                    A.o[c * 4 + 1] = fmaf(e, vv[u][c].y, A.o[c * 4 + 1] * corr);
-                    A.o[c * 4 + 2] = fmaf(e, vv[u][c].z, A.o[c * 4 + 2] * corr);
-                    A.o[c * 4 + 3] = fmaf(e, vv[u][c].w, A.o[c * 4 + 3] * corr);
-                }
-            }
-        }
+        for (int u = 0; u < UK; ++u) attn_regs_step(q, kk[u], vv[u], ok[u], A);
     }
-#pragma unroll
-    for (int off = 4; off < 32; off <<= 1) {   // merge the 8 key sub-groups
-        const float m2 = __shfl_xor_sync(0xffffffffu, A.m, off);
-        const float l2 = __shfl_xor_sync(0xffffffffu, A.l, off);
-        const float mn = fmaxf(A.m, m2);
-        const float c1 = A.m > -INFINITY ? expf(A.m - mn) : 0.0f;
-        const float c2 = m2 > -INFINITY ? expf(m2 - mn) : 0.0f;
-        A.l = A.l * c1 + l2 * c2;
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-            const float o2 = __shfl_xor_sync(0xffffffffu, A.o[c], off);
-            A.o[c] = A.o[c] * c1 + o2 * c2;
-        }
-        A.m = mn;
-    }
+    attn_merge_subs(A);
 }
 
 // Ring variant for long key ranges (cross attention over up to 1500 encoder positions): K/V go global -> shared
@@ -538,9 +544,34 @@ __device__ __forceinline__ int attn_bulk_dim(int l4, int i) {   // which of the 
     constexpr int CE = 16 / (int)sizeof(KT);                    // elements per 16-byte chunk
     return (l4 + 4 * (i / CE)) * CE + i % CE;
 }
+// The first NSTG-1 batches of attn_warp_bulk, issued ahead of time (the K/V rows are static: nothing to wait for); the
+// matching attn_warp_bulk call passes prefilled = true and the SAME base / n_keys / wslot / nwarps / ring_count.
+template <int NSTG, typename KT>
+__device__ __forceinline__ void attn_bulk_prefill(const KT* base, int n_keys, int wslot, int nwarps, unsigned char* ring, uint64_t* mbar,
+                                                  unsigned int ring_count) {
+    constexpr int ROWB = 128 * (int)sizeof(KT), STGB = 8 * ROWB;
+    if ((threadIdx.x & 31) != 0) return;
+    const int n_batches = (n_keys + 7) >> 3;
+    const int n_it = n_batches > wslot ? (n_batches - wslot + nwarps - 1) / nwarps : 0;
+#pragma unroll
+    for (int it = 0; it < NSTG - 1; ++it) {
+        if (it < n_it) {
+            const int bb = wslot + it * nwarps;
+            const int slot = (int)((ring_count + (unsigned int)it) % NSTG);
+            const uint32_t bytes = (uint32_t)min(8, n_keys - bb * 8) * ROWB;
+            const uint32_t mb = (uint32_t)__cvta_generic_to_shared(mbar + slot);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             (uint32_t)__cvta_generic_to_shared(ring + slot * STGB)),
+                         "l"(base + (int64_t)bb * 8 * 128), "r"(bytes), "r"(mb)
+                         : "memory");
+        }
+    }
+}
 template <int NSTG, typename KT>
 __device__ __forceinline__ void attn_warp_bulk(const float* q_smem, const KT* base, int n_keys, int wslot, int nwarps, int swz,
-                                               unsigned char* ring, uint64_t* mbar, unsigned int& ring_count, AttnAcc& A) {
+                                               unsigned char* ring, uint64_t* mbar, unsigned int& ring_count, AttnAcc& A,
+                                               bool prefilled = false) {
     constexpr int CE = 16 / (int)sizeof(KT), NC = 16 / CE;      // chunk elements; chunks per lane and tensor
     constexpr int ROWB = 128 * (int)sizeof(KT), STGB = 8 * ROWB;
     const int lane = threadIdx.x & 31, sub = lane >> 2, l4 = lane & 3;
@@ -567,8 +598,10 @@ __device__ __forceinline__ void attn_warp_bulk(const float* q_smem, const KT* ba
                          : "memory");
         }
     };
+    if (!prefilled) {
 #pragma unroll
-    for (int s = 0; s < NSTG - 1; ++s) issue(s);
+        for (int s = 0; s < NSTG - 1; ++s) issue(s);
+    }
 #pragma unroll 1
     for (int it = 0; it < n_it; ++it) {
         __syncwarp();                 // every lane is done with the slot that is refilled now (consumed one iteration ago)
@@ -639,14 +672,9 @@ __device__ __forceinline__ void attn_warp_bulk(const float* q_smem, const KT* ba
     }
 }
 
-// one (query row, head) unit handled by the 8 warps of a CTA (keys strided over warps); returns the merged
-// (M, L) and the unnormalised output in out[64] (shared memory), valid after the trailing __syncthreads().
-template <typename KF, typename VF>
-__device__ __forceinline__ void attn_cta(const float* q_smem, int n_keys, KF&& kptr, VF&& vptr, float* wm, float* wl,
-                                         float* wo, float* out, float* ML, int swz = -1) {
+// block-level merge of the 8 warps' partial attention results; out[64] / ML valid after the trailing __syncthreads()
+__device__ __forceinline__ void attn_cta_tail(const AttnAcc& A, float* wm, float* wl, float* wo, float* out, float* ML) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    AttnAcc A;
-    attn_warp(q_smem, n_keys, warp, NW, kptr, vptr, A, swz);
     if (lane < 4) {
 #pragma unroll
         for (int c = 0; c < 16; ++c) wo[warp * 64 + lane * 16 + c] = A.o[c];
@@ -669,6 +697,17 @@ __device__ __forceinline__ void attn_cta(const float* q_smem, int n_keys, KF&& k
         if (tid == 0) { ML[0] = M; ML[1] = L; }
     }
     __syncthreads();
+}
+
+// one (query row, head) unit handled by the 8 warps of a CTA (keys strided over warps); returns the merged
+// (M, L) and the unnormalised output in out[64] (shared memory), valid after the trailing __syncthreads().
+template <typename KF, typename VF>
+__device__ __forceinline__ void attn_cta(const float* q_smem, int n_keys, KF&& kptr, VF&& vptr, float* wm, float* wl,
+                                         float* wo, float* out, float* ML, int swz = -1) {
+    const int warp = threadIdx.x >> 5;
+    AttnAcc A;
+    attn_warp(q_smem, n_keys, warp, NW, kptr, vptr, A, swz);
+    attn_cta_tail(A, wm, wl, wo, out, ML);
 }
 
 // ---- tensor-core helpers (mma.sync m16n8k16, fp16 hi/lo split of fp32 activations; see decoder5.cu) -------------

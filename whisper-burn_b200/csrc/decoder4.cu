@@ -60,6 +60,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
+// 16-byte asynchronous copy global -> shared (L2 only), lane-private destination: completion with cp_async_wait_all()
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 template <int NR, int VPL>
 struct RowRegs {
     uint4 v[NR][VPL];
@@ -152,81 +158,83 @@ __device__ __forceinline__ void dot_rows1(const RowRegs<NR, VPL>& r, const float
     }
 }
 
-// store v into the same shared-memory slot of every CTA of the cluster (lane r -> rank r)
-__device__ __forceinline__ void bcast(cg::cluster_group& cl, float* local, float v) {
-    const int lane = threadIdx.x & 31;
-    if (lane < CS) *cl.map_shared_rank(local, lane) = v;
+// A CTA's contiguous slice of a stage output (staged in local shared memory) -> the same slice of the destination array in
+// every CTA of the cluster.  16-byte remote stores, consecutive lanes -> consecutive addresses of one destination: a stage costs
+// CS * CNT / 32 DSMEM transactions instead of one per (value, destination) -- the scalar per-value broadcast was what made
+// the wide stages (q|k|v, MLP1) slow.
+template <int CNT>
+__device__ __forceinline__ void bcast_slice(cg::cluster_group& cl, const float* stage_s, float* dst_local) {
+    static_assert(CNT % 4 == 0, "slice must be a whole number of 16-byte vectors");
+    constexpr int Q = CNT / 4;
+    for (int i = threadIdx.x; i < CS * Q; i += NT) {
+        const int dest = i / Q, q = i - dest * Q;
+        const float4 v = reinterpret_cast<const float4*>(stage_s)[q];
+        reinterpret_cast<float4*>(cl.map_shared_rank(dst_local, dest))[q] = v;
+    }
 }
 
-// LayerNorm of one row held in shared memory (burn 0.9 form) by the whole CTA: thread t owns elements t, t+NT.
-// If delta != null the row is first updated in place (x += delta).  gamma/beta are fetched before the
-// reductions so their latency is hidden.  red: [2*NW] floats of scratch.  Ends with a __syncthreads().
-// gamma / beta of the LayerNorm that follows the NEXT cluster barrier: fetched before the barrier like the weight rows (the
-// barrier flushes L1, so afterwards they would cost an L2 round trip on the critical path)
-template <int D>
-struct LnRegs {
-    float g[(D + NT - 1) / NT], b[(D + NT - 1) / NT];
-    float eps;
+// The residual row x is double-buffered in shared memory (read one copy, write the other); every warp of the CTA loads it
+// into registers (lane owns the float4s lane, lane+32, ...), applies the broadcast delta and runs LayerNorm ITSELF (two
+// shuffle reductions, no block barrier); the 8 warps compute identical values, warp 0 writes the updated row back.
+template <int PF>
+struct XRegs {
+    float4 v[PF];
 };
-template <int D>
-__device__ __forceinline__ void ln_prefetch(const float* __restrict__ g, const float* __restrict__ b, float eps, LnRegs<D>& r) {
-#pragma unroll
-    for (int i = 0; i < (D + NT - 1) / NT; ++i) {
-        const int c = threadIdx.x + i * NT;
-        r.g[i] = c < D ? __ldg(g + c) : 0.0f;
-        r.b[i] = c < D ? __ldg(b + c) : 0.0f;
-    }
-    r.eps = eps;
+__device__ __forceinline__ float4 add4(const float4& a, const float4& b) {
+    return make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w));
 }
+template <int PF>
+__device__ __forceinline__ void x_update(XRegs<PF>& x, const float* src_s, const float* d_s, float* dst_s) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < PF; ++k)
+        x.v[k] = add4(reinterpret_cast<const float4*>(src_s)[lane + 32 * k], reinterpret_cast<const float4*>(d_s)[lane + 32 * k]);
+    if (dst_s != nullptr && threadIdx.x < 32) {
+#pragma unroll
+        for (int k = 0; k < PF; ++k) reinterpret_cast<float4*>(dst_s)[lane + 32 * k] = x.v[k];
+    }
+}
+// gamma | beta of the LayerNorm that follows the NEXT cluster barrier -> shared memory (2D floats), fetched before the barrier
+// like the weight rows (afterwards they would cost an L2 round trip on the critical path)
 template <int D>
-__device__ __forceinline__ void ln_block(float* x_s, const float* delta_s, float* out_s, const LnRegs<D>& P, int eps_outside, float* red) {
-    constexpr int PT = (D + NT - 1) / NT;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const float eps = P.eps;
-    float xv[PT];
-    const float (&gv)[PT] = P.g;
-    const float (&bv)[PT] = P.b;
+__device__ __forceinline__ void ln_fetch(float* gb_s, const float* __restrict__ g, const float* __restrict__ b) {
+    for (int c = threadIdx.x; c < D; c += NT) {
+        gb_s[c] = __ldg(g + c);
+        gb_s[D + c] = __ldg(b + c);
+    }
+}
+// LayerNorm (burn 0.9 form, layernorm in oracle/model.py) of the warp's register copy of x -> out_s (shared memory).  Every
+// warp stores the same values (identical arithmetic) and reads them back after its own stores.  The normalisation multiplies
+// by 1/den (<= 1.5 ulp from the divide).
+template <int D, int PF>
+__device__ __forceinline__ void ln_warp(XRegs<PF>& x, const float* gb_s, float eps, int eps_outside, float* out_s) {
+    const int lane = threadIdx.x & 31;
     float s = 0.0f;
 #pragma unroll
-    for (int i = 0; i < PT; ++i) {
-        const int c = tid + i * NT;
-        xv[i] = 0.0f;
-        if (c < D) {
-            xv[i] = delta_s ? __fadd_rn(x_s[c], delta_s[c]) : x_s[c];
-            if (delta_s) x_s[c] = xv[i];
-            s += xv[i];
-        }
-    }
+    for (int k = 0; k < PF; ++k) s += (x.v[k].x + x.v[k].y) + (x.v[k].z + x.v[k].w);
     s = warp_sum(s);
-    if (lane == 0) red[warp] = s;
-    __syncthreads();
-    s = 0.0f;
-#pragma unroll
-    for (int w = 0; w < NW; ++w) s += red[w];
     const float mean = __fdiv_rn(s, (float)D);
     float q = 0.0f;
 #pragma unroll
-    for (int i = 0; i < PT; ++i) {
-        const int c = tid + i * NT;
-        if (c < D) {
-            xv[i] = __fsub_rn(xv[i], mean);
-            q = __fadd_rn(q, __fmul_rn(xv[i], xv[i]));
-        }
+    for (int k = 0; k < PF; ++k) {
+        x.v[k].x = __fsub_rn(x.v[k].x, mean); x.v[k].y = __fsub_rn(x.v[k].y, mean);
+        x.v[k].z = __fsub_rn(x.v[k].z, mean); x.v[k].w = __fsub_rn(x.v[k].w, mean);
+        q = fmaf(x.v[k].x, x.v[k].x, q); q = fmaf(x.v[k].y, x.v[k].y, q);
+        q = fmaf(x.v[k].z, x.v[k].z, q); q = fmaf(x.v[k].w, x.v[k].w, q);
     }
     q = warp_sum(q);
-    if (lane == 0) red[NW + warp] = q;
-    __syncthreads();
-    q = 0.0f;
-#pragma unroll
-    for (int w = 0; w < NW; ++w) q += red[NW + w];
     const float var = __fdiv_rn(q, (float)D);
     const float den = eps_outside ? __fadd_rn(__fsqrt_rn(var), eps) : __fsqrt_rn(__fadd_rn(var, eps));
+    const float rinv = __fdiv_rn(1.0f, den);
 #pragma unroll
-    for (int i = 0; i < PT; ++i) {
-        const int c = tid + i * NT;
-        if (c < D) out_s[c] = __fadd_rn(__fmul_rn(__fdiv_rn(xv[i], den), gv[i]), bv[i]);
+    for (int k = 0; k < PF; ++k) {
+        const float4 g = reinterpret_cast<const float4*>(gb_s)[lane + 32 * k];
+        const float4 b = reinterpret_cast<const float4*>(gb_s + D)[lane + 32 * k];
+        reinterpret_cast<float4*>(out_s)[lane + 32 * k] =
+            make_float4(fmaf(__fmul_rn(x.v[k].x, rinv), g.x, b.x), fmaf(__fmul_rn(x.v[k].y, rinv), g.y, b.y),
+                        fmaf(__fmul_rn(x.v[k].z, rinv), g.z, b.z), fmaf(__fmul_rn(x.v[k].w, rinv), g.w, b.w));
     }
-    __syncthreads();
+    __syncwarp();
 }
 
 template <int D, int RC, typename KVT>
@@ -246,9 +254,9 @@ dec4_kernel(const Dec3Args a) {
     const bool active = row < R;
     const int gw = blockIdx.x * NW + warp, n_gw = gridDim.x * NW;
 
-    float* x_s = sm;                  // [D]   residual stream (own copy)
-    float* xn_s = x_s + D;            // [D]   LayerNorm output
-    float* qkv_s = xn_s + D;          // [3D]  q | k | v of the current position
+    float* lnb = sm;                  // [2][2D] LayerNorm gamma | beta; the two buffers alternate: the next LayerNorm's parameters
+                                      //       are fetched while the current ones may still be read
+    float* qkv_s = lnb + 4 * D;       // [3D]  q | k | v of the current position
     float* att_s = qkv_s + 3 * D;     // [D]   attention output (self, then merged cross)
     float* dl_s = att_s + D;          // [D]   out-projection / MLP2 output incl. bias ("delta" for x)
     float* q2_s = dl_s + D;           // [D]   cross query
@@ -259,7 +267,10 @@ dec4_kernel(const Dec3Args a) {
     float* wo = wl + NW;              // [NW][64]
     float* ao = wo + NW * 64;         // [64]
     float* ML = ao + 64;              // [2]
-    float* xs = ML + 4;               // logits stage: [RC][D] LayerNorm rows, then merge scratch
+    float* stg_s = ML + 4;            // [4D/CS] this CTA's slice of a stage output, staged for the vector broadcast
+    float* xb = stg_s + 4 * D / CS;   // [2][D] residual row x, two copies used alternately (read one, write the other)
+    float* xn_s = xb + 2 * D;            // [D]   LayerNorm output (written identically by every warp)
+    float* xs = xn_s + D;             // logits stage: [RC][D] LayerNorm rows, then merge scratch
     float* red = xs + RC * D;         // [NW][8 rows][m, s, best value, best id] logits merge scratch (sized [NW*4][RC][2 + 2*KC])
     constexpr int RINGW = (LG_NBUF * LG_RB * D * 2 > KV_STG * 8 * 128 * 4) ? LG_NBUF * LG_RB * D * 2 : KV_STG * 8 * 128 * 4;   // bytes of a warp's ring (logits rows / cross K/V batches)
     constexpr int LG_PITCH = D * 2;                                        // bytes per staged vocabulary row (rows contiguous: one bulk copy per block)
@@ -289,49 +300,145 @@ dec4_kernel(const Dec3Args a) {
         if (active) {
             // ---- embed (mod.rs:141-146): every CTA of the cluster builds its own copy of x
             const int tok = __ldcg(a.tokens + (int64_t)row * t_max + p);
-            for (int c = tid; c < D; c += NT) x_s[c] = __fadd_rn(__ldg(a.tok_emb + (int64_t)tok * D + c), __ldg(a.pos_emb + (int64_t)p * D + c));
+            // cross attention geometry of this CTA: head = rank % H, the CTAs of a head split the keys
+            const int xh = rank % H, xci = rank / H;
+            const int xnch = (CS - xh + H - 1) / H;              // CTAs working on head xh
+            const int xw = __ldcg(a.row_window + row);
+            const int xT = a.win_T[xw];
+            const int64_t xoff = a.win_row_off[xw] * (int64_t)(2 * D) + (a.ckv_hm ? (int64_t)xh * xT * 128 : (int64_t)xh * 64);
+            const int sub = lane >> 2, l4 = lane & 3;
+            const bool self_fast = p + 1 <= NW * 16;             // self attention: every cached position fits one register batch
+            constexpr int PF = D / 128;   // float4s of the row per lane
+            static_assert(D % 128 == 0, "row must be a whole number of float4s per lane");
+            int xsel = 0, lsel = 0;       // which copy of x / of the LayerNorm parameters is current
+            XRegs<PF> x;
+#pragma unroll
+            for (int k = 0; k < PF; ++k)
+                x.v[k] = add4(__ldg(reinterpret_cast<const float4*>(a.tok_emb + (int64_t)tok * D) + lane + 32 * k),
+                              __ldg(reinterpret_cast<const float4*>(a.pos_emb + (int64_t)p * D) + lane + 32 * k));
+            if (warp == 0) {
+#pragma unroll
+                for (int k = 0; k < PF; ++k) reinterpret_cast<float4*>(xb)[lane + 32 * k] = x.v[k];
+            }
             RowRegs<NR_QKV, VPL> w_qkv;
             load_rows<NR_QKV, VPL>(reinterpret_cast<const __half*>(a.layers[0].Wqkv), a.layers[0].bqkv, D, rank * (3 * D / CS) + warp, NW, w_qkv);
-            LnRegs<D> ln1;
-            ln_prefetch<D>(a.layers[0].ln1_g, a.layers[0].ln1_b, a.layers[0].ln1_eps, ln1);
+            ln_fetch<D>(lnb, a.layers[0].ln1_g, a.layers[0].ln1_b);
             __syncthreads();
             for (int l = 0; l < L; ++l) {
                 const Dec3Layer& W = a.layers[l];
                 KVT* kcl = reinterpret_cast<KVT*>(a.kc) + (size_t)l * a.Rmax * t_max * D;
                 KVT* vcl = reinterpret_cast<KVT*>(a.vc) + (size_t)l * a.Rmax * t_max * D;
                 // ================= S1: q | k | v = LN1(x) Wqkv + b
-                ln_block<D>(x_s, l > 0 ? dl_s : nullptr, xn_s, ln1, a.eps_outside, wm);   // l > 0: += MLP2 of the previous layer
+                if (l > 0) {   // += MLP2 of the previous layer
+                    x_update<PF>(x, xb + xsel * D, dl_s, xb + (xsel ^ 1) * D);
+                    xsel ^= 1;
+                }
+                ln_warp<D, PF>(x, lnb + lsel * 2 * D, W.ln1_eps, a.eps_outside, xn_s);
                 {
                     float acc[NR_QKV];
                     dot_rows1<NR_QKV, VPL, false>(w_qkv, xn_s, D, acc);
-                    float mine = warp_reduce_owner<NR_QKV>(acc);   // lane 2i: sum of row i
-                    {
-                        mine = __fadd_rn(mine, w_qkv.bias_own);
-                        if (rank * (3 * D / CS) + warp + (lane >> 1) * NW < 2 * D) mine = __fmul_rn(mine, scale);
-                    }
-#pragma unroll
-                    for (int i = 0; i < NR_QKV; ++i) {
-                        const int n = rank * (3 * D / CS) + warp + i * NW;
-                        const float v = __shfl_sync(0xffffffffu, mine, 2 * i);
-                        bcast(cl, qkv_s + n, v);
-                        if (lane == 0 && n >= D) {
-                            if (n < 2 * D) kcl[((int64_t)row * t_max + p) * D + (n - D)] = (KVT)v;
-                            else vcl[((int64_t)row * t_max + p) * D + (n - 2 * D)] = (KVT)v;
-                        }
-                    }
+                    float mine = warp_reduce_owner<NR_QKV>(acc);   // lanes 2i, 2i+1: sum of row i
+                    mine = __fadd_rn(mine, w_qkv.bias_own);
+                    const int j = warp + (lane >> 1) * NW;          // index inside this CTA's slice
+                    if (rank * (3 * D / CS) + j < 2 * D) mine = __fmul_rn(mine, scale);
+                    if (!(lane & 1) && (lane >> 1) < NR_QKV) stg_s[j] = mine;
                 }
                 RowRegs<NR_D, VPL> w_o;
                 load_rows<NR_D, VPL>(reinterpret_cast<const __half*>(W.Wo), W.bo, D, rank * (D / CS) + warp, NW, w_o);
+                // self attention (next stage): the cached positions j < p of this head are copied (asynchronously, lane-private
+                // slots of this warp's ring, free until the cross K/V prefill of S3) BEFORE the barrier -- they are from earlier
+                // steps; position p itself is taken from the broadcast q|k|v row afterwards.  Key j = warp + NW*(u*8+sub).
+                constexpr int SNV = sizeof(KVT) == 4 ? 4 : 2;   // 16-byte vectors per lane and tensor (16 dims)
+                uint8_t* sring = ring + (size_t)warp * RINGW;
+                if (rank < H && self_fast) {
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int j = warp + NW * (u * 8 + sub);
+                        if (j < p) {
+                            const int64_t o = ((int64_t)row * t_max + j) * D + rank * 64 + l4 * 16;
+#pragma unroll
+                            for (int c = 0; c < SNV; ++c) {
+                                cp_async16(sring + ((u * 2 + 0) * 4 + c) * 512 + lane * 16, reinterpret_cast<const uint4*>(kcl + o) + c);
+                                cp_async16(sring + ((u * 2 + 1) * 4 + c) * 512 + lane * 16, reinterpret_cast<const uint4*>(vcl + o) + c);
+                            }
+                        }
+                    }
+                }
+                __syncthreads();   // the stage's outputs are staged; the loads above were issued first so they overlap the broadcast
+                bcast_slice<3 * D / CS>(cl, stg_s, qkv_s + rank * (3 * D / CS));
+                if (tid < 3 * D / CS) {   // k | v of this position -> cache (one coalesced run per CTA)
+                    const int n = rank * (3 * D / CS) + tid;
+                    const float v = stg_s[tid];
+                    if (n >= 2 * D) vcl[((int64_t)row * t_max + p) * D + (n - 2 * D)] = (KVT)v;
+                    else if (n >= D) kcl[((int64_t)row * t_max + p) * D + (n - D)] = (KVT)v;
+                }
                 cl.sync();
                 WB_TRACE();
                 // ================= S2: self attention, head = rank (ranks >= H idle)
                 if (rank < H) {
                     const int h = rank;
-                    const KVT* kb = kcl + h * 64;
-                    const KVT* vb = vcl + h * 64;
-                    auto kp = [&](int j) { return kb + ((int64_t)row * t_max + j) * D; };
-                    auto vp = [&](int j) { return vb + ((int64_t)row * t_max + j) * D; };
-                    attn_cta(qkv_s + h * 64, p + 1, kp, vp, wm, wl, wo, ao, ML);
+                    if (self_fast) {
+                        cp_async_wait_all();
+                        float q[16];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const float4 t4 = *reinterpret_cast<const float4*>(qkv_s + h * 64 + l4 * 16 + c * 4);
+                            q[c * 4] = t4.x; q[c * 4 + 1] = t4.y; q[c * 4 + 2] = t4.z; q[c * 4 + 3] = t4.w;
+                        }
+                        AttnAcc A;
+                        A.m = -INFINITY;
+                        A.l = 0.0f;
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) A.o[c] = 0.0f;
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int j = warp + NW * (u * 8 + sub);
+                            float4 skk[4], svv[4];
+                            if (j < p) {
+                                if constexpr (sizeof(KVT) == 4) {
+#pragma unroll
+                                    for (int c = 0; c < 4; ++c) {
+                                        skk[c] = *reinterpret_cast<const float4*>(sring + ((u * 2 + 0) * 4 + c) * 512 + lane * 16);
+                                        svv[c] = *reinterpret_cast<const float4*>(sring + ((u * 2 + 1) * 4 + c) * 512 + lane * 16);
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int c = 0; c < 2; ++c) {
+                                        float w8[8];
+                                        cvt8(*reinterpret_cast<const uint4*>(sring + ((u * 2 + 0) * 4 + c) * 512 + lane * 16), w8);
+                                        skk[2 * c] = make_float4(w8[0], w8[1], w8[2], w8[3]); skk[2 * c + 1] = make_float4(w8[4], w8[5], w8[6], w8[7]);
+                                        cvt8(*reinterpret_cast<const uint4*>(sring + ((u * 2 + 1) * 4 + c) * 512 + lane * 16), w8);
+                                        svv[2 * c] = make_float4(w8[0], w8[1], w8[2], w8[3]); svv[2 * c + 1] = make_float4(w8[4], w8[5], w8[6], w8[7]);
+                                    }
+                                }
+                            } else {
+#pragma unroll
+                                for (int c = 0; c < 4; ++c) { skk[c] = make_float4(0.f, 0.f, 0.f, 0.f); svv[c] = skk[c]; }
+                            }
+                            if (j == p) {   // the current position: from the broadcast row, rounded like the cache entry
+#pragma unroll
+                                for (int c = 0; c < 4; ++c) {
+                                    float4 k4 = *reinterpret_cast<const float4*>(qkv_s + D + h * 64 + l4 * 16 + c * 4);
+                                    float4 v4 = *reinterpret_cast<const float4*>(qkv_s + 2 * D + h * 64 + l4 * 16 + c * 4);
+                                    if constexpr (sizeof(KVT) == 2) {
+                                        k4 = make_float4((float)(KVT)k4.x, (float)(KVT)k4.y, (float)(KVT)k4.z, (float)(KVT)k4.w);
+                                        v4 = make_float4((float)(KVT)v4.x, (float)(KVT)v4.y, (float)(KVT)v4.z, (float)(KVT)v4.w);
+                                    }
+                                    skk[c] = k4;
+                                    svv[c] = v4;
+                                }
+                            }
+                            attn_regs_step(q, skk, svv, j <= p, A);
+                        }
+                        attn_merge_subs(A);
+                        attn_cta_tail(A, wm, wl, wo, ao, ML);
+                    } else {
+                        const KVT* kb = kcl + h * 64;
+                        const KVT* vb = vcl + h * 64;
+                        auto kp = [&](int j) { return kb + ((int64_t)row * t_max + j) * D; };
+                        auto vp = [&](int j) { return vb + ((int64_t)row * t_max + j) * D; };
+                        attn_cta(qkv_s + h * 64, p + 1, kp, vp, wm, wl, wo, ao, ML);
+                    }
                     {
                         const int c = tid & 63, r0b = (tid >> 6) * 4;
                         const float v = __fdiv_rn(ao[c], ML[1]);
@@ -345,41 +452,43 @@ dec4_kernel(const Dec3Args a) {
                 {
                     float acc[NR_D];
                     dot_rows1<NR_D, VPL>(w_o, att_s, D, acc);
+                    if (lane == 0) {
 #pragma unroll
-                    for (int i = 0; i < NR_D; ++i) {
-                        const int n = rank * (D / CS) + warp + i * NW;
-                        bcast(cl, dl_s + n, __fadd_rn(acc[i], w_o.bias[i]));
+                        for (int i = 0; i < NR_D; ++i) stg_s[warp + i * NW] = __fadd_rn(acc[i], w_o.bias[i]);
                     }
                 }
                 RowRegs<NR_D, VPL> w_cq;
                 load_rows<NR_D, VPL>(reinterpret_cast<const __half*>(W.Wcq), W.bcq, D, rank * (D / CS) + warp, NW, w_cq);
-                LnRegs<D> ln23;
-                ln_prefetch<D>(W.ln2_g, W.ln2_b, W.ln2_eps, ln23);
+                ln_fetch<D>(lnb + (lsel ^ 1) * 2 * D, W.ln2_g, W.ln2_b);
+                if (a.ckv_hm)   // first batches of this layer's cross K/V: static data, two barriers ahead of its use
+                    attn_bulk_prefill<KV_STG, KVT>(reinterpret_cast<const KVT*>(a.ckv) + (size_t)l * a.Mcap * 2 * D + xoff, xT, xci * NW + warp,
+                                                   xnch * NW, ring + (size_t)warp * RINGW, kv_bar + warp * KV_STG, kv_count);
+                __syncthreads();
+                bcast_slice<D / CS>(cl, stg_s, dl_s + rank * (D / CS));
                 cl.sync();
                 WB_TRACE();
                 // ================= S4: x += delta; cross query = LN2(x) Wcq + b
-                ln_block<D>(x_s, dl_s, xn_s, ln23, a.eps_outside, wm);
+                x_update<PF>(x, xb + xsel * D, dl_s, xb + (xsel ^ 1) * D);
+                xsel ^= 1;
+                ln_warp<D, PF>(x, lnb + (lsel ^ 1) * 2 * D, W.ln2_eps, a.eps_outside, xn_s);
                 {
                     float acc[NR_D];
                     dot_rows1<NR_D, VPL>(w_cq, xn_s, D, acc);
+                    if (lane == 0) {
 #pragma unroll
-                    for (int i = 0; i < NR_D; ++i) {
-                        const int n = rank * (D / CS) + warp + i * NW;
-                        bcast(cl, q2_s + n, __fmul_rn(__fadd_rn(acc[i], w_cq.bias[i]), scale));
+                        for (int i = 0; i < NR_D; ++i) stg_s[warp + i * NW] = __fmul_rn(__fadd_rn(acc[i], w_cq.bias[i]), scale);
                     }
                 }
                 RowRegs<NR_D, VPL> w_co;
                 load_rows<NR_D, VPL>(reinterpret_cast<const __half*>(W.Wco), W.bco, D, rank * (D / CS) + warp, NW, w_co);
+                __syncthreads();
+                bcast_slice<D / CS>(cl, stg_s, q2_s + rank * (D / CS));
                 cl.sync();
                 WB_TRACE();
                 // ================= S5: cross attention; head = rank % H, the CTAs of a head split the keys
                 {
-                    const int h = rank % H, ci = rank / H;
-                    const int nch = (CS - h + H - 1) / H;              // CTAs working on head h
-                    const int w = __ldcg(a.row_window + row);
-                    const int T = a.win_T[w];
-                    const KVT* ckvl = reinterpret_cast<const KVT*>(a.ckv) + (size_t)l * a.Mcap * 2 * D;
-                    const KVT* kbase = ckvl + a.win_row_off[w] * (int64_t)(2 * D) + (a.ckv_hm ? (int64_t)h * T * 128 : (int64_t)h * 64);
+                    const int h = xh, ci = xci, nch = xnch, T = xT;
+                    const KVT* kbase = reinterpret_cast<const KVT*>(a.ckv) + (size_t)l * a.Mcap * 2 * D + xoff;
                     const int64_t ld = a.ckv_hm ? 128 : 2 * (int64_t)D;
                     const int voff = a.ckv_hm ? 64 : D;
                     auto kp = [&](int j) { return kbase + j * ld; };
@@ -388,7 +497,7 @@ dec4_kernel(const Dec3Args a) {
                     AttnAcc A;
                     if (a.ckv_hm) {   // contiguous head-major block: 8-key batches by bulk copy into this warp's ring (shared with the logits stage)
                         attn_warp_bulk<KV_STG, KVT>(q2_s + h * 64, kbase, T, ci * NW + warp, nch * NW, 0, ring + (size_t)warp * RINGW,
-                                                    kv_bar + warp * KV_STG, kv_count, A);
+                                                    kv_bar + warp * KV_STG, kv_count, A, true);
                     } else {
                         attn_warp(q2_s + h * 64, T, ci * NW + warp, nch * NW, kp, vp, A, -1);
                     }
@@ -444,64 +553,101 @@ dec4_kernel(const Dec3Args a) {
                 {
                     float acc[NR_D];
                     dot_rows1<NR_D, VPL>(w_co, att_s, D, acc);
+                    if (lane == 0) {
 #pragma unroll
-                    for (int i = 0; i < NR_D; ++i) {
-                        const int n = rank * (D / CS) + warp + i * NW;
-                        bcast(cl, dl_s + n, __fadd_rn(acc[i], w_co.bias[i]));
+                        for (int i = 0; i < NR_D; ++i) stg_s[warp + i * NW] = __fadd_rn(acc[i], w_co.bias[i]);
                     }
                 }
                 RowRegs<NR_H, VPL> w_1;
                 load_rows<NR_H, VPL>(reinterpret_cast<const __half*>(W.W1), W.b1, D, rank * (4 * D / CS) + warp, NW, w_1);
-                ln_prefetch<D>(W.ln3_g, W.ln3_b, W.ln3_eps, ln23);
+                ln_fetch<D>(lnb + lsel * 2 * D, W.ln3_g, W.ln3_b);   // buffer of LN1: last read three barriers ago
+                __syncthreads();
+                bcast_slice<D / CS>(cl, stg_s, dl_s + rank * (D / CS));
                 cl.sync();
                 WB_TRACE();
                 // ================= S7: x += delta; hid = gelu(LN3(x) W1 + b1)
-                ln_block<D>(x_s, dl_s, xn_s, ln23, a.eps_outside, wm);
+                x_update<PF>(x, xb + xsel * D, dl_s, xb + (xsel ^ 1) * D);
+                xsel ^= 1;
+                ln_warp<D, PF>(x, lnb + lsel * 2 * D, W.ln3_eps, a.eps_outside, xn_s);
                 {
                     float acc[NR_H];
                     dot_rows1<NR_H, VPL, false>(w_1, xn_s, D, acc);
-                    // lane 2i ends up with the sum of row i: ONE erf-GELU per row instead of one per lane and row
+                    // lanes 2i, 2i+1 end up with the sum of row i: ONE erf-GELU per row instead of one per lane and row
                     float mine = warp_reduce_owner<NR_H>(acc);
                     mine = gelu_erf(__fadd_rn(mine, w_1.bias_own));
-#pragma unroll
-                    for (int i = 0; i < NR_H; ++i) {
-                        const int n = rank * (4 * D / CS) + warp + i * NW;
-                        bcast(cl, hid_s + n, __shfl_sync(0xffffffffu, mine, 2 * i));
-                    }
+                    if (!(lane & 1) && (lane >> 1) < NR_H) stg_s[warp + (lane >> 1) * NW] = mine;
                 }
                 RowRegs<NR_D, VPL4> w_2;
                 load_rows<NR_D, VPL4>(reinterpret_cast<const __half*>(W.W2), W.b2, 4 * D, rank * (D / CS) + warp, NW, w_2);
+                __syncthreads();
+                bcast_slice<4 * D / CS>(cl, stg_s, hid_s + rank * (4 * D / CS));
                 cl.sync();
                 WB_TRACE();
                 // ================= S8: delta = hid W2 + b2
                 {
                     float acc[NR_D];
                     dot_rows1<NR_D, VPL4>(w_2, hid_s, 4 * D, acc);
+                    if (lane == 0) {
 #pragma unroll
-                    for (int i = 0; i < NR_D; ++i) {
-                        const int n = rank * (D / CS) + warp + i * NW;
-                        bcast(cl, dl_s + n, __fadd_rn(acc[i], w_2.bias[i]));
+                        for (int i = 0; i < NR_D; ++i) stg_s[warp + i * NW] = __fadd_rn(acc[i], w_2.bias[i]);
                     }
                 }
                 if (l + 1 < L) {
                     load_rows<NR_QKV, VPL>(reinterpret_cast<const __half*>(a.layers[l + 1].Wqkv), a.layers[l + 1].bqkv, D, rank * (3 * D / CS) + warp, NW, w_qkv);
-                    ln_prefetch<D>(a.layers[l + 1].ln1_g, a.layers[l + 1].ln1_b, a.layers[l + 1].ln1_eps, ln1);
+                    ln_fetch<D>(lnb + (lsel ^ 1) * 2 * D, a.layers[l + 1].ln1_g, a.layers[l + 1].ln1_b);   // buffer of LN2: last read four barriers ago
                 }
+                lsel ^= 1;
+                __syncthreads();
+                bcast_slice<D / CS>(cl, stg_s, dl_s + rank * (D / CS));
                 cl.sync();
                 WB_TRACE();
             }
             // final residual add; rank 0 publishes the row for the vocabulary projection
-            if (want_logits && rank == 0)
-                for (int c = tid; c < D; c += NT) a.x[(int64_t)row * D + c] = __fadd_rn(x_s[c], dl_s[c]);
+            if (want_logits && rank == 0 && warp == 0) {
+                x_update<PF>(x, xb + xsel * D, dl_s, nullptr);
+#pragma unroll
+                for (int k = 0; k < PF; ++k) reinterpret_cast<float4*>(a.x + (int64_t)row * D)[lane + 32 * k] = x.v[k];
+            }
         }
         if (!want_logits) continue;   // prefill positions: clusters stay independent, no chip-wide step
+        // ---- vocabulary tiles of this warp.  CTAs of clusters without a row have nothing to do until the rows are published: they
+        // take their first LG_NBUF half-tiles into the ring BEFORE the grid barrier (the embedding matrix does not depend on the
+        // activations), and their warps own one extra tile each (stage A) so that what remains to be streamed after the barrier
+        // is spread evenly (stage B: round robin over all warps).
+        constexpr int KH = D / 2, NCH = KH / 32;               // columns / 32-column chunks per half-tile
+        constexpr uint32_t BLKB = 16 * KH * 2;                 // bytes per half-tile
+        static_assert(LG_NBUF * LG_RB * D * 2 >= LG_NBUF * (int)BLKB, "ring slot too small");
+        const __half* Et = reinterpret_cast<const __half*>(a.E_tiled);
+        const int v_tiles = (V + 15) / 16;
+        const int n_clusters = gridDim.x / CS;
+        const int n_idle_w = max(0, n_clusters - R) * CS * NW;
+        const int na = (n_idle_w > 0 && 2 * n_idle_w <= v_tiles) ? 1 : 0;
+        const int tiles_a = na * n_idle_w, tiles_b = v_tiles - tiles_a;
+        const int iw = ((row - R) * CS + rank) * NW + warp;          // index among the idle warps
+        const int my_a = active ? 0 : na;
+        const int my_tiles = my_a + (gw < tiles_b ? (tiles_b - gw + n_gw - 1) / n_gw : 0);
+        const int total = my_tiles * 2;                        // half-tiles of this warp
+        auto tile_of = [&](int i) { return i < my_a ? iw + i * n_idle_w : tiles_a + gw + (i - my_a) * n_gw; };
+        uint8_t* wring = ring + (size_t)warp * RINGW;
+        uint64_t* wbar = lg_bar + warp * LG_NBUF;
+        auto issue = [&](int it) {
+            if (it < total && lane == 0) {
+                const int vt = tile_of(it >> 1);
+                const int slot = (int)((lg_count + (unsigned int)it) % LG_NBUF);
+                mbar_expect_tx(wbar + slot, BLKB);
+                bulk_g2s(wring + (size_t)slot * BLKB, Et + ((int64_t)vt * 2 + (it & 1)) * 16 * KH, BLKB, wbar + slot);
+            }
+        };
+        if (!active) {
+#pragma unroll
+            for (int j = 0; j < LG_NBUF; ++j) issue(j);
+        }
         WB_TRACE();
         grid_sync(a.bar, gen);
         WB_TRACE();
         // ================= logits (all CTAs): LN(x) tok_emb^T + mask + online softmax + candidates
         {
             const bool use_mask = a.is_special != nullptr && (a.mask_mode == 1 || (a.mask_mode == 2 && p + 1 <= 5));
-            const __half* Et = reinterpret_cast<const __half*>(a.E_tiled);
             stage_ln<RC>(a.x, 0, R, D, a.lnf_g, a.lnf_b, a.lnf_eps, a.eps_outside, xs);
             __syncthreads();
             // fp32 rows -> fp16 hi / lo planes in MMA fragment order (decoder5.cu); rows >= R are zero
@@ -516,31 +662,16 @@ dec4_kernel(const Dec3Args a) {
             // The matrix is streamed as contiguous half-tiles [16][D/2] (one bulk copy each, TMA engine) through this warp's
             // ring -- LG_NBUF-1 copies in flight while the MMAs of the current half-tile run from shared memory.
             const int g = lane >> 2, t = lane & 3;
-            constexpr int KH = D / 2, NCH = KH / 32;               // columns / 32-column chunks per half-tile
-            constexpr uint32_t BLKB = 16 * KH * 2;                 // bytes per half-tile
-            static_assert(LG_NBUF * LG_RB * D * 2 >= LG_NBUF * (int)BLKB, "ring slot too small");
-            const int v_tiles = (V + 15) / 16;
-            const int my_tiles = gw < v_tiles ? (v_tiles - gw + n_gw - 1) / n_gw : 0;
-            const int total = my_tiles * 2;                        // half-tiles of this warp
-            uint8_t* wring = ring + (size_t)warp * RINGW;
-            uint64_t* wbar = lg_bar + warp * LG_NBUF;
-            auto issue = [&](int it) {
-                if (it < total && lane == 0) {
-                    const int vt = gw + (it >> 1) * n_gw;
-                    const int slot = (int)((lg_count + (unsigned int)it) % LG_NBUF);
-                    mbar_expect_tx(wbar + slot, BLKB);
-                    bulk_g2s(wring + (size_t)slot * BLKB, Et + ((int64_t)vt * 2 + (it & 1)) * 16 * KH, BLKB, wbar + slot);
-                }
-            };
             float m_run[2] = {-INFINITY, -INFINITY}, s_run[2] = {0.0f, 0.0f}, bv[2] = {-INFINITY, -INFINITY};
             int bi[2] = {INT_MAX, INT_MAX};
+            if (active) {
 #pragma unroll
-            for (int j = 0; j < LG_NBUF - 1; ++j) issue(j);
+                for (int j = 0; j < LG_NBUF; ++j) issue(j);
+            }
             float ah[4], al[4];
+            unsigned int sp01 = 0;   // is_special of vocabulary rows g / g+8 of the current tile: fetched a half-tile ahead of its use
 #pragma unroll 1
             for (int it = 0; it < total; ++it) {
-                __syncwarp();   // the slot refilled now was read one iteration ago
-                issue(it + LG_NBUF - 1);
                 const unsigned int cnt = lg_count + (unsigned int)it;
                 const int slot = (int)(cnt % LG_NBUF);
                 mbar_wait(wbar + slot, (cnt / LG_NBUF) & 1);
@@ -549,6 +680,10 @@ dec4_kernel(const Dec3Args a) {
                 if (half == 0) {
 #pragma unroll
                     for (int c = 0; c < 4; ++c) { ah[c] = 0.0f; al[c] = 0.0f; }
+                    if (use_mask) {
+                        const int n = tile_of(it >> 1) * 16 + g;
+                        sp01 = (n < V ? (unsigned int)a.is_special[n] : 0u) | (n + 8 < V ? (unsigned int)a.is_special[n + 8] << 8 : 0u);
+                    }
                 }
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) {
@@ -565,13 +700,13 @@ dec4_kernel(const Dec3Args a) {
                 }
                 if (half == 1) {
                     // C fragment: c0,c1 -> (vocabulary row g, batch rows 2t, 2t+1), c2,c3 -> (row g+8, same batch rows)
-                    const int n0 = (gw + (it >> 1) * n_gw) * 16;
+                    const int n0 = tile_of(it >> 1) * 16;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         const int n = n0 + g + (c >> 1) * 8, e = c & 1;
                         if (n < V && 2 * t + e < R) {
                             const float raw = fmaf(al[c], 1.0f / 2048.0f, ah[c]);
-                            const float v = (use_mask && a.is_special[n]) ? __fadd_rn(raw, -INFINITY) : raw;
+                            const float v = (use_mask && ((sp01 >> ((c >> 1) * 8)) & 0xffu)) ? __fadd_rn(raw, -INFINITY) : raw;
                             if (v > -INFINITY) {
                                 if (v > m_run[e]) { s_run[e] = s_run[e] * expf(m_run[e] - v) + 1.0f; m_run[e] = v; }
                                 else s_run[e] += expf(v - m_run[e]);
@@ -580,6 +715,8 @@ dec4_kernel(const Dec3Args a) {
                         }
                     }
                 }
+                __syncwarp();   // every lane is done with the slot
+                issue(it + LG_NBUF);
             }
             lg_count += (unsigned int)total;
             WB_TRACE();
@@ -696,7 +833,7 @@ dec4_kernel(const Dec3Args a) {
 
 template <int D, int RC>
 size_t dec4_smem() {
-    return sizeof(float) * ((size_t)12 * D + CS * 68 + 2 * NW + NW * 64 + 64 + 4 + (size_t)RC * D + (size_t)NW * 4 * RC * 6 + 16) +
+    return sizeof(float) * ((size_t)17 * D + 4 * D / CS + CS * 68 + 2 * NW + NW * 64 + 64 + 4 + (size_t)RC * D + (size_t)NW * 4 * RC * 6 + 16) +
            (size_t)NW * std::max(LG_NBUF * LG_RB * D * 2, KV_STG * 8 * 128 * 4) + NW * LG_NBUF * 8 + NW * KV_STG * 8 + (size_t)2 * (D / 32) * 32 * 16 + 16;
 }
 
