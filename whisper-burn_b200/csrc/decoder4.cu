@@ -28,6 +28,45 @@ namespace wb {
 
 namespace {
 
+// End of a stage: every CTA sends its slice of the stage output to all 16 CTAs of the cluster, then needs everybody's slice.
+// D4_ASYNC 1: the slices travel as st.async stores that complete transaction bytes on an mbarrier of the RECEIVING CTA; a CTA
+//   waits on its own mbarrier for the expected byte count -- no cluster barrier, no release fence on the sending side (the
+//   fence + barrier.cluster.arrive was ~0.5 us per stage).  The all-to-all data dependence orders everything else: a CTA can
+//   only send stage k+1 after it has received stage k from everyone, i.e. after everyone finished reading what stage k-1 sent.
+// D4_ASYNC 0: plain remote stores + barrier.cluster arrive (release) / wait (acquire), the prefetch between the two.
+#ifndef D4_ASYNC
+#define D4_ASYNC 1
+#endif
+// IDX: stage (mbarrier) index, RXBYTES: bytes this CTA receives in the stage, SEND: lambda issuing this CTA's sends (staged
+// values are complete: a __syncthreads precedes it), PF: lambda prefetching the next stage's static operands
+#define D4_EXCHANGE(IDX, RXBYTES, SEND, PF)                  \
+    do {                                                     \
+        WB_FINE();                                           \
+        __syncthreads();                                     \
+        WB_FINE();                                           \
+        SEND();                                              \
+        WB_FINE();                                           \
+        if (D4_ASYNC) {                                      \
+            PF();                                            \
+            WB_FINE();                                       \
+            xwait(xbar + (IDX), (RXBYTES), lc & 1u);         \
+        } else {                                             \
+            cluster_arrive();                                \
+            PF();                                            \
+            WB_FINE();                                       \
+            cluster_wait();                                  \
+        }                                                    \
+    } while (0)
+// sub-stage time stamps (profiling builds only: -DD4_FINE=1)
+#ifndef D4_FINE
+#define D4_FINE 0
+#endif
+#if D4_FINE
+#define WB_FINE() WB_TRACE()
+#else
+#define WB_FINE() do { } while (0)
+#endif
+
 constexpr int CS = 16;   // CTAs per cluster
 constexpr int LG_NBUF = 3;                 // logits stage: ring slots per warp
 constexpr int LG_RB = 8;                   // vocabulary rows per slot
@@ -65,6 +104,9 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
 template <int NR, int VPL>
 struct RowRegs {
@@ -158,18 +200,48 @@ __device__ __forceinline__ void dot_rows1(const RowRegs<NR, VPL>& r, const float
     }
 }
 
-// A CTA's contiguous slice of a stage output (staged in local shared memory) -> the same slice of the destination array in
-// every CTA of the cluster.  16-byte remote stores, consecutive lanes -> consecutive addresses of one destination: a stage costs
-// CS * CNT / 32 DSMEM transactions instead of one per (value, destination) -- the scalar per-value broadcast was what made
-// the wide stages (q|k|v, MLP1) slow.
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+// 16 bytes -> shared memory of another CTA of the cluster, completing 16 transaction bytes on that CTA's mbarrier
+__device__ __forceinline__ void st_async_v4(uint32_t raddr, const float4& v, uint32_t rbar) {
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr), "f"(v.x),
+                 "f"(v.y), "f"(v.z), "f"(v.w), "r"(rbar)
+                 : "memory");
+}
+// 16 bytes to CTA `dest`: dst / bar are LOCAL addresses of the destination array element and of the stage's mbarrier
+__device__ __forceinline__ void put16(cg::cluster_group& cl, float* dst, uint64_t* bar, int dest, const float4& v) {
+#if D4_ASYNC
+    st_async_v4(mapa_u32(smem_u32(dst), (uint32_t)dest), v, mapa_u32(smem_u32(bar), (uint32_t)dest));
+#else
+    *reinterpret_cast<float4*>(cl.map_shared_rank(dst, dest)) = v;
+#endif
+}
+// A CTA's contiguous slice of a stage output (CNT floats staged in local shared memory) -> the same slice of the destination
+// array in every CTA of the cluster.  16-byte stores, consecutive lanes -> consecutive addresses of one destination.
 template <int CNT>
-__device__ __forceinline__ void bcast_slice(cg::cluster_group& cl, const float* stage_s, float* dst_local) {
+__device__ __forceinline__ void put_slice(cg::cluster_group& cl, const float* stage_s, float* dst_local, uint64_t* bar) {
     static_assert(CNT % 4 == 0, "slice must be a whole number of 16-byte vectors");
     constexpr int Q = CNT / 4;
     for (int i = threadIdx.x; i < CS * Q; i += NT) {
         const int dest = i / Q, q = i - dest * Q;
-        const float4 v = reinterpret_cast<const float4*>(stage_s)[q];
-        reinterpret_cast<float4*>(cl.map_shared_rank(dst_local, dest))[q] = v;
+        put16(cl, dst_local + 4 * q, bar, dest, reinterpret_cast<const float4*>(stage_s)[q]);
+    }
+}
+// wait until `bytes` have arrived on this CTA's stage mbarrier (D4_ASYNC): thread 0 posts the expectation, everybody polls
+__device__ __forceinline__ void xwait(uint64_t* bar, uint32_t bytes, uint32_t parity) {
+    if (threadIdx.x == 0) mbar_expect_tx(bar, bytes);
+    const uint32_t mb = smem_u32(bar);
+    uint32_t done = 0;
+    int spins = 0;
+    while (!done) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done)
+                     : "r"(mb), "r"(parity)
+                     : "memory");
+        if (!done && ++spins > (1 << 24)) __trap();   // a lost message must not hang the GPU
     }
 }
 
@@ -194,13 +266,15 @@ __device__ __forceinline__ void x_update(XRegs<PF>& x, const float* src_s, const
         for (int k = 0; k < PF; ++k) reinterpret_cast<float4*>(dst_s)[lane + 32 * k] = x.v[k];
     }
 }
-// gamma | beta of the LayerNorm that follows the NEXT cluster barrier -> shared memory (2D floats), fetched before the barrier
-// like the weight rows (afterwards they would cost an L2 round trip on the critical path)
-template <int D>
-__device__ __forceinline__ void ln_fetch(float* gb_s, const float* __restrict__ g, const float* __restrict__ b) {
-    for (int c = threadIdx.x; c < D; c += NT) {
-        gb_s[c] = __ldg(g + c);
-        gb_s[D + c] = __ldg(b + c);
+// gamma | beta of a LayerNorm a few stages ahead -> this WARP's private copy (2D floats), lane-private 16-byte cp.async
+// (each lane copies exactly the vectors it reads in ln_warp): no register stall, no barrier; cp_async_wait_all() before use.
+template <int D, int PF>
+__device__ __forceinline__ void ln_fetch(float* lnp, const float* __restrict__ g, const float* __restrict__ b) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < PF; ++k) {
+        cp_async16(lnp + 4 * (lane + 32 * k), g + 4 * (lane + 32 * k));
+        cp_async16(lnp + D + 4 * (lane + 32 * k), b + 4 * (lane + 32 * k));
     }
 }
 // LayerNorm (burn 0.9 form, layernorm in oracle/model.py) of the warp's register copy of x -> out_s (shared memory).  Every
@@ -209,6 +283,7 @@ __device__ __forceinline__ void ln_fetch(float* gb_s, const float* __restrict__ 
 template <int D, int PF>
 __device__ __forceinline__ void ln_warp(XRegs<PF>& x, const float* gb_s, float eps, int eps_outside, float* out_s) {
     const int lane = threadIdx.x & 31;
+    cp_async_wait_all();   // this lane's gamma / beta vectors (ln_fetch)
     float s = 0.0f;
 #pragma unroll
     for (int k = 0; k < PF; ++k) s += (x.v[k].x + x.v[k].y) + (x.v[k].z + x.v[k].w);
@@ -254,9 +329,8 @@ dec4_kernel(const Dec3Args a) {
     const bool active = row < R;
     const int gw = blockIdx.x * NW + warp, n_gw = gridDim.x * NW;
 
-    float* lnb = sm;                  // [2][2D] LayerNorm gamma | beta; the two buffers alternate: the next LayerNorm's parameters
-                                      //       are fetched while the current ones may still be read
-    float* qkv_s = lnb + 4 * D;       // [3D]  q | k | v of the current position
+    float* lnp = sm + warp * 2 * D;   // [NW][2D] LayerNorm gamma | beta of the next LayerNorm, one private copy per warp
+    float* qkv_s = sm + NW * 2 * D;   // [3D]  q | k | v of the current position
     float* att_s = qkv_s + 3 * D;     // [D]   attention output (self, then merged cross)
     float* dl_s = att_s + D;          // [D]   out-projection / MLP2 output incl. bias ("delta" for x)
     float* q2_s = dl_s + D;           // [D]   cross query
@@ -267,27 +341,35 @@ dec4_kernel(const Dec3Args a) {
     float* wo = wl + NW;              // [NW][64]
     float* ao = wo + NW * 64;         // [64]
     float* ML = ao + 64;              // [2]
-    float* stg_s = ML + 4;            // [4D/CS] this CTA's slice of a stage output, staged for the vector broadcast
-    float* xb = stg_s + 4 * D / CS;   // [2][D] residual row x, two copies used alternately (read one, write the other)
-    float* xn_s = xb + 2 * D;            // [D]   LayerNorm output (written identically by every warp)
-    float* xs = xn_s + D;             // logits stage: [RC][D] LayerNorm rows, then merge scratch
-    float* red = xs + RC * D;         // [NW][8 rows][m, s, best value, best id] logits merge scratch (sized [NW*4][RC][2 + 2*KC])
+    constexpr int STG_N = 4 * D / CS > 68 ? 4 * D / CS : 68;
+    float* stg_s = ML + 4;            // [STG_N] this CTA's slice of a stage output, staged for the 16-byte sends
+    float* xb = stg_s + STG_N;        // [2][D] residual row x, two copies used alternately (read one, write the other)
+    float* xn_s = xb + 2 * D;         // [D]   LayerNorm output (written identically by every warp)
+    float* xs = qkv_s;                // logits stage: [RC][D] LayerNorm rows -- aliases the layer-phase arrays q|k|v .. hidden (10D floats),
+                                      // dead by then (remote writes into them resume only after the step's closing flag wait)
+    static_assert(RC <= 10, "logits rows must fit the aliased layer-phase arrays");
+    float* red = xn_s + D;            // [NW][8 rows][m, s, best value, best id] logits merge scratch (sized [NW*4][RC][2 + 2*KC])
     constexpr int RINGW = (LG_NBUF * LG_RB * D * 2 > KV_STG * 8 * 128 * 4) ? LG_NBUF * LG_RB * D * 2 : KV_STG * 8 * 128 * 4;   // bytes of a warp's ring (logits rows / cross K/V batches)
     constexpr int LG_PITCH = D * 2;                                        // bytes per staged vocabulary row (rows contiguous: one bulk copy per block)
     uint8_t* ring = reinterpret_cast<uint8_t*>(red + NW * 4 * RC * 6);      // [NW][LG_NBUF][LG_RB][LG_PITCH]
     uint64_t* lg_bar = reinterpret_cast<uint64_t*>(ring + (size_t)NW * RINGW);   // [NW][LG_NBUF]
     uint64_t* kv_bar = lg_bar + NW * LG_NBUF;   // [NW][KV_STG] cross-attention K/V ring (aliases the logits ring: different stages)
-    uint4* pl_hi = reinterpret_cast<uint4*>(kv_bar + NW * KV_STG);   // logits stage: fragment-order fp16 hi plane of the 8 (padded) LayerNorm rows [D/32][32]
+    uint64_t* xbar = kv_bar + NW * KV_STG;      // [8] stage exchange barriers (D4_ASYNC): transaction bytes sent by the 16 CTAs of the cluster
+    uint4* pl_hi = reinterpret_cast<uint4*>(xbar + 8);   // logits stage: fragment-order fp16 hi plane of the 8 (padded) LayerNorm rows [D/32][32]
     uint4* pl_lo = pl_hi + (D / 32) * 32;                           // same, residual * 2^11
     if (lane == 0) {
         for (int j = 0; j < KV_STG; ++j) mbar_init(kv_bar + warp * KV_STG + j, 1);
         for (int j = 0; j < LG_NBUF; ++j) mbar_init(lg_bar + warp * LG_NBUF + j, 1);
+        if (warp == 0)
+            for (int j = 0; j < 8; ++j) mbar_init(xbar + j, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
+    cl.sync();                   // every CTA's stage barriers exist before the first remote store can target them
+    unsigned int lc = 0;         // layers this CTA has run: phase parity of the stage barriers (each is used once per layer)
     unsigned int kv_count = 0;   // batches this warp has pushed through its K/V ring
     unsigned int lg_count = 0;   // blocks this warp has pushed through its ring since kernel start (slot / parity bookkeeping)
     unsigned int gen = 0;
+    unsigned int lstep = 0;      // vocabulary steps this launch has finished (ticket / flag bookkeeping)
     int tr_n = 0;
     const float scale = a.qk_scale;
     WB_TRACE();
@@ -310,7 +392,7 @@ dec4_kernel(const Dec3Args a) {
             const bool self_fast = p + 1 <= NW * 16;             // self attention: every cached position fits one register batch
             constexpr int PF = D / 128;   // float4s of the row per lane
             static_assert(D % 128 == 0, "row must be a whole number of float4s per lane");
-            int xsel = 0, lsel = 0;       // which copy of x / of the LayerNorm parameters is current
+            int xsel = 0;                 // which copy of x is current
             XRegs<PF> x;
 #pragma unroll
             for (int k = 0; k < PF; ++k)
@@ -322,7 +404,7 @@ dec4_kernel(const Dec3Args a) {
             }
             RowRegs<NR_QKV, VPL> w_qkv;
             load_rows<NR_QKV, VPL>(reinterpret_cast<const __half*>(a.layers[0].Wqkv), a.layers[0].bqkv, D, rank * (3 * D / CS) + warp, NW, w_qkv);
-            ln_fetch<D>(lnb, a.layers[0].ln1_g, a.layers[0].ln1_b);
+            if (step == 0) ln_fetch<D, PF>(lnp, a.layers[0].ln1_g, a.layers[0].ln1_b);   // later steps: fetched by the previous step's last layer
             __syncthreads();
             for (int l = 0; l < L; ++l) {
                 const Dec3Layer& W = a.layers[l];
@@ -333,7 +415,8 @@ dec4_kernel(const Dec3Args a) {
                     x_update<PF>(x, xb + xsel * D, dl_s, xb + (xsel ^ 1) * D);
                     xsel ^= 1;
                 }
-                ln_warp<D, PF>(x, lnb + lsel * 2 * D, W.ln1_eps, a.eps_outside, xn_s);
+                ln_warp<D, PF>(x, lnp, W.ln1_eps, a.eps_outside, xn_s);
+                ln_fetch<D, PF>(lnp, W.ln2_g, W.ln2_b);
                 {
                     float acc[NR_QKV];
                     dot_rows1<NR_QKV, VPL, false>(w_qkv, xn_s, D, acc);
@@ -344,35 +427,39 @@ dec4_kernel(const Dec3Args a) {
                     if (!(lane & 1) && (lane >> 1) < NR_QKV) stg_s[j] = mine;
                 }
                 RowRegs<NR_D, VPL> w_o;
-                load_rows<NR_D, VPL>(reinterpret_cast<const __half*>(W.Wo), W.bo, D, rank * (D / CS) + warp, NW, w_o);
                 // self attention (next stage): the cached positions j < p of this head are copied (asynchronously, lane-private
-                // slots of this warp's ring, free until the cross K/V prefill of S3) BEFORE the barrier -- they are from earlier
+                // slots of this warp's ring, free until the cross K/V prefill of S3) ahead of their use -- they are from earlier
                 // steps; position p itself is taken from the broadcast q|k|v row afterwards.  Key j = warp + NW*(u*8+sub).
                 constexpr int SNV = sizeof(KVT) == 4 ? 4 : 2;   // 16-byte vectors per lane and tensor (16 dims)
                 uint8_t* sring = ring + (size_t)warp * RINGW;
-                if (rank < H && self_fast) {
+                auto pre_s2 = [&]() {
+                    load_rows<NR_D, VPL>(reinterpret_cast<const __half*>(W.Wo), W.bo, D, rank * (D / CS) + warp, NW, w_o);
+                    if (rank < H && self_fast) {
 #pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const int j = warp + NW * (u * 8 + sub);
-                        if (j < p) {
-                            const int64_t o = ((int64_t)row * t_max + j) * D + rank * 64 + l4 * 16;
+                        for (int u = 0; u < 2; ++u) {
+                            const int j = warp + NW * (u * 8 + sub);
+                            if (j < p) {
+                                const int64_t o = ((int64_t)row * t_max + j) * D + rank * 64 + l4 * 16;
 #pragma unroll
-                            for (int c = 0; c < SNV; ++c) {
-                                cp_async16(sring + ((u * 2 + 0) * 4 + c) * 512 + lane * 16, reinterpret_cast<const uint4*>(kcl + o) + c);
-                                cp_async16(sring + ((u * 2 + 1) * 4 + c) * 512 + lane * 16, reinterpret_cast<const uint4*>(vcl + o) + c);
+                                for (int c = 0; c < SNV; ++c) {
+                                    cp_async16(sring + ((u * 2 + 0) * 4 + c) * 512 + lane * 16, reinterpret_cast<const uint4*>(kcl + o) + c);
+                                    cp_async16(sring + ((u * 2 + 1) * 4 + c) * 512 + lane * 16, reinterpret_cast<const uint4*>(vcl + o) + c);
+                                }
                             }
                         }
                     }
-                }
-                __syncthreads();   // the stage's outputs are staged; the loads above were issued first so they overlap the broadcast
-                bcast_slice<3 * D / CS>(cl, stg_s, qkv_s + rank * (3 * D / CS));
-                if (tid < 3 * D / CS) {   // k | v of this position -> cache (one coalesced run per CTA)
-                    const int n = rank * (3 * D / CS) + tid;
-                    const float v = stg_s[tid];
-                    if (n >= 2 * D) vcl[((int64_t)row * t_max + p) * D + (n - 2 * D)] = (KVT)v;
-                    else if (n >= D) kcl[((int64_t)row * t_max + p) * D + (n - D)] = (KVT)v;
-                }
-                cl.sync();
+                };
+                auto send_s1 = [&]() {
+                    put_slice<3 * D / CS>(cl, stg_s, qkv_s + rank * (3 * D / CS), xbar + 0);
+                    if (tid < 3 * D / CS) {   // k | v of this position -> cache (one coalesced run per CTA)
+                        const int n = rank * (3 * D / CS) + tid;
+                        const float v = stg_s[tid];
+                        if (n >= 2 * D) vcl[((int64_t)row * t_max + p) * D + (n - 2 * D)] = (KVT)v;
+                        else if (n >= D) kcl[((int64_t)row * t_max + p) * D + (n - D)] = (KVT)v;
+                    }
+                };
+                D4_EXCHANGE(0, 3 * D * 4, send_s1, pre_s2);
+                if (D4_ASYNC && !self_fast) cl.sync();   // the long-context path reads position p's k | v back from the cache: order the stores
                 WB_TRACE();
                 // ================= S2: self attention, head = rank (ranks >= H idle)
                 if (rank < H) {
@@ -439,51 +526,58 @@ dec4_kernel(const Dec3Args a) {
                         auto vp = [&](int j) { return vb + ((int64_t)row * t_max + j) * D; };
                         attn_cta(qkv_s + h * 64, p + 1, kp, vp, wm, wl, wo, ao, ML);
                     }
-                    {
-                        const int c = tid & 63, r0b = (tid >> 6) * 4;
-                        const float v = __fdiv_rn(ao[c], ML[1]);
-#pragma unroll
-                        for (int r2 = 0; r2 < 4; ++r2) *cl.map_shared_rank(att_s + h * 64 + c, r0b + r2) = v;
-                    }
                 }
-                cl.sync();
+                auto send_s2 = [&]() {   // the 6 head CTAs: 64 normalised values -> every CTA (thread = destination x float4)
+                    if (rank < H) {
+                        const int dest = tid >> 4, q = tid & 15;
+                        const float4 o4 = reinterpret_cast<const float4*>(ao)[q];
+                        const float den = ML[1];
+                        put16(cl, att_s + rank * 64 + 4 * q, xbar + 1, dest,
+                              make_float4(__fdiv_rn(o4.x, den), __fdiv_rn(o4.y, den), __fdiv_rn(o4.z, den), __fdiv_rn(o4.w, den)));
+                    }
+                };
+                auto pf_none = [&]() {};
+                D4_EXCHANGE(1, D * 4, send_s2, pf_none);
                 WB_TRACE();
                 // ================= S3: delta = att Wo + bo
                 {
                     float acc[NR_D];
                     dot_rows1<NR_D, VPL>(w_o, att_s, D, acc);
+                    WB_FINE();
                     if (lane == 0) {
 #pragma unroll
                         for (int i = 0; i < NR_D; ++i) stg_s[warp + i * NW] = __fadd_rn(acc[i], w_o.bias[i]);
                     }
                 }
                 RowRegs<NR_D, VPL> w_cq;
-                load_rows<NR_D, VPL>(reinterpret_cast<const __half*>(W.Wcq), W.bcq, D, rank * (D / CS) + warp, NW, w_cq);
-                ln_fetch<D>(lnb + (lsel ^ 1) * 2 * D, W.ln2_g, W.ln2_b);
-                if (a.ckv_hm)   // first batches of this layer's cross K/V: static data, two barriers ahead of its use
-                    attn_bulk_prefill<KV_STG, KVT>(reinterpret_cast<const KVT*>(a.ckv) + (size_t)l * a.Mcap * 2 * D + xoff, xT, xci * NW + warp,
-                                                   xnch * NW, ring + (size_t)warp * RINGW, kv_bar + warp * KV_STG, kv_count);
-                __syncthreads();
-                bcast_slice<D / CS>(cl, stg_s, dl_s + rank * (D / CS));
-                cl.sync();
+                auto pre_s4 = [&]() {
+                    load_rows<NR_D, VPL>(reinterpret_cast<const __half*>(W.Wcq), W.bcq, D, rank * (D / CS) + warp, NW, w_cq);
+                    if (a.ckv_hm)   // first batches of this layer's cross K/V: static data, two barriers ahead of its use
+                        attn_bulk_prefill<KV_STG, KVT>(reinterpret_cast<const KVT*>(a.ckv) + (size_t)l * a.Mcap * 2 * D + xoff, xT, xci * NW + warp,
+                                                       xnch * NW, ring + (size_t)warp * RINGW, kv_bar + warp * KV_STG, kv_count);
+                };
+                auto send_s3 = [&]() { put_slice<D / CS>(cl, stg_s, dl_s + rank * (D / CS), xbar + 2); };
+                D4_EXCHANGE(2, D * 4, send_s3, pre_s4);
                 WB_TRACE();
                 // ================= S4: x += delta; cross query = LN2(x) Wcq + b
                 x_update<PF>(x, xb + xsel * D, dl_s, xb + (xsel ^ 1) * D);
                 xsel ^= 1;
-                ln_warp<D, PF>(x, lnb + (lsel ^ 1) * 2 * D, W.ln2_eps, a.eps_outside, xn_s);
+                ln_warp<D, PF>(x, lnp, W.ln2_eps, a.eps_outside, xn_s);
+                ln_fetch<D, PF>(lnp, W.ln3_g, W.ln3_b);
+                WB_FINE();
                 {
                     float acc[NR_D];
                     dot_rows1<NR_D, VPL>(w_cq, xn_s, D, acc);
+                    WB_FINE();
                     if (lane == 0) {
 #pragma unroll
                         for (int i = 0; i < NR_D; ++i) stg_s[warp + i * NW] = __fmul_rn(__fadd_rn(acc[i], w_cq.bias[i]), scale);
                     }
                 }
                 RowRegs<NR_D, VPL> w_co;
-                load_rows<NR_D, VPL>(reinterpret_cast<const __half*>(W.Wco), W.bco, D, rank * (D / CS) + warp, NW, w_co);
-                __syncthreads();
-                bcast_slice<D / CS>(cl, stg_s, q2_s + rank * (D / CS));
-                cl.sync();
+                auto pre_s6 = [&]() { load_rows<NR_D, VPL>(reinterpret_cast<const __half*>(W.Wco), W.bco, D, rank * (D / CS) + warp, NW, w_co); };
+                auto send_s4 = [&]() { put_slice<D / CS>(cl, stg_s, q2_s + rank * (D / CS), xbar + 3); };
+                D4_EXCHANGE(3, D * 4, send_s4, pre_s6);
                 WB_TRACE();
                 // ================= S5: cross attention; head = rank % H, the CTAs of a head split the keys
                 {
@@ -519,21 +613,12 @@ dec4_kernel(const Dec3Args a) {
                             Ls += sc * wl[w2];
                             o += sc * wo[w2 * 64 + tid];
                         }
-                        ao[tid] = o;
-                        if (tid == 0) { ML[0] = M; ML[1] = Ls; }
-                    }
-                    __syncthreads();
-                    {
-                        const int c = tid & 63, r0b = (tid >> 6) * 4;
-#pragma unroll
-                        for (int r2 = 0; r2 < 4; ++r2) {
-                            float* dst = cl.map_shared_rank(part_s + rank * 68, r0b + r2);
-                            dst[4 + c] = ao[c];
-                            if (c == 0) { dst[0] = ML[0]; dst[1] = ML[1]; }
-                        }
+                        stg_s[4 + tid] = o;                      // this CTA's partial: M, L, -, -, o[64]
+                        if (tid < 4) stg_s[tid] = tid == 0 ? M : tid == 1 ? Ls : 0.0f;
                     }
                 }
-                cl.sync();
+                auto send_s5 = [&]() { put_slice<68>(cl, stg_s, part_s + rank * 68, xbar + 4); };
+                D4_EXCHANGE(4, CS * 68 * 4, send_s5, pf_none);
                 WB_TRACE();
                 // ================= S6: merge the head partials, delta = cross Wco + bco
                 for (int c = tid; c < D; c += NT) {
@@ -559,29 +644,32 @@ dec4_kernel(const Dec3Args a) {
                     }
                 }
                 RowRegs<NR_H, VPL> w_1;
-                load_rows<NR_H, VPL>(reinterpret_cast<const __half*>(W.W1), W.b1, D, rank * (4 * D / CS) + warp, NW, w_1);
-                ln_fetch<D>(lnb + lsel * 2 * D, W.ln3_g, W.ln3_b);   // buffer of LN1: last read three barriers ago
-                __syncthreads();
-                bcast_slice<D / CS>(cl, stg_s, dl_s + rank * (D / CS));
-                cl.sync();
+                auto pre_s7 = [&]() { load_rows<NR_H, VPL>(reinterpret_cast<const __half*>(W.W1), W.b1, D, rank * (4 * D / CS) + warp, NW, w_1); };
+                auto send_s6 = [&]() { put_slice<D / CS>(cl, stg_s, dl_s + rank * (D / CS), xbar + 5); };
+                D4_EXCHANGE(5, D * 4, send_s6, pre_s7);
                 WB_TRACE();
                 // ================= S7: x += delta; hid = gelu(LN3(x) W1 + b1)
                 x_update<PF>(x, xb + xsel * D, dl_s, xb + (xsel ^ 1) * D);
                 xsel ^= 1;
-                ln_warp<D, PF>(x, lnb + lsel * 2 * D, W.ln3_eps, a.eps_outside, xn_s);
+                ln_warp<D, PF>(x, lnp, W.ln3_eps, a.eps_outside, xn_s);
+                {   // LN1 of the next layer, or of layer 0 for the next position
+                    const Dec3Layer& Wn = a.layers[l + 1 < L ? l + 1 : 0];
+                    ln_fetch<D, PF>(lnp, Wn.ln1_g, Wn.ln1_b);
+                }
+                WB_FINE();
                 {
                     float acc[NR_H];
                     dot_rows1<NR_H, VPL, false>(w_1, xn_s, D, acc);
                     // lanes 2i, 2i+1 end up with the sum of row i: ONE erf-GELU per row instead of one per lane and row
                     float mine = warp_reduce_owner<NR_H>(acc);
                     mine = gelu_erf(__fadd_rn(mine, w_1.bias_own));
+                    WB_FINE();
                     if (!(lane & 1) && (lane >> 1) < NR_H) stg_s[warp + (lane >> 1) * NW] = mine;
                 }
                 RowRegs<NR_D, VPL4> w_2;
-                load_rows<NR_D, VPL4>(reinterpret_cast<const __half*>(W.W2), W.b2, 4 * D, rank * (D / CS) + warp, NW, w_2);
-                __syncthreads();
-                bcast_slice<4 * D / CS>(cl, stg_s, hid_s + rank * (4 * D / CS));
-                cl.sync();
+                auto pre_s8 = [&]() { load_rows<NR_D, VPL4>(reinterpret_cast<const __half*>(W.W2), W.b2, 4 * D, rank * (D / CS) + warp, NW, w_2); };
+                auto send_s7 = [&]() { put_slice<4 * D / CS>(cl, stg_s, hid_s + rank * (4 * D / CS), xbar + 6); };
+                D4_EXCHANGE(6, 4 * D * 4, send_s7, pre_s8);
                 WB_TRACE();
                 // ================= S8: delta = hid W2 + b2
                 {
@@ -592,14 +680,13 @@ dec4_kernel(const Dec3Args a) {
                         for (int i = 0; i < NR_D; ++i) stg_s[warp + i * NW] = __fadd_rn(acc[i], w_2.bias[i]);
                     }
                 }
-                if (l + 1 < L) {
-                    load_rows<NR_QKV, VPL>(reinterpret_cast<const __half*>(a.layers[l + 1].Wqkv), a.layers[l + 1].bqkv, D, rank * (3 * D / CS) + warp, NW, w_qkv);
-                    ln_fetch<D>(lnb + (lsel ^ 1) * 2 * D, a.layers[l + 1].ln1_g, a.layers[l + 1].ln1_b);   // buffer of LN2: last read four barriers ago
-                }
-                lsel ^= 1;
-                __syncthreads();
-                bcast_slice<D / CS>(cl, stg_s, dl_s + rank * (D / CS));
-                cl.sync();
+                auto pre_s1 = [&]() {
+                    if (l + 1 < L)
+                        load_rows<NR_QKV, VPL>(reinterpret_cast<const __half*>(a.layers[l + 1].Wqkv), a.layers[l + 1].bqkv, D, rank * (3 * D / CS) + warp, NW, w_qkv);
+                };
+                auto send_s8 = [&]() { put_slice<D / CS>(cl, stg_s, dl_s + rank * (D / CS), xbar + 7); };
+                D4_EXCHANGE(7, D * 4, send_s8, pre_s1);
+                ++lc;
                 WB_TRACE();
             }
             // final residual add; rank 0 publishes the row for the vocabulary projection
@@ -609,7 +696,10 @@ dec4_kernel(const Dec3Args a) {
                 for (int k = 0; k < PF; ++k) reinterpret_cast<float4*>(a.x + (int64_t)row * D)[lane + 32 * k] = x.v[k];
             }
         }
-        if (!want_logits) continue;   // prefill positions: clusters stay independent, no chip-wide step
+        if (!want_logits) {   // prefill positions: clusters stay independent, no chip-wide step
+            if (D4_ASYNC && active) cl.sync();   // this position's k | v stores (global) are ordered before the next position reads them
+            continue;
+        }
         // ---- vocabulary tiles of this warp.  CTAs of clusters without a row have nothing to do until the rows are published: they
         // take their first LG_NBUF half-tiles into the ring BEFORE the grid barrier (the embedding matrix does not depend on the
         // activations), and their warps own one extra tile each (stage A) so that what remains to be streamed after the barrier
@@ -760,11 +850,21 @@ dec4_kernel(const Dec3Args a) {
             }
         }
         WB_TRACE();
-        grid_sync(a.bar, gen);
+        // ================= finish (greedy: beam.rs:9-37 with beam_size 1) by the LAST CTA to deliver its records: every CTA
+        // takes a ticket after publishing its records; the holder of the last ticket of this step merges them (one warp
+        // per row) and releases a flag the others wait on -- one flag wait instead of two grid barriers around the finish.
+        ++lstep;
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            const unsigned int ticket = atomicAdd(a.bar + 1, 1u);
+            reinterpret_cast<int*>(ML)[2] = (ticket == lstep * gridDim.x - 1) ? 1 : 0;
+        }
+        __syncthreads();
         WB_TRACE();
-        // ================= finish: one CTA per row (greedy: beam.rs:9-37 with beam_size 1)
-        for (int r = blockIdx.x; r < R; r += gridDim.x) {
-            if (warp == 0) {   // one warp per row over the per-CTA records (this code runs once per step: keep it small)
+        if (reinterpret_cast<int*>(ML)[2]) {
+            __threadfence();
+            for (int r = warp; r < R; r += NW) {
                 const int NP = gridDim.x;   // <= 128 co-resident CTAs: at most 4 records per lane, all loads issued before any use
                 float rm[4], rs[4], rv[4];
                 int ri[4];
@@ -809,9 +909,20 @@ dec4_kernel(const Dec3Args a) {
                     }
                 }
             }
+            __syncthreads();
+            if (tid == 0) {
+                __threadfence();
+                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.bar + 2), "r"(lstep) : "memory");
+            }
         }
         WB_TRACE();
-        grid_sync(a.bar, gen);
+        if (tid == 0) {
+            const long long t0 = clock64();
+            while (ld_acquire(a.bar + 2) < lstep) {
+                if (clock64() - t0 > 40000000000LL) __trap();   // ~20 s of SM clocks: fail loudly instead of hanging the GPU
+            }
+        }
+        __syncthreads();
         WB_TRACE();
         {
             int live = 0;
@@ -833,8 +944,8 @@ dec4_kernel(const Dec3Args a) {
 
 template <int D, int RC>
 size_t dec4_smem() {
-    return sizeof(float) * ((size_t)17 * D + 4 * D / CS + CS * 68 + 2 * NW + NW * 64 + 64 + 4 + (size_t)RC * D + (size_t)NW * 4 * RC * 6 + 16) +
-           (size_t)NW * std::max(LG_NBUF * LG_RB * D * 2, KV_STG * 8 * 128 * 4) + NW * LG_NBUF * 8 + NW * KV_STG * 8 + (size_t)2 * (D / 32) * 32 * 16 + 16;
+    return sizeof(float) * ((size_t)(2 * NW + 13) * D + (4 * D / CS > 68 ? 4 * D / CS : 68) + CS * 68 + 2 * NW + NW * 64 + 64 + 4 + (size_t)NW * 4 * RC * 6 + 16) +
+           (size_t)NW * std::max(LG_NBUF * LG_RB * D * 2, KV_STG * 8 * 128 * 4) + NW * LG_NBUF * 8 + NW * KV_STG * 8 + 8 * 8 + (size_t)2 * (D / 32) * 32 * 16 + 16;
 }
 
 struct LaunchState4 {
@@ -882,6 +993,7 @@ bool launch4_t(const Dec3Args& a, cudaStream_t st) {
             S.clusters = -1;
             return false;
         }
+        S.cooperative = getenv("WB200_NO_COOP") == nullptr;   // profilers cannot replay cooperative cluster launches
         S.clusters = std::min(n_clusters, 8);   // every launched cluster must be co-resident (grid barriers); B200: 7 of size 16
     }
     if (S.clusters < 0 || a.R > S.clusters) return false;

@@ -1201,6 +1201,7 @@ bool launch6_t(const Dec3Args& a, cudaStream_t st) {
     const int n_cl = S.clusters;
     cfg.gridDim = dim3(n_cl * G::CS);
     cudaError_t e = cudaErrorUnknown;
+    if (S.cooperative && getenv("WB200_NO_COOP")) S.cooperative = false;   // profilers cannot replay cooperative cluster launches
     if (S.cooperative) {
         cfg.numAttrs = 2;
         e = cudaLaunchKernelEx(&cfg, k, a);
