@@ -345,9 +345,6 @@ dec4_kernel(const Dec3Args a) {
     float* stg_s = ML + 4;            // [STG_N] this CTA's slice of a stage output, staged for the 16-byte sends
     float* xb = stg_s + STG_N;        // [2][D] residual row x, two copies used alternately (read one, write the other)
     float* xn_s = xb + 2 * D;         // [D]   LayerNorm output (written identically by every warp)
-    float* xs = qkv_s;                // logits stage: [RC][D] LayerNorm rows -- aliases the layer-phase arrays q|k|v .. hidden (10D floats),
-                                      // dead by then (remote writes into them resume only after the step's closing flag wait)
-    static_assert(RC <= 10, "logits rows must fit the aliased layer-phase arrays");
     float* red = xn_s + D;            // [NW][8 rows][m, s, best value, best id] logits merge scratch (sized [NW*4][RC][2 + 2*KC])
     constexpr int RINGW = (LG_NBUF * LG_RB * D * 2 > KV_STG * 8 * 128 * 4) ? LG_NBUF * LG_RB * D * 2 : KV_STG * 8 * 128 * 4;   // bytes of a warp's ring (logits rows / cross K/V batches)
     constexpr int LG_PITCH = D * 2;                                        // bytes per staged vocabulary row (rows contiguous: one bulk copy per block)
@@ -379,6 +376,33 @@ dec4_kernel(const Dec3Args a) {
     for (int step = 0; step < a.n_steps; ++step) {
         const int p = a.pos0 + step;
         const bool want_logits = p >= a.logits_from;
+        // ---- vocabulary tiles of this warp (round robin over all warps of the grid).  The tied-embedding matrix does not depend
+        // on the activations: every warp takes its first LG_NBUF half-tiles into its ring BEFORE the grid barrier -- warps of
+        // clusters without a row right away, the others as soon as the last layer's cross attention has released the ring.
+        constexpr int KH = D / 2, NCH = KH / 32;               // columns / 32-column chunks per half-tile
+        constexpr uint32_t BLKB = 16 * KH * 2;                 // bytes per half-tile
+        static_assert(LG_NBUF * LG_RB * D * 2 >= LG_NBUF * (int)BLKB, "ring slot too small");
+        const __half* Et = reinterpret_cast<const __half*>(a.E_tiled);
+        const int v_tiles = (V + 15) / 16;
+        const int my_tiles = gw < v_tiles ? (v_tiles - gw + n_gw - 1) / n_gw : 0;
+        const int total = my_tiles * 2;                        // half-tiles of this warp
+        auto tile_of = [&](int i) { return gw + i * n_gw; };
+        uint8_t* wring = ring + (size_t)warp * RINGW;
+        uint64_t* wbar = lg_bar + warp * LG_NBUF;
+        auto issue = [&](int it) {
+            if (it < total && lane == 0) {
+                const int vt = tile_of(it >> 1);
+                const int slot = (int)((lg_count + (unsigned int)it) % LG_NBUF);
+                mbar_expect_tx(wbar + slot, BLKB);
+                bulk_g2s(wring + (size_t)slot * BLKB, Et + ((int64_t)vt * 2 + (it & 1)) * 16 * KH, BLKB, wbar + slot);
+            }
+        };
+        uint4* gpl_hi = reinterpret_cast<uint4*>(a.att_pl);   // published final-LayerNorm rows: fragment-order fp16 hi / lo planes [D/32][32]
+        uint4* gpl_lo = gpl_hi + (D / 32) * 32;
+        if (want_logits && !active) {
+#pragma unroll
+            for (int j = 0; j < LG_NBUF; ++j) issue(j);
+        }
         if (active) {
             // ---- embed (mod.rs:141-146): every CTA of the cluster builds its own copy of x
             const int tok = __ldcg(a.tokens + (int64_t)row * t_max + p);
@@ -595,6 +619,12 @@ dec4_kernel(const Dec3Args a) {
                     } else {
                         attn_warp(q2_s + h * 64, T, ci * NW + warp, nch * NW, kp, vp, A, -1);
                     }
+                    if (l == L - 1 && want_logits) {   // the ring is free until the next position: first vocabulary half-tiles of this warp
+                        __syncwarp();
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of the ring before the bulk copies
+#pragma unroll
+                        for (int j = 0; j < LG_NBUF; ++j) issue(j);
+                    }
                     if (lane < 4) {
 #pragma unroll
                         for (int c = 0; c < 16; ++c) wo[warp * 64 + (a.ckv_hm ? attn_bulk_dim<KVT>(lane, c) : lane * 16 + c)] = A.o[c];
@@ -652,7 +682,9 @@ dec4_kernel(const Dec3Args a) {
                 x_update<PF>(x, xb + xsel * D, dl_s, xb + (xsel ^ 1) * D);
                 xsel ^= 1;
                 ln_warp<D, PF>(x, lnp, W.ln3_eps, a.eps_outside, xn_s);
-                {   // LN1 of the next layer, or of layer 0 for the next position
+                if (l == L - 1 && want_logits && rank == 0 && warp == 0) {   // this warp publishes the row: final LayerNorm next
+                    ln_fetch<D, PF>(lnp, a.lnf_g, a.lnf_b);
+                } else {   // LN1 of the next layer, or of layer 0 for the next position
                     const Dec3Layer& Wn = a.layers[l + 1 < L ? l + 1 : 0];
                     ln_fetch<D, PF>(lnp, Wn.ln1_g, Wn.ln1_b);
                 }
@@ -689,48 +721,20 @@ dec4_kernel(const Dec3Args a) {
                 ++lc;
                 WB_TRACE();
             }
-            // final residual add; rank 0 publishes the row for the vocabulary projection
+            // final residual add + final LayerNorm (mod.rs:153-155); rank 0 publishes the row for the vocabulary projection, already
+            // split into the fp16 hi / lo fragment planes every CTA needs (rows of other clusters land in the same planes)
             if (want_logits && rank == 0 && warp == 0) {
                 x_update<PF>(x, xb + xsel * D, dl_s, nullptr);
+                ln_warp<D, PF>(x, lnp, a.lnf_eps, a.eps_outside, xn_s);
 #pragma unroll
-                for (int k = 0; k < PF; ++k) reinterpret_cast<float4*>(a.x + (int64_t)row * D)[lane + 32 * k] = x.v[k];
+                for (int k = 0; k < PF; ++k)
+                    store_frag(gpl_hi, gpl_lo, D / 32, row, 4 * (lane + 32 * k), reinterpret_cast<const float4*>(xn_s)[lane + 32 * k]);
+                ln_fetch<D, PF>(lnp, a.layers[0].ln1_g, a.layers[0].ln1_b);   // LN1 of layer 0 for the next position
             }
         }
         if (!want_logits) {   // prefill positions: clusters stay independent, no chip-wide step
             if (D4_ASYNC && active) cl.sync();   // this position's k | v stores (global) are ordered before the next position reads them
             continue;
-        }
-        // ---- vocabulary tiles of this warp.  CTAs of clusters without a row have nothing to do until the rows are published: they
-        // take their first LG_NBUF half-tiles into the ring BEFORE the grid barrier (the embedding matrix does not depend on the
-        // activations), and their warps own one extra tile each (stage A) so that what remains to be streamed after the barrier
-        // is spread evenly (stage B: round robin over all warps).
-        constexpr int KH = D / 2, NCH = KH / 32;               // columns / 32-column chunks per half-tile
-        constexpr uint32_t BLKB = 16 * KH * 2;                 // bytes per half-tile
-        static_assert(LG_NBUF * LG_RB * D * 2 >= LG_NBUF * (int)BLKB, "ring slot too small");
-        const __half* Et = reinterpret_cast<const __half*>(a.E_tiled);
-        const int v_tiles = (V + 15) / 16;
-        const int n_clusters = gridDim.x / CS;
-        const int n_idle_w = max(0, n_clusters - R) * CS * NW;
-        const int na = (n_idle_w > 0 && 2 * n_idle_w <= v_tiles) ? 1 : 0;
-        const int tiles_a = na * n_idle_w, tiles_b = v_tiles - tiles_a;
-        const int iw = ((row - R) * CS + rank) * NW + warp;          // index among the idle warps
-        const int my_a = active ? 0 : na;
-        const int my_tiles = my_a + (gw < tiles_b ? (tiles_b - gw + n_gw - 1) / n_gw : 0);
-        const int total = my_tiles * 2;                        // half-tiles of this warp
-        auto tile_of = [&](int i) { return i < my_a ? iw + i * n_idle_w : tiles_a + gw + (i - my_a) * n_gw; };
-        uint8_t* wring = ring + (size_t)warp * RINGW;
-        uint64_t* wbar = lg_bar + warp * LG_NBUF;
-        auto issue = [&](int it) {
-            if (it < total && lane == 0) {
-                const int vt = tile_of(it >> 1);
-                const int slot = (int)((lg_count + (unsigned int)it) % LG_NBUF);
-                mbar_expect_tx(wbar + slot, BLKB);
-                bulk_g2s(wring + (size_t)slot * BLKB, Et + ((int64_t)vt * 2 + (it & 1)) * 16 * KH, BLKB, wbar + slot);
-            }
-        };
-        if (!active) {
-#pragma unroll
-            for (int j = 0; j < LG_NBUF; ++j) issue(j);
         }
         WB_TRACE();
         grid_sync(a.bar, gen);
@@ -738,14 +742,9 @@ dec4_kernel(const Dec3Args a) {
         // ================= logits (all CTAs): LN(x) tok_emb^T + mask + online softmax + candidates
         {
             const bool use_mask = a.is_special != nullptr && (a.mask_mode == 1 || (a.mask_mode == 2 && p + 1 <= 5));
-            stage_ln<RC>(a.x, 0, R, D, a.lnf_g, a.lnf_b, a.lnf_eps, a.eps_outside, xs);
-            __syncthreads();
-            // fp32 rows -> fp16 hi / lo planes in MMA fragment order (decoder5.cu); rows >= R are zero
-            for (int i = tid; i < 8 * (D / 4); i += NT) {
-                const int row = i / (D / 4), c4 = i % (D / 4);
-                const float4 v = row < RC ? *reinterpret_cast<const float4*>(xs + row * D + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                store_frag(pl_hi, pl_lo, D / 32, row, c4 * 4, v);
-            }
+            // the published rows: fp16 hi / lo planes in MMA fragment order (decoder5.cu); rows >= R are never used
+            for (int i = tid; i < 2 * (D / 32) * 32; i += NT) cp_async16(pl_hi + i, gpl_hi + i);   // pl_lo follows pl_hi in both spaces
+            cp_async_wait_all();
             __syncthreads();
             WB_TRACE();
             // Swap-AB tensor-core product: a warp owns tiles of 16 vocabulary rows (M), the 8 padded batch rows are N, K = D.
@@ -754,10 +753,6 @@ dec4_kernel(const Dec3Args a) {
             const int g = lane >> 2, t = lane & 3;
             float m_run[2] = {-INFINITY, -INFINITY}, s_run[2] = {0.0f, 0.0f}, bv[2] = {-INFINITY, -INFINITY};
             int bi[2] = {INT_MAX, INT_MAX};
-            if (active) {
-#pragma unroll
-                for (int j = 0; j < LG_NBUF; ++j) issue(j);
-            }
             float ah[4], al[4];
             unsigned int sp01 = 0;   // is_special of vocabulary rows g / g+8 of the current tile: fetched a half-tile ahead of its use
 #pragma unroll 1
