@@ -3,7 +3,7 @@ usage: python scripts/trace_decode5.py [model] [n_chunks] [kv]"""
 import os, sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
-os.environ["WB200_TRACE"] = "1"
+os.environ["WB200_TRACE"] = "gpurun_out/d3_trace.txt"; os.makedirs("gpurun_out", exist_ok=True)
 import numpy as np
 import wb200  # noqa
 from whisper_burn_b200 import ffi, model, synth, transcribe

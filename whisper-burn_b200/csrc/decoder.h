@@ -29,7 +29,8 @@ struct Dec5Desc {
     float eps = 0.0f;
     int src = 0;                   // input planes of a linear stage: 1 = attention output, 2 = MLP hidden, 3 = LayerNorm output
     int ks = 0;                    // K slab width of a linear stage (= columns staged per item); d except MLP2 when 4d splits into 3
-    int pad_[3] = {0, 0, 0};       // sizeof % 16 == 0: the table is copied to shared memory in 16-byte words
+    int n_fold = 0;                // LayerNorm stage: K-slab partial sums (ypart) folded into x first (the producing stage's n_slabs)
+    int pad_[2] = {0, 0};          // sizeof % 16 == 0: the table is copied to shared memory in 16-byte words
 };
 static_assert(sizeof(Dec5Desc) % 16 == 0, "Dec5Desc must be a whole number of 16-byte words");
 struct Dec3Args {
@@ -55,6 +56,8 @@ struct Dec3Args {
     const void* ckv = nullptr;            // [L][Mcap][2d]
     int ckv_hm = 0;                       // 1: head-major cross K/V (encoder.cu ckv_relayout_kernel), 0: GEMM row-major order
     int kv_half = 0;
+    int64_t pf_ckv_bytes = 0;             // decoder5.cu: bytes of a layer's cross K/V block every CTA helps to pull into L2 ahead of the cross-attention stage (0: off)
+    int d5_bulk_stage = 1;                // decoder5.cu: activation planes staged by bulk copies (TMA engine) instead of per-thread cp.async
     int kv_row0 = 0;                      // decoder5.cu row groups: local row r of this launch is cache row r + kv_row0 (ancestry entries are absolute)
     const int* row_window = nullptr;
     const int64_t* win_row_off = nullptr;

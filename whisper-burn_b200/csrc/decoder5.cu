@@ -123,6 +123,12 @@ dec5_kernel(const Dec3Args a) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     unsigned int kv_count = 0;   // batches this warp has pushed through its K/V ring
+    uint64_t* st_bar = kv_bar + NW * 8;   // activation-plane staging by bulk copies: one mbarrier, one phase per staging
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(st_bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    unsigned int st_phase = 0;
     __syncthreads();
     unsigned int gen = 0;
     int tr_n = 0;
@@ -138,8 +144,9 @@ dec5_kernel(const Dec3Args a) {
     uint4* xn_lo = xn_hi + pl_plane;
     uint4* hid_hi = reinterpret_cast<uint4*>(a.hid_pl);   // [slabs] hi planes, then [slabs] lo planes (slab width hks columns: 4d in 4 or 3 slabs)
     uint4* hid_lo = hid_hi + 4 * pl_plane;
-    const int n_part = ds[SL_MLP2].n_slabs;               // MLP2 partial sums to fold (3 or 4)
     const int hks = ds[SL_MLP2].ks;                       // K slab width of MLP2 = column width of the hidden-layer planes
+    const int aks = ds[SL_OUT].ks;                        // K slab width of the out projections = column width of the attention-output planes (d: unsplit)
+    const int cq_parts = ds[SL_CQ].emit == EM_PART ? ds[SL_CQ].n_slabs : 0;   // cross query delivered as K-slab partial sums (folded where it is read)
     float* x = a.x;
 
     AFrag pf;
@@ -164,6 +171,7 @@ dec5_kernel(const Dec3Args a) {
                     const int r = blockIdx.x;
                     if (r < R) {
                         constexpr int PT = 2;   // float4 per thread: d <= 1280 -> d / 4 <= 320 <= 2 * 256
+                        const int n_part = D.n_fold;   // K-slab partial sums of the producing linear stage (MLP2, or a split out projection)
                         float4 v[PT], g4[PT], b4[PT];
                         int tok = 0;
                         if (D.stage == ST_LN_EMB) tok = a.use_cur_tok ? __ldcg(a.cur_tok + r) : __ldcg(a.tokens + (int64_t)r * t_max + p);
@@ -182,7 +190,7 @@ dec5_kernel(const Dec3Args a) {
                                 if (D.stage != ST_LN_X) {
                                     const float4 p0 = __ldcg(reinterpret_cast<const float4*>(yp + (int64_t)r * d) + c);
                                     const float4 p1 = __ldcg(reinterpret_cast<const float4*>(yp + yps + (int64_t)r * d) + c);
-                                    const float4 p2 = __ldcg(reinterpret_cast<const float4*>(yp + 2 * yps + (int64_t)r * d) + c);
+                                    const float4 p2 = n_part > 2 ? __ldcg(reinterpret_cast<const float4*>(yp + 2 * yps + (int64_t)r * d) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
                                     const float4 p3 = n_part > 3 ? __ldcg(reinterpret_cast<const float4*>(yp + 3 * yps + (int64_t)r * d) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
                                     v[i].x = __fadd_rn(v[i].x, __fadd_rn(__fadd_rn(p0.x, p1.x), __fadd_rn(p2.x, p3.x)));
                                     v[i].y = __fadd_rn(v[i].y, __fadd_rn(__fadd_rn(p0.y, p1.y), __fadd_rn(p2.y, p3.y)));
@@ -234,7 +242,8 @@ dec5_kernel(const Dec3Args a) {
                                 o.y = __fadd_rn(__fmul_rn(__fdiv_rn(v[i].y, den), g4[i].y), b4[i].y);
                                 o.z = __fadd_rn(__fmul_rn(__fdiv_rn(v[i].z, den), g4[i].z), b4[i].z);
                                 o.w = __fadd_rn(__fmul_rn(__fdiv_rn(v[i].w, den), g4[i].w), b4[i].w);
-                                store_frag(xn_hi, xn_lo, nchunks, r, c * 4, o);
+                                const int oks = D.ks, osl = (c * 4) / oks;   // slab-major output planes when the consuming linear stage splits K (oks == d: one slab)
+                                store_frag(xn_hi + osl * (PL_ROWS * oks / 8), xn_lo + osl * (PL_ROWS * oks / 8), oks >> 5, r, c * 4 - osl * oks, o);
                             }
                         }
                     }
@@ -250,7 +259,22 @@ dec5_kernel(const Dec3Args a) {
                         int r, h, sp = 0;
                         if (is_cross) { sp = u % S; h = (u / S) % H; r = u / (S * H); }
                         else { r = u / H; h = u % H; }
-                        if (gt < 16) *reinterpret_cast<float4*>(qs + grp * 64 + gt * 4) = __ldcg(reinterpret_cast<const float4*>(a.q + (int64_t)r * d + h * 64) + gt);
+                        if (gt < 16) {
+                            float4 q4;
+                            if (is_cross && cq_parts > 0) {   // (p0 + p1) + (p2 + p3), bias inside p0, then the (d/H)^-0.25 scale (EM_CQ)
+                                const float4* pq = reinterpret_cast<const float4*>(yp + (int64_t)r * d + h * 64) + gt;
+                                const float4 p0 = __ldcg(pq), p1 = __ldcg(pq + yps / 4);
+                                const float4 p2 = cq_parts > 2 ? __ldcg(pq + 2 * (yps / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                const float4 p3 = cq_parts > 3 ? __ldcg(pq + 3 * (yps / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                q4.x = __fmul_rn(__fadd_rn(__fadd_rn(p0.x, p1.x), __fadd_rn(p2.x, p3.x)), scale);
+                                q4.y = __fmul_rn(__fadd_rn(__fadd_rn(p0.y, p1.y), __fadd_rn(p2.y, p3.y)), scale);
+                                q4.z = __fmul_rn(__fadd_rn(__fadd_rn(p0.z, p1.z), __fadd_rn(p2.z, p3.z)), scale);
+                                q4.w = __fmul_rn(__fadd_rn(__fadd_rn(p0.w, p1.w), __fadd_rn(p2.w, p3.w)), scale);
+                            } else {
+                                q4 = __ldcg(reinterpret_cast<const float4*>(a.q + (int64_t)r * d + h * 64) + gt);
+                            }
+                            *reinterpret_cast<float4*>(qs + grp * 64 + gt * 4) = q4;
+                        }
                         bar_named(1 + grp, 128);
                         int nk = p + 1, swz = -1;
                         const KVT* kbase = nullptr;
@@ -307,7 +331,8 @@ dec5_kernel(const Dec3Args a) {
                                 o += sc * wo[(grp * 4 + w2) * 64 + gt];
                             }
                             if (!is_cross || S == 1) {
-                                store_plane_elem(att_hi, att_lo, nchunks, r, h * 64 + gt, __fdiv_rn(o, Ls));
+                                const int col = h * 64 + gt, asl = col / aks;   // slab-major planes: slab asl holds columns [asl * aks, +aks)
+                                store_plane_elem(att_hi + asl * (PL_ROWS * aks / 8), att_lo + asl * (PL_ROWS * aks / 8), aks >> 5, r, col - asl * aks, __fdiv_rn(o, Ls));
                             } else {
                                 const int64_t oi = ((int64_t)r * H + h) * S + sp;
                                 a.part_o[oi * 64 + gt] = o;
@@ -341,11 +366,33 @@ dec5_kernel(const Dec3Args a) {
                                 const uint4* sh = (D.src == 2 ? hid_hi : D.src == 3 ? xn_hi : att_hi) + (int64_t)slab * (PL_ROWS * ks / 8);
                                 const uint4* sl = sh + (D.src == 2 ? 4 * pl_plane : pl_plane);
                                 const int n16 = NT8 * nchunks_s * 32;
-                                for (int i = tid; i < n16; i += NT) {
-                                    cp_async16(xhi + i, sh + i);
-                                    cp_async16(xlo + i, sl + i);
+                                if (a.d5_bulk_stage) {
+                                    // two contiguous blocks -> bulk copies by the TMA engine, 8 KB pieces, completion on one mbarrier (73 KB per CTA
+                                    // for small.en: 0.8 us instead of 1.4 us of per-thread cp.async, scripts/ubench).  The planes were written by other
+                                    // CTAs through the generic proxy (ordered by the grid barrier) and this buffer was last read through it.
+                                    const uint32_t mb = (uint32_t)__cvta_generic_to_shared(st_bar);
+                                    if (tid == 0) {
+                                        asm volatile("fence.proxy.async;" ::: "memory");
+                                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"((uint32_t)n16 * 32u) : "memory");
+                                        for (int o = 0; o < n16; o += 512) {
+                                            const uint32_t bytes = (uint32_t)min(512, n16 - o) * 16u;
+                                            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"((uint32_t)__cvta_generic_to_shared(xhi + o)),
+                                                         "l"(sh + o), "r"(bytes), "r"(mb) : "memory");
+                                            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"((uint32_t)__cvta_generic_to_shared(xlo + o)),
+                                                         "l"(sl + o), "r"(bytes), "r"(mb) : "memory");
+                                        }
+                                    }
+                                    uint32_t done = 0;
+                                    while (!done)
+                                        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(mb), "r"(st_phase) : "memory");
+                                    st_phase ^= 1u;
+                                } else {
+                                    for (int i = tid; i < n16; i += NT) {
+                                        cp_async16(xhi + i, sh + i);
+                                        cp_async16(xlo + i, sl + i);
+                                    }
+                                    cp_async_wait_all();
                                 }
-                                cp_async_wait_all();
                             } else {
                                 // ---- merge the cross-attention split partials (S > 1) while staging
                                 float* wn = red;   // [RP][H][S] normalised split weights
@@ -376,8 +423,8 @@ dec5_kernel(const Dec3Args a) {
                                     }
                                 }
                                 __syncthreads();
-                                for (int i = tid; i < RP * d / 4; i += NT) {   // 4 consecutive dims of one (row, head)
-                                    const int r = (i * 4) / d, c = (i * 4) % d, rc = min(r, R - 1);
+                                for (int i = tid; i < RP * ks / 4; i += NT) {   // 4 consecutive dims of one (row, head), columns of this K slab
+                                    const int r = (i * 4) / ks, cl = (i * 4) % ks, c = slab * ks + cl, rc = min(r, R - 1);
                                     const int h = c / 64;
                                     const float4* po = reinterpret_cast<const float4*>(a.part_o + (((int64_t)rc * H + h) * S) * 64 + (c & 63));
                                     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -388,7 +435,7 @@ dec5_kernel(const Dec3Args a) {
                                         acc.x = fmaf(wgt, v.x, acc.x); acc.y = fmaf(wgt, v.y, acc.y);
                                         acc.z = fmaf(wgt, v.z, acc.z); acc.w = fmaf(wgt, v.w, acc.w);
                                     }
-                                    store_frag(xhi, xlo, nchunks, r, c, acc);
+                                    store_frag(xhi, xlo, nchunks_s, r, cl, acc);
                                 }
                             }
                         }
@@ -522,6 +569,18 @@ dec5_kernel(const Dec3Args a) {
                         }
                     }
                     __syncthreads();
+                }
+                // L2 prefetch of THIS layer's cross K/V block (static data, read five stages from now): the stages in between are
+                // latency-bound and leave HBM idle, so the one HBM-bound stage of the layer finds its stream in L2.  Every CTA
+                // requests a 1/grid slice in 16 KB pieces (one bulk-prefetch instruction per lane; a hint: no completion, no hazard).
+                if (slot == SL_LN1 && a.pf_ckv_bytes > 0 && warp == NW - 1) {
+                    const char* base = reinterpret_cast<const char*>(a.ckv) + (size_t)l * a.Mcap * 2 * d * sizeof(KVT);
+                    const size_t per = (((size_t)a.pf_ckv_bytes / 16 + gridDim.x - 1) / gridDim.x) * 16;
+                    const size_t b0 = (size_t)blockIdx.x * per, b1 = min((size_t)a.pf_ckv_bytes, b0 + per);
+                    for (size_t o = b0 + (size_t)lane * 16384; o < b1; o += 32 * 16384) {
+                        const uint32_t bytes = (uint32_t)min((size_t)16384, b1 - o);
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + o), "r"(bytes) : "memory");
+                    }
                 }
                 // prefetch the first A fragments of the NEXT linear stage: weights do not depend on activations
                 if (!pf_valid) {

@@ -102,8 +102,15 @@ Session::Session(Model* model, int64_t max_w, int64_t max_b, int64_t max_text_le
                     q.kind = D5_KIND_GEMM; q.W = Wp; q.bias = bias; q.N = N; q.n_slabs = n_slabs; q.stage = stage; q.emit = emit; q.src = src; q.ks = d;
                 };
                 auto ln = [&](Dec5Desc& q, const LayerNormW& w, int stage) {
-                    q.kind = D5_KIND_LN; q.g = w.g; q.b = w.b; q.eps = w.eps; q.stage = stage;
+                    q.kind = D5_KIND_LN; q.g = w.g; q.b = w.b; q.eps = w.eps; q.stage = stage; q.ks = d;
                 };
+                // The d x d projections (out, cross query, cross out) have only d/16 feature tiles -- 48 of 148 CTAs busy for small.en, each
+                // staging all K columns of every row.  When d/256 slabs x d/16 tiles still fit ONE round of the grid, they run as K slabs of
+                // 256 columns (one 32-column chunk per warp): three times the CTAs, a third of the staging each; the partial sums go to
+                // ypart and are folded, in a fixed order, by the consumer (the next LayerNorm stage / the cross-attention query load).
+                const int psl = d / 256;
+                const char* e_split = getenv("WB200_D5_SPLIT");
+                const bool split_dd = !(e_split && e_split[0] == '0') && d % 256 == 0 && psl >= 2 && psl <= 4 && (d / 16) * psl <= n_sm;
                 for (int l = 0; l < L; ++l) {
                     const DecBlockW& B = m->dec[(size_t)l];
                     Dec5Desc* q = ds.data() + (size_t)l * 16;
@@ -121,8 +128,15 @@ Session::Session(Model* model, int64_t max_w, int64_t max_b, int64_t max_text_le
                     // MLP2 K = 4d: 3 slabs of 4d/3 when that keeps the 8-warp K split (multiple of 256, <= 1280): d/16 tiles x 3 slabs
                     // = 144 items for small.en -> ONE round on 148 CTAs instead of 192 items in two
                     if ((4 * d) % 3 == 0 && (4 * d / 3) % 256 == 0 && 4 * d / 3 <= 1280) { q[10].n_slabs = 3; q[10].ks = 4 * d / 3; }
+                    if (split_dd) {
+                        for (int sl : {3, 5, 7}) { q[sl].n_slabs = psl; q[sl].ks = 256; q[sl].emit = D5_EM_PART; }
+                        q[4].stage = D5_ST_LN_FOLD; q[4].n_fold = psl; q[4].ks = 256;   // folds the out projection, feeds the split cross query
+                        q[8].stage = D5_ST_LN_FOLD; q[8].n_fold = psl;                  // folds the cross out projection
+                    }
+                    if (l > 0) q[0].n_fold = q[10].n_slabs;                             // folds MLP2 of the previous layer
                 }
                 ln(ds[(size_t)L * 16 + 11], m->dec_ln, D5_ST_LN_FOLD_NOPUB);
+                ds[(size_t)L * 16 + 11].n_fold = ds[(size_t)(L - 1) * 16 + 10].n_slabs;
                 gemm(ds[(size_t)L * 16 + 12], m->tok_emb16, nullptr, V, 1, D5_ST_PLANES, D5_EM_LOGITS, 3);
                 d5_desc.alloc(ds.size());
                 WB_CUDA(cudaMemcpy(d5_desc.p, ds.data(), ds.size() * sizeof(Dec5Desc), cudaMemcpyHostToDevice));
@@ -449,6 +463,15 @@ void Session::launch_v3(int R_, int pos0, int n_steps, int logits_from, bool use
     a.kv_half = kv_dtype == WB_KV_F16 ? 1 : 0;
     if (a.kv_half) { a.kc = kc16.p; a.vc = vc16.p; a.ckv = ckv16.p; } else { a.kc = kc.p; a.vc = vc.p; a.ckv = ckv.p; }
     a.row_window = row_window.p; a.win_row_off = d_win_row_off.p; a.win_T = d_win_T.p;
+    {   // decoder5.cu pulls each layer's cross K/V block into L2 ahead of its cross-attention stage when the block fits beside the
+        // layer's weights (one launch covering all windows only: row groups would each re-request everything); WB200_D5_PF=<MB> sets
+        // the budget, 0 disables
+        const char* e_pf = getenv("WB200_D5_PF");
+        const int64_t pf_budget = (int64_t)(e_pf ? atoll(e_pf) : 96) * 1000000;
+        const int64_t layer_bytes = M_tot * 2 * d * (int64_t)(kv_dtype == WB_KV_F16 ? 2 : 4);
+        a.pf_ckv_bytes = (R_ <= 32 && layer_bytes <= pf_budget) ? (layer_bytes / 16) * 16 : 0;
+    }
+    { const char* e_bulk = getenv("WB200_D5_BULK"); a.d5_bulk_stage = (e_bulk && e_bulk[0] == '0') ? 0 : 1; }
     a.anc = anc_identity ? nullptr : (anc_cur == 0 ? anc0.p : anc1.p);
     a.n_splits = std::max(1, std::min(16, n_sm / std::max(1, R_ * H)));
     a.part_o = part_o.p; a.part_m = part_m.p; a.part_l = part_l.p;
