@@ -16,6 +16,9 @@ namespace {
 
 constexpr int NT = 256;
 constexpr int NW = 8;
+#ifndef WB_ATTN_PAIR
+#define WB_ATTN_PAIR 1   // attn_warp_bulk: two 8-key batches per iteration
+#endif
 
 __device__ __forceinline__ float gelu_erf(float x) {
     const float t = __fadd_rn(erff(__fdiv_rn(x, 1.41421356237309504880f)), 1.0f);
@@ -602,6 +605,89 @@ __device__ __forceinline__ void attn_warp_bulk(const float* q_smem, const KT* ba
 #pragma unroll
         for (int s = 0; s < NSTG - 1; ++s) issue(s);
     }
+#if WB_ATTN_PAIR
+    // TWO batches (16 keys per warp) per iteration: the loop is bound by its dependent chain (wait -> loads -> 16-FMA dot ->
+    // quad shuffles -> max / exp -> rescale), ~1100 cycles per iteration whatever the element size (decoder5.cu stage trace:
+    // fp16 K/V streamed at half the bytes per second of fp32), so two independent score chains share one rescale of the state.
+    auto load16 = [&](const unsigned char* p16, int par, float (&f)[16]) {   // this lane's 16 dims of one K or V row
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const int phys = (l4 + 4 * c) ^ (4 * par);
+            const uint4 u = *reinterpret_cast<const uint4*>(p16 + phys * 16);
+            if constexpr (sizeof(KT) == 4) {
+                f[c * 4] = __uint_as_float(u.x); f[c * 4 + 1] = __uint_as_float(u.y); f[c * 4 + 2] = __uint_as_float(u.z); f[c * 4 + 3] = __uint_as_float(u.w);
+            } else {
+                float w[8];
+                cvt8(u, w);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[c * 8 + e] = w[e];
+            }
+        }
+    };
+    auto wait_slot = [&](unsigned int cnt) {
+        const uint32_t mb = (uint32_t)__cvta_generic_to_shared(mbar + (int)(cnt % NSTG)), parity = (cnt / NSTG) & 1;
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(mb), "r"(parity) : "memory");
+        }
+    };
+    int issued = min(NSTG - 1, n_it);   // by attn_bulk_prefill or just above
+    const unsigned qmask = 0xfu << (lane & 28);
+#pragma unroll 1
+    for (int it = 0; it < n_it; it += 2) {
+        __syncwarp();                 // every lane is done with the slots that are refilled now (consumed one iteration ago)
+        for (const int lim = min(n_it, it + NSTG); issued < lim; ++issued) issue(issued);
+        const bool two = it + 1 < n_it;
+        const unsigned int cnt0 = ring_count + (unsigned int)it;
+        wait_slot(cnt0);
+        if (two) wait_slot(cnt0 + 1u);
+        const int j0 = (wslot + it * nwarps) * 8 + sub, j1 = j0 + nwarps * 8;
+        const bool v0 = j0 < n_keys, v1 = two && j1 < n_keys;   // v1 implies v0
+        if (v0) {
+            const unsigned char* row0 = ring + (int)(cnt0 % NSTG) * STGB + sub * ROWB;
+            const unsigned char* row1 = ring + (int)((cnt0 + 1u) % NSTG) * STGB + sub * ROWB;
+            const int par0 = (swz + j0) & 1, par1 = (swz + j1) & 1;
+            float s0, s1 = -INFINITY;
+            {
+                float k0[16], k1[16];
+                load16(row0, par0, k0);
+                if (v1) load16(row1, par1, k1);
+                float a0 = 0.0f, b0 = 0.0f, a1 = 0.0f, b1 = 0.0f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) { a0 = fmaf(q[c], k0[c], a0); b0 = fmaf(q[c + 8], k0[c + 8], b0); }
+                s0 = a0 + b0;
+                if (v1) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) { a1 = fmaf(q[c], k1[c], a1); b1 = fmaf(q[c + 8], k1[c + 8], b1); }
+                    s1 = a1 + b1;
+                }
+            }
+            s0 += __shfl_xor_sync(qmask, s0, 1);
+            s0 += __shfl_xor_sync(qmask, s0, 2);
+            if (v1) {
+                s1 += __shfl_xor_sync(qmask, s1, 1);
+                s1 += __shfl_xor_sync(qmask, s1, 2);
+            }
+            const float mn = fmaxf(A.m, fmaxf(s0, s1));
+            const float corr = expf(A.m - mn);
+            const float e0 = expf(s0 - mn), e1 = expf(s1 - mn);   // s1 = -inf without a second key: e1 = 0
+            A.l = A.l * corr + (e0 + e1);
+            A.m = mn;
+            asm volatile("" ::: "memory");   // keep the V loads behind the scores (register pressure)
+            {
+                float vv[16];
+                load16(row0 + ROWB / 2, par0, vv);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) A.o[c] = fmaf(e0, vv[c], A.o[c] * corr);
+                if (v1) {
+                    load16(row1 + ROWB / 2, par1, vv);
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) A.o[c] = fmaf(e1, vv[c], A.o[c]);
+                }
+            }
+        }
+    }
+#else
 #pragma unroll 1
     for (int it = 0; it < n_it; ++it) {
         __syncwarp();                 // every lane is done with the slot that is refilled now (consumed one iteration ago)
@@ -653,6 +739,7 @@ __device__ __forceinline__ void attn_warp_bulk(const float* q_smem, const KT* ba
             for (int c = 0; c < 16; ++c) A.o[c] = fmaf(e, vf[c], A.o[c] * corr);
         }
     }
+#endif
     ring_count += (unsigned int)n_it;
     __syncwarp();
 #pragma unroll

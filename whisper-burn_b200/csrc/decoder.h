@@ -56,8 +56,6 @@ struct Dec3Args {
     const void* ckv = nullptr;            // [L][Mcap][2d]
     int ckv_hm = 0;                       // 1: head-major cross K/V (encoder.cu ckv_relayout_kernel), 0: GEMM row-major order
     int kv_half = 0;
-    int64_t pf_ckv_bytes = 0;             // decoder5.cu: bytes of a layer's cross K/V block every CTA helps to pull into L2 ahead of the cross-attention stage (0: off)
-    int d5_bulk_stage = 1;                // decoder5.cu: activation planes staged by bulk copies (TMA engine) instead of per-thread cp.async
     int kv_row0 = 0;                      // decoder5.cu row groups: local row r of this launch is cache row r + kv_row0 (ancestry entries are absolute)
     const int* row_window = nullptr;
     const int64_t* win_row_off = nullptr;

@@ -123,12 +123,6 @@ dec5_kernel(const Dec3Args a) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     unsigned int kv_count = 0;   // batches this warp has pushed through its K/V ring
-    uint64_t* st_bar = kv_bar + NW * 8;   // activation-plane staging by bulk copies: one mbarrier, one phase per staging
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(st_bar)));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    unsigned int st_phase = 0;
     __syncthreads();
     unsigned int gen = 0;
     int tr_n = 0;
@@ -366,33 +360,13 @@ dec5_kernel(const Dec3Args a) {
                                 const uint4* sh = (D.src == 2 ? hid_hi : D.src == 3 ? xn_hi : att_hi) + (int64_t)slab * (PL_ROWS * ks / 8);
                                 const uint4* sl = sh + (D.src == 2 ? 4 * pl_plane : pl_plane);
                                 const int n16 = NT8 * nchunks_s * 32;
-                                if (a.d5_bulk_stage) {
-                                    // two contiguous blocks -> bulk copies by the TMA engine, 8 KB pieces, completion on one mbarrier (73 KB per CTA
-                                    // for small.en: 0.8 us instead of 1.4 us of per-thread cp.async, scripts/ubench).  The planes were written by other
-                                    // CTAs through the generic proxy (ordered by the grid barrier) and this buffer was last read through it.
-                                    const uint32_t mb = (uint32_t)__cvta_generic_to_shared(st_bar);
-                                    if (tid == 0) {
-                                        asm volatile("fence.proxy.async;" ::: "memory");
-                                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"((uint32_t)n16 * 32u) : "memory");
-                                        for (int o = 0; o < n16; o += 512) {
-                                            const uint32_t bytes = (uint32_t)min(512, n16 - o) * 16u;
-                                            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"((uint32_t)__cvta_generic_to_shared(xhi + o)),
-                                                         "l"(sh + o), "r"(bytes), "r"(mb) : "memory");
-                                            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"((uint32_t)__cvta_generic_to_shared(xlo + o)),
-                                                         "l"(sl + o), "r"(bytes), "r"(mb) : "memory");
-                                        }
-                                    }
-                                    uint32_t done = 0;
-                                    while (!done)
-                                        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(mb), "r"(st_phase) : "memory");
-                                    st_phase ^= 1u;
-                                } else {
-                                    for (int i = tid; i < n16; i += NT) {
-                                        cp_async16(xhi + i, sh + i);
-                                        cp_async16(xlo + i, sl + i);
-                                    }
-                                    cp_async_wait_all();
+                                // (bulk copies by one thread were measured here: 0.6 us faster in isolation -- scripts/ubench -- but 4 % slower in
+                                // the kernel, profiles/r02_dec5_ab.txt; the per-thread cp.async stays)
+                                for (int i = tid; i < n16; i += NT) {
+                                    cp_async16(xhi + i, sh + i);
+                                    cp_async16(xlo + i, sl + i);
                                 }
+                                cp_async_wait_all();
                             } else {
                                 // ---- merge the cross-attention split partials (S > 1) while staging
                                 float* wn = red;   // [RP][H][S] normalised split weights
@@ -569,18 +543,6 @@ dec5_kernel(const Dec3Args a) {
                         }
                     }
                     __syncthreads();
-                }
-                // L2 prefetch of THIS layer's cross K/V block (static data, read five stages from now): the stages in between are
-                // latency-bound and leave HBM idle, so the one HBM-bound stage of the layer finds its stream in L2.  Every CTA
-                // requests a 1/grid slice in 16 KB pieces (one bulk-prefetch instruction per lane; a hint: no completion, no hazard).
-                if (slot == SL_LN1 && a.pf_ckv_bytes > 0 && warp == NW - 1) {
-                    const char* base = reinterpret_cast<const char*>(a.ckv) + (size_t)l * a.Mcap * 2 * d * sizeof(KVT);
-                    const size_t per = (((size_t)a.pf_ckv_bytes / 16 + gridDim.x - 1) / gridDim.x) * 16;
-                    const size_t b0 = (size_t)blockIdx.x * per, b1 = min((size_t)a.pf_ckv_bytes, b0 + per);
-                    for (size_t o = b0 + (size_t)lane * 16384; o < b1; o += 32 * 16384) {
-                        const uint32_t bytes = (uint32_t)min((size_t)16384, b1 - o);
-                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + o), "r"(bytes) : "memory");
-                    }
                 }
                 // prefetch the first A fragments of the NEXT linear stage: weights do not depend on activations
                 if (!pf_valid) {

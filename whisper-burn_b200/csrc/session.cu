@@ -463,15 +463,6 @@ void Session::launch_v3(int R_, int pos0, int n_steps, int logits_from, bool use
     a.kv_half = kv_dtype == WB_KV_F16 ? 1 : 0;
     if (a.kv_half) { a.kc = kc16.p; a.vc = vc16.p; a.ckv = ckv16.p; } else { a.kc = kc.p; a.vc = vc.p; a.ckv = ckv.p; }
     a.row_window = row_window.p; a.win_row_off = d_win_row_off.p; a.win_T = d_win_T.p;
-    {   // decoder5.cu pulls each layer's cross K/V block into L2 ahead of its cross-attention stage when the block fits beside the
-        // layer's weights (one launch covering all windows only: row groups would each re-request everything); WB200_D5_PF=<MB> sets
-        // the budget, 0 disables
-        const char* e_pf = getenv("WB200_D5_PF");
-        const int64_t pf_budget = (int64_t)(e_pf ? atoll(e_pf) : 96) * 1000000;
-        const int64_t layer_bytes = M_tot * 2 * d * (int64_t)(kv_dtype == WB_KV_F16 ? 2 : 4);
-        a.pf_ckv_bytes = (R_ <= 32 && layer_bytes <= pf_budget) ? (layer_bytes / 16) * 16 : 0;
-    }
-    { const char* e_bulk = getenv("WB200_D5_BULK"); a.d5_bulk_stage = (e_bulk && e_bulk[0] == '0') ? 0 : 1; }
     a.anc = anc_identity ? nullptr : (anc_cur == 0 ? anc0.p : anc1.p);
     a.n_splits = std::max(1, std::min(16, n_sm / std::max(1, R_ * H)));
     a.part_o = part_o.p; a.part_m = part_m.p; a.part_l = part_l.p;
