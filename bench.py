@@ -33,7 +33,7 @@ sys.path.insert(0, str(ROOT))
 
 CHUNK_SAMPLES = 480000
 CHUNK_SECONDS = 30.0
-DEFAULT_CONFIGS = "tiny.en:1:f32,small.en:8:f32,small.en:8:f16"
+DEFAULT_CONFIGS = "tiny.en:1:f32,small.en:8:f32,small.en:8:f16,tiny.en:1:f16"
 
 
 def parse_args():

@@ -16,9 +16,6 @@ namespace {
 
 constexpr int NT = 256;
 constexpr int NW = 8;
-#ifndef WB_ATTN_PAIR
-#define WB_ATTN_PAIR 1   // attn_warp_bulk: two 8-key batches per iteration
-#endif
 
 __device__ __forceinline__ float gelu_erf(float x) {
     const float t = __fadd_rn(erff(__fdiv_rn(x, 1.41421356237309504880f)), 1.0f);
@@ -537,36 +534,45 @@ __device__ __forceinline__ void attn_warp_ring(const float* q_smem, int n_keys, 
 }
 
 // Bulk-copy variant for the head-major cross K/V layout (encoder.cu ckv_relayout_kernel): the unit's keys are ONE contiguous
-// [n_keys][128] block, so a batch of 8 keys (K and V) is a single cp.async.bulk (TMA engine, no tensor map) into this warp's
-// ring, completion on the stage's mbarrier; NSTG-1 batches are in flight per warp.  The warps of the unit take batches
-// round-robin (wslot of nwarps).  Lane (sub, l4) handles key `sub` of the batch and the 16-byte chunks l4 + 4c of its K and V
-// rows -- with the layout's XOR-4 swizzle on odd positions the 8 lanes of a quarter warp hit 8 distinct bank groups.
+// [n_keys][128] block, so a batch of keys (K and V rows) is a single cp.async.bulk (TMA engine, no tensor map) into this warp's
+// ring, completion on the stage's mbarrier; NSTG-1 batches are in flight per warp.  A batch is 4 KB whatever the element type:
+// 8 keys of fp32 or 16 keys of fp16 -- with 8-key (2 KB) fp16 batches the fp16 cache streamed at HALF the bytes per second of the
+// fp32 one (decoder5.cu stage trace: 13.6 us vs 16.2 us for half the bytes): the stage is paced by batches, not by bytes.
+// The warps of the unit take batches round-robin (wslot of nwarps).  Lane (sub, l4) handles key `sub` (and `sub + 8` of a 16-key
+// batch: two independent score chains, one rescale of the running state) and the 16-byte chunks l4 + 4c of its K and V rows --
+// with the layout's XOR-4 swizzle on odd positions the 8 lanes of a quarter warp hit 8 distinct bank groups.
 // ring_count: batches this warp has pushed through its ring since kernel start (stage / parity bookkeeping).
 template <typename KT>
 __device__ __forceinline__ int attn_bulk_dim(int l4, int i) {   // which of the 64 head dims is o[i] / q[i] of lane l4
     constexpr int CE = 16 / (int)sizeof(KT);                    // elements per 16-byte chunk
     return (l4 + 4 * (i / CE)) * CE + i % CE;
 }
+template <typename KT>
+struct AttnBulkGeom {
+    static constexpr int ROWB = 128 * (int)sizeof(KT);   // bytes of one key: K row | V row of this head
+    static constexpr int STGB = 4096;                    // bytes per batch / ring stage
+    static constexpr int KPB = STGB / ROWB;              // keys per batch: 8 (fp32) or 16 (fp16)
+};
 // The first NSTG-1 batches of attn_warp_bulk, issued ahead of time (the K/V rows are static: nothing to wait for); the
 // matching attn_warp_bulk call passes prefilled = true and the SAME base / n_keys / wslot / nwarps / ring_count.
 template <int NSTG, typename KT>
 __device__ __forceinline__ void attn_bulk_prefill(const KT* base, int n_keys, int wslot, int nwarps, unsigned char* ring, uint64_t* mbar,
                                                   unsigned int ring_count) {
-    constexpr int ROWB = 128 * (int)sizeof(KT), STGB = 8 * ROWB;
+    constexpr int ROWB = AttnBulkGeom<KT>::ROWB, STGB = AttnBulkGeom<KT>::STGB, KPB = AttnBulkGeom<KT>::KPB;
     if ((threadIdx.x & 31) != 0) return;
-    const int n_batches = (n_keys + 7) >> 3;
+    const int n_batches = (n_keys + KPB - 1) / KPB;
     const int n_it = n_batches > wslot ? (n_batches - wslot + nwarps - 1) / nwarps : 0;
 #pragma unroll
     for (int it = 0; it < NSTG - 1; ++it) {
         if (it < n_it) {
             const int bb = wslot + it * nwarps;
             const int slot = (int)((ring_count + (unsigned int)it) % NSTG);
-            const uint32_t bytes = (uint32_t)min(8, n_keys - bb * 8) * ROWB;
+            const uint32_t bytes = (uint32_t)min(KPB, n_keys - bb * KPB) * ROWB;
             const uint32_t mb = (uint32_t)__cvta_generic_to_shared(mbar + slot);
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                              (uint32_t)__cvta_generic_to_shared(ring + slot * STGB)),
-                         "l"(base + (int64_t)bb * 8 * 128), "r"(bytes), "r"(mb)
+                         "l"(base + (int64_t)bb * KPB * 128), "r"(bytes), "r"(mb)
                          : "memory");
         }
     }
@@ -576,7 +582,7 @@ __device__ __forceinline__ void attn_warp_bulk(const float* q_smem, const KT* ba
                                                unsigned char* ring, uint64_t* mbar, unsigned int& ring_count, AttnAcc& A,
                                                bool prefilled = false) {
     constexpr int CE = 16 / (int)sizeof(KT), NC = 16 / CE;      // chunk elements; chunks per lane and tensor
-    constexpr int ROWB = 128 * (int)sizeof(KT), STGB = 8 * ROWB;
+    constexpr int ROWB = AttnBulkGeom<KT>::ROWB, STGB = AttnBulkGeom<KT>::STGB, KPB = AttnBulkGeom<KT>::KPB;
     const int lane = threadIdx.x & 31, sub = lane >> 2, l4 = lane & 3;
     float q[16];
 #pragma unroll
@@ -585,30 +591,22 @@ __device__ __forceinline__ void attn_warp_bulk(const float* q_smem, const KT* ba
     A.l = 0.0f;
 #pragma unroll
     for (int c = 0; c < 16; ++c) A.o[c] = 0.0f;
-    const int n_batches = (n_keys + 7) >> 3;
+    const int n_batches = (n_keys + KPB - 1) / KPB;
     const int n_it = n_batches > wslot ? (n_batches - wslot + nwarps - 1) / nwarps : 0;
     auto issue = [&](int it) {
         if (it < n_it && lane == 0) {
             const int bb = wslot + it * nwarps;
             const unsigned int cnt = ring_count + (unsigned int)it;
             const int slot = (int)(cnt % NSTG);
-            const uint32_t bytes = (uint32_t)min(8, n_keys - bb * 8) * ROWB;
+            const uint32_t bytes = (uint32_t)min(KPB, n_keys - bb * KPB) * ROWB;
             const uint32_t mb = (uint32_t)__cvta_generic_to_shared(mbar + slot);
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                              (uint32_t)__cvta_generic_to_shared(ring + slot * STGB)),
-                         "l"(base + (int64_t)bb * 8 * 128), "r"(bytes), "r"(mb)
+                         "l"(base + (int64_t)bb * KPB * 128), "r"(bytes), "r"(mb)
                          : "memory");
         }
     };
-    if (!prefilled) {
-#pragma unroll
-        for (int s = 0; s < NSTG - 1; ++s) issue(s);
-    }
-#if WB_ATTN_PAIR
-    // TWO batches (16 keys per warp) per iteration: the loop is bound by its dependent chain (wait -> loads -> 16-FMA dot ->
-    // quad shuffles -> max / exp -> rescale), ~1100 cycles per iteration whatever the element size (decoder5.cu stage trace:
-    // fp16 K/V streamed at half the bytes per second of fp32), so two independent score chains share one rescale of the state.
     auto load16 = [&](const unsigned char* p16, int par, float (&f)[16]) {   // this lane's 16 dims of one K or V row
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
@@ -624,70 +622,11 @@ __device__ __forceinline__ void attn_warp_bulk(const float* q_smem, const KT* ba
             }
         }
     };
-    auto wait_slot = [&](unsigned int cnt) {
-        const uint32_t mb = (uint32_t)__cvta_generic_to_shared(mbar + (int)(cnt % NSTG)), parity = (cnt / NSTG) & 1;
-        uint32_t done = 0;
-        while (!done) {
-            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(mb), "r"(parity) : "memory");
-        }
-    };
-    int issued = min(NSTG - 1, n_it);   // by attn_bulk_prefill or just above
-    const unsigned qmask = 0xfu << (lane & 28);
-#pragma unroll 1
-    for (int it = 0; it < n_it; it += 2) {
-        __syncwarp();                 // every lane is done with the slots that are refilled now (consumed one iteration ago)
-        for (const int lim = min(n_it, it + NSTG); issued < lim; ++issued) issue(issued);
-        const bool two = it + 1 < n_it;
-        const unsigned int cnt0 = ring_count + (unsigned int)it;
-        wait_slot(cnt0);
-        if (two) wait_slot(cnt0 + 1u);
-        const int j0 = (wslot + it * nwarps) * 8 + sub, j1 = j0 + nwarps * 8;
-        const bool v0 = j0 < n_keys, v1 = two && j1 < n_keys;   // v1 implies v0
-        if (v0) {
-            const unsigned char* row0 = ring + (int)(cnt0 % NSTG) * STGB + sub * ROWB;
-            const unsigned char* row1 = ring + (int)((cnt0 + 1u) % NSTG) * STGB + sub * ROWB;
-            const int par0 = (swz + j0) & 1, par1 = (swz + j1) & 1;
-            float s0, s1 = -INFINITY;
-            {
-                float k0[16], k1[16];
-                load16(row0, par0, k0);
-                if (v1) load16(row1, par1, k1);
-                float a0 = 0.0f, b0 = 0.0f, a1 = 0.0f, b1 = 0.0f;
+    if (!prefilled) {
 #pragma unroll
-                for (int c = 0; c < 8; ++c) { a0 = fmaf(q[c], k0[c], a0); b0 = fmaf(q[c + 8], k0[c + 8], b0); }
-                s0 = a0 + b0;
-                if (v1) {
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) { a1 = fmaf(q[c], k1[c], a1); b1 = fmaf(q[c + 8], k1[c + 8], b1); }
-                    s1 = a1 + b1;
-                }
-            }
-            s0 += __shfl_xor_sync(qmask, s0, 1);
-            s0 += __shfl_xor_sync(qmask, s0, 2);
-            if (v1) {
-                s1 += __shfl_xor_sync(qmask, s1, 1);
-                s1 += __shfl_xor_sync(qmask, s1, 2);
-            }
-            const float mn = fmaxf(A.m, fmaxf(s0, s1));
-            const float corr = expf(A.m - mn);
-            const float e0 = expf(s0 - mn), e1 = expf(s1 - mn);   // s1 = -inf without a second key: e1 = 0
-            A.l = A.l * corr + (e0 + e1);
-            A.m = mn;
-            asm volatile("" ::: "memory");   // keep the V loads behind the scores (register pressure)
-            {
-                float vv[16];
-                load16(row0 + ROWB / 2, par0, vv);
-#pragma unroll
-                for (int c = 0; c < 16; ++c) A.o[c] = fmaf(e0, vv[c], A.o[c] * corr);
-                if (v1) {
-                    load16(row1 + ROWB / 2, par1, vv);
-#pragma unroll
-                    for (int c = 0; c < 16; ++c) A.o[c] = fmaf(e1, vv[c], A.o[c]);
-                }
-            }
-        }
+        for (int s = 0; s < NSTG - 1; ++s) issue(s);
     }
-#else
+    const unsigned qmask = 0xfu << (lane & 28);
 #pragma unroll 1
     for (int it = 0; it < n_it; ++it) {
         __syncwarp();                 // every lane is done with the slot that is refilled now (consumed one iteration ago)
@@ -702,44 +641,71 @@ __device__ __forceinline__ void attn_warp_bulk(const float* q_smem, const KT* ba
             }
         }
         const int bb = wslot + it * nwarps;
-        const int j = bb * 8 + sub;
-        if (j < n_keys) {
-            const int par = (swz + j) & 1;
-            const unsigned char* row = ring + slot * STGB + sub * ROWB;
-            float kf[16], vf[16];
+        const int j0 = bb * KPB + sub;
+        if (j0 < n_keys) {
+            const unsigned char* row0 = ring + slot * STGB + sub * ROWB;
+            const int par0 = (swz + j0) & 1;
+            if constexpr (KPB == 8) {
+                float kf[16], vf[16];
+                load16(row0, par0, kf);
+                load16(row0 + ROWB / 2, par0, vf);
+                float s = 0.0f;
 #pragma unroll
-            for (int c = 0; c < NC; ++c) {
-                const int phys = (l4 + 4 * c) ^ (4 * par);
-                const uint4 kk = *reinterpret_cast<const uint4*>(row + phys * 16);
-                const uint4 vv = *reinterpret_cast<const uint4*>(row + ROWB / 2 + phys * 16);
-                if constexpr (sizeof(KT) == 4) {
-                    kf[c * 4] = __uint_as_float(kk.x); kf[c * 4 + 1] = __uint_as_float(kk.y); kf[c * 4 + 2] = __uint_as_float(kk.z); kf[c * 4 + 3] = __uint_as_float(kk.w);
-                    vf[c * 4] = __uint_as_float(vv.x); vf[c * 4 + 1] = __uint_as_float(vv.y); vf[c * 4 + 2] = __uint_as_float(vv.z); vf[c * 4 + 3] = __uint_as_float(vv.w);
-                } else {
-                    float w[8];
-                    cvt8(kk, w);
+                for (int c = 0; c < 16; ++c) s = fmaf(q[c], kf[c], s);
+                s += __shfl_xor_sync(qmask, s, 1);
+                s += __shfl_xor_sync(qmask, s, 2);
+                const float mn = fmaxf(A.m, s);
+                const float corr = expf(A.m - mn);
+                const float e = expf(s - mn);
+                A.l = A.l * corr + e;
+                A.m = mn;
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) kf[c * 8 + e] = w[e];
-                    cvt8(vv, w);
+                for (int c = 0; c < 16; ++c) A.o[c] = fmaf(e, vf[c], A.o[c] * corr);
+            } else {
+                // keys sub and sub + 8 of the batch: two score chains, one rescale
+                const int j1 = j0 + 8;
+                const bool v1 = j1 < n_keys;
+                const unsigned char* row1 = row0 + 8 * ROWB;
+                const int par1 = (swz + j1) & 1;
+                float s0, s1 = -INFINITY;
+                {
+                    float k0[16], k1[16];
+                    load16(row0, par0, k0);
+                    if (v1) load16(row1, par1, k1);
+                    float a0 = 0.0f, a1 = 0.0f;
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) vf[c * 8 + e] = w[e];
+                    for (int c = 0; c < 16; ++c) a0 = fmaf(q[c], k0[c], a0);
+                    s0 = a0;
+                    if (v1) {
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) a1 = fmaf(q[c], k1[c], a1);
+                        s1 = a1;
+                    }
+                }
+                s0 += __shfl_xor_sync(qmask, s0, 1);
+                s0 += __shfl_xor_sync(qmask, s0, 2);
+                if (v1) {   // uniform over the four lanes of a key
+                    s1 += __shfl_xor_sync(qmask, s1, 1);
+                    s1 += __shfl_xor_sync(qmask, s1, 2);
+                }
+                const float mn = fmaxf(A.m, fmaxf(s0, s1));
+                const float corr = expf(A.m - mn);
+                const float e0 = expf(s0 - mn), e1 = expf(s1 - mn);   // s1 = -inf without a second key: e1 = 0
+                A.l = A.l * corr + (e0 + e1);
+                A.m = mn;
+                asm volatile("" ::: "memory");   // keep the V loads behind the scores (register pressure)
+                float vv[16];
+                load16(row0 + ROWB / 2, par0, vv);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) A.o[c] = fmaf(e0, vv[c], A.o[c] * corr);
+                if (v1) {
+                    load16(row1 + ROWB / 2, par1, vv);
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) A.o[c] = fmaf(e1, vv[c], A.o[c]);
                 }
             }
-            float s = 0.0f;
-#pragma unroll
-            for (int c = 0; c < 16; ++c) s = fmaf(q[c], kf[c], s);
-            s += __shfl_xor_sync(0xfu << (lane & 28), s, 1);
-            s += __shfl_xor_sync(0xfu << (lane & 28), s, 2);
-            const float mn = fmaxf(A.m, s);
-            const float corr = expf(A.m - mn);
-            const float e = expf(s - mn);
-            A.l = A.l * corr + e;
-            A.m = mn;
-#pragma unroll
-            for (int c = 0; c < 16; ++c) A.o[c] = fmaf(e, vf[c], A.o[c] * corr);
         }
     }
-#endif
     ring_count += (unsigned int)n_it;
     __syncwarp();
 #pragma unroll

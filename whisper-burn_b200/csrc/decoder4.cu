@@ -327,7 +327,6 @@ dec4_kernel(const Dec3Args a) {
     const int rank = (int)cl.block_rank();
     const int row = blockIdx.x / CS;              // batch row of this cluster
     const bool active = row < R;
-    const int gw = blockIdx.x * NW + warp, n_gw = gridDim.x * NW;
 
     float* lnp = sm + warp * 2 * D;   // [NW][2D] LayerNorm gamma | beta of the next LayerNorm, one private copy per warp
     float* qkv_s = sm + NW * 2 * D;   // [3D]  q | k | v of the current position
@@ -384,9 +383,12 @@ dec4_kernel(const Dec3Args a) {
         static_assert(LG_NBUF * LG_RB * D * 2 >= LG_NBUF * (int)BLKB, "ring slot too small");
         const __half* Et = reinterpret_cast<const __half*>(a.E_tiled);
         const int v_tiles = (V + 15) / 16;
-        const int my_tiles = gw < v_tiles ? (v_tiles - gw + n_gw - 1) / n_gw : 0;
+        // tile t belongs to CTA t % grid and, inside it, to warp (t / grid) % NW: every CTA streams the same number of tiles (+-1) --
+        // with tiles dealt to the warps of the whole grid in order, the first CTAs got 32 tiles and the last 24 (3242 tiles, 896 warps)
+        const int t0w = (int)blockIdx.x + (int)gridDim.x * warp, tstep = (int)gridDim.x * NW;
+        const int my_tiles = t0w < v_tiles ? (v_tiles - t0w + tstep - 1) / tstep : 0;
         const int total = my_tiles * 2;                        // half-tiles of this warp
-        auto tile_of = [&](int i) { return gw + i * n_gw; };
+        auto tile_of = [&](int i) { return t0w + i * tstep; };
         uint8_t* wring = ring + (size_t)warp * RINGW;
         uint64_t* wbar = lg_bar + warp * LG_NBUF;
         auto issue = [&](int it) {

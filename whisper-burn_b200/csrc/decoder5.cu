@@ -102,7 +102,6 @@ dec5_kernel(const Dec3Args a) {
     extern __shared__ __align__(16) float sm[];
     const int d = a.d, H = a.H, L = a.L, V = a.V, R = a.R, t_max = a.t_max;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int gw = blockIdx.x * NW + warp, n_gw = gridDim.x * NW;
     constexpr int RP = NT8 * 8;
     constexpr int KC = DEC5_KC;
     constexpr int NE = (16 * RP + NT - 1) / NT;
@@ -117,7 +116,7 @@ dec5_kernel(const Dec3Args a) {
     GemmDesc* ds = reinterpret_cast<GemmDesc*>(wo + NW * 64);   // [L * 16 + 16] stage descriptors: a global load per stage would be a dependent round trip
     for (int i = tid; i < (L * 16 + 16) * (int)(sizeof(GemmDesc) / 16); i += NT) reinterpret_cast<uint4*>(ds)[i] = __ldg(reinterpret_cast<const uint4*>(a.d5) + i);
     uint64_t* kv_bar = reinterpret_cast<uint64_t*>(ds + L * 16 + 16);   // [NW][KV_STG] cross-attention K/V ring: one mbarrier per stage
-    constexpr int KV_STG = RING_W / (8 * 128 * (int)sizeof(KVT));          // fp32: 4 stages of 8 keys, fp16: 8
+    constexpr int KV_STG = RING_W / AttnBulkGeom<KVT>::STGB;               // 4 stages of 4 KB: 8 fp32 keys or 16 fp16 keys each
     if (lane == 0) {
         for (int j = 0; j < KV_STG; ++j) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(kv_bar + warp * KV_STG + j)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -489,11 +488,13 @@ dec5_kernel(const Dec3Args a) {
                             const __half* E = reinterpret_cast<const __half*>(D.W);
                             const int g = lane >> 2, t = lane & 3;
                             const int v_tiles = (V + 15) / 16, ngrp = d / (32 * GC);
-                            const int my_tiles = gw < v_tiles ? (v_tiles - gw + n_gw - 1) / n_gw : 0;
+                            // tile t: CTA t % grid, warp (t / grid) % NW -- every CTA streams the same number of tiles (+-1)
+                            const int t0w = (int)blockIdx.x + (int)gridDim.x * warp, tstep = (int)gridDim.x * NW;
+                            const int my_tiles = t0w < v_tiles ? (v_tiles - t0w + tstep - 1) / tstep : 0;
                             const int total = my_tiles * ngrp;
                             uint4 A0[GC][2], A1[GC][2];
                             auto load_grp = [&](int it, uint4 (&A)[GC][2]) {
-                                const int vt = gw + (it / ngrp) * n_gw, grp = it % ngrp;
+                                const int vt = t0w + (it / ngrp) * tstep, grp = it % ngrp;
                                 const int ra = min(vt * 16 + g, V - 1), rb = min(vt * 16 + g + 8, V - 1);
                                 const uint4* pa = reinterpret_cast<const uint4*>(E + (int64_t)ra * d + grp * (32 * GC) + t * 8);
                                 const uint4* pb = reinterpret_cast<const uint4*>(E + (int64_t)rb * d + grp * (32 * GC) + t * 8);
@@ -526,7 +527,7 @@ dec5_kernel(const Dec3Args a) {
                                     }
                                 }
                                 if (grp == ngrp - 1) {
-                                    const int n0 = (gw + (it / ngrp) * n_gw) * 16;
+                                    const int n0 = (t0w + (it / ngrp) * tstep) * 16;
 #pragma unroll
                                     for (int j = 0; j < NT8; ++j) {
                                         const int r0 = j * 8 + 2 * t;
