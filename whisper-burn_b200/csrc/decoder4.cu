@@ -728,9 +728,11 @@ dec4_kernel(const Dec3Args a) {
             if (want_logits && rank == 0 && warp == 0) {
                 x_update<PF>(x, xb + xsel * D, dl_s, nullptr);
                 ln_warp<D, PF>(x, lnp, a.lnf_eps, a.eps_outside, xn_s);
+                // RC == 4 (<= 4 rows): the residual plane of row r travels as batch column r + 4 of the SAME plane, so one MMA yields
+                // the hi product in columns 0..3 and the lo product in columns 4..7 (half the tensor-core instructions of the stage)
 #pragma unroll
                 for (int k = 0; k < PF; ++k)
-                    store_frag(gpl_hi, gpl_lo, D / 32, row, 4 * (lane + 32 * k), reinterpret_cast<const float4*>(xn_s)[lane + 32 * k]);
+                    store_frag(gpl_hi, RC == 4 ? gpl_hi + 16 : gpl_lo, D / 32, row, 4 * (lane + 32 * k), reinterpret_cast<const float4*>(xn_s)[lane + 32 * k]);
                 ln_fetch<D, PF>(lnp, a.layers[0].ln1_g, a.layers[0].ln1_b);   // LN1 of layer 0 for the next position
             }
         }
@@ -779,11 +781,13 @@ dec4_kernel(const Dec3Args a) {
                     const uint4 a8 = *reinterpret_cast<const uint4*>(blk + (size_t)(g + 8) * (KH * 2) + c * 64 + t * 16);
                     const int chunk = half * NCH + c;
                     const uint4 bh = pl_hi[chunk * 32 + lane];
-                    const uint4 bl = pl_lo[chunk * 32 + lane];
                     mma16816(ah, a0.x, a8.x, a0.y, a8.y, bh.x, bh.y);
                     mma16816(ah, a0.z, a8.z, a0.w, a8.w, bh.z, bh.w);
-                    mma16816(al, a0.x, a8.x, a0.y, a8.y, bl.x, bl.y);
-                    mma16816(al, a0.z, a8.z, a0.w, a8.w, bl.z, bl.w);
+                    if constexpr (RC != 4) {
+                        const uint4 bl = pl_lo[chunk * 32 + lane];
+                        mma16816(al, a0.x, a8.x, a0.y, a8.y, bl.x, bl.y);
+                        mma16816(al, a0.z, a8.z, a0.w, a8.w, bl.z, bl.w);
+                    }
                 }
                 if (half == 1) {
                     // C fragment: c0,c1 -> (vocabulary row g, batch rows 2t, 2t+1), c2,c3 -> (row g+8, same batch rows)
@@ -791,7 +795,8 @@ dec4_kernel(const Dec3Args a) {
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         const int n = n0 + g + (c >> 1) * 8, e = c & 1;
-                        if (n < V && 2 * t + e < R) {
+                        if constexpr (RC == 4) al[c] = __shfl_xor_sync(0xffffffffu, ah[c], 2);   // lo product of rows 2t, 2t+1: columns 2t+4, 2t+5 = lane t + 2
+                        if (n < V && 2 * t + e < R) {   // RC == 4: R <= 4, i.e. lanes t < 2
                             const float raw = fmaf(al[c], 1.0f / 2048.0f, ah[c]);
                             const float v = (use_mask && ((sp01 >> ((c >> 1) * 8)) & 0xffu)) ? __fadd_rn(raw, -INFINITY) : raw;
                             if (v > -INFINITY) {
