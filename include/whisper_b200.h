@@ -17,6 +17,9 @@
  *   mels_to_text (token part)          src/transcribe.rs:148-383   -> wb_transcribe_windows
  *   waveform_to_text (token part)      src/transcribe.rs:23-74     -> wb_waveform_to_tokens
  *   find_chunk_overlap                 src/transcribe.rs:76-110    -> wb_find_chunk_overlap
+ *   first_repetition_end / repetition_period / find_repeated_tokens_index
+ *                                      src/transcribe.rs:385-447   -> wb_first_repetition_end, wb_repetition_period,
+ *                                                                     wb_find_repeated_tokens_index (compiled but unused there)
  *
  * Conventions:
  *   - plain pointers and sizes only; host buffers are caller-owned and only read/written
@@ -176,6 +179,16 @@ int wb_window_bounds(int64_t n_samples, int64_t sample_rate, int64_t window_len,
 /* transcribe.rs:76-110; returns 1 and fills the indices if an overlap was found, else 0 */
 int wb_find_chunk_overlap(const int64_t* prev, int64_t n_prev, const int64_t* curr, int64_t n_curr,
                           int64_t max_n_offsets, int64_t min_n_overlaps, int64_t* prev_index, int64_t* curr_index);
+/* Repetition heuristics the reference compiles but calls only from its commented-out greedy loop (transcribe.rs:314-380).
+ * transcribe.rs:385-393: position after the last mismatch between a block of `period` tokens and the block before it, walking
+ * back from the end; `period` when none; -1 where the reference's usize arithmetic underflows (period > n). */
+int64_t wb_first_repetition_end(const int64_t* tokens, int64_t n, int64_t period);
+/* transcribe.rs:395-419: the period of a suffix repeated at least min_repetitions times before itself, 0 for None. */
+int64_t wb_repetition_period(const int64_t* tokens, int64_t n, int64_t min_repetitions);
+/* transcribe.rs:421-447: 1 and (first_repeat_index, end) when at least min_repeat_count earlier windows equal the last window of
+ * window_size tokens, 0 for None, -1 where the reference unwraps a second repeat that does not exist. */
+int wb_find_repeated_tokens_index(const int64_t* tokens, int64_t n, int64_t window_size, int64_t min_repeat_count,
+                                  int64_t* first_repeat_index, int64_t* end);
 
 /* ---- beam.rs (host) ------------------------------------------------------------------------ */
 /* get_top_elements (beam.rs:81-110) on f64 scores: writes the indices of the kept elements in

@@ -177,3 +177,44 @@ def waveform_to_tokens(w: dict, dims: model.WhisperDims, sp: SpecialTokens, wave
         else:
             tokens = tokens + new_tokens
     return tokens
+
+
+# ---- repetition heuristics the reference compiles but only its commented-out greedy loop calls (transcribe.rs:314-447) ----
+def first_repetition_end(tokens, period: int) -> int:
+    """transcribe.rs:385-393.  `tokens.len() - period` is usize arithmetic: period > len panics there, ValueError here."""
+    n = len(tokens)
+    if period > n:
+        raise ValueError("attempt to subtract with overflow")
+    for i in reversed(range(period, n - period)):
+        if list(tokens[i - period:i]) != list(tokens[i:i + period]):
+            return i + 1
+    return period
+
+
+def repetition_period(tokens, min_repetitions: int):
+    """transcribe.rs:395-419."""
+    n = len(tokens)
+    for i in reversed(range(n)):
+        period = n - i
+        if i // period < min_repetitions:
+            return None
+        if all(list(tokens[i - period * j - period:i - period * j]) == list(tokens[i:i + period]) for j in range(min_repetitions)):
+            return period
+    return None
+
+
+def find_repeated_tokens_index(tokens, window_size: int, min_repeat_count: int):
+    """transcribe.rs:421-447.  `repeats.next().unwrap()` twice: fewer than two repeats that still satisfy
+    min_repeat_count panic in the reference (ValueError here)."""
+    n = len(tokens)
+    if 2 * window_size > n:
+        return None
+    last_index = n - window_size
+    last_window = list(tokens[last_index:])
+    repeats = [i for i in range(0, last_index - window_size + 1) if list(tokens[i:i + window_size]) == last_window]
+    if len(repeats) >= min_repeat_count:
+        if len(repeats) < 2:
+            raise ValueError("called `Option::unwrap()` on a `None` value")
+        return repeats[0], repeats[1]
+    return None
+

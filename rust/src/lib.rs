@@ -49,6 +49,9 @@ pub mod ffi {
         pub fn wb_session_begin(s: *mut c_void, prompt: *const i64, prompt_len: i64) -> c_int;
         pub fn wb_session_step(s: *mut c_void, n_rows: i64, window_of_row: *const i32, parent_row: *const i32, token: *const i64, apply_special_mask: c_int,
                                is_special: *const u8, k: c_int, topk_ids_out: *mut i64, topk_logprob_out: *mut f32) -> c_int;
+        pub fn wb_first_repetition_end(tokens: *const i64, n: i64, period: i64) -> i64;
+        pub fn wb_repetition_period(tokens: *const i64, n: i64, min_repetitions: i64) -> i64;
+        pub fn wb_find_repeated_tokens_index(tokens: *const i64, n: i64, window_size: i64, min_repeat_count: i64, first_repeat_index: *mut i64, end: *mut i64) -> c_int;
         pub fn wb_waveform_to_tokens(s: *mut c_void, waveform: *const f32, n_samples: i64, sample_rate: i64, beam_size: c_int, max_depth: c_int,
                                      ids: *const wb_special_ids, is_special: *const u8, tokens_out: *mut i64, capacity: i64, n_tokens_out: *mut i64) -> c_int;
     }
@@ -252,6 +255,29 @@ pub mod transcribe {
         })?;
         let tokens: Vec<usize> = out[..n as usize].iter().map(|&t| t as usize).collect();
         Ok((bpe.decode(&tokens[..], true)?, tokens))
+    }
+
+    /// transcribe.rs:385-393 (same signature; private and only reachable from the reference's commented-out greedy loop there).
+    pub fn first_repetition_end(tokens: &[usize], period: usize) -> usize {
+        let t: Vec<i64> = tokens.iter().map(|&x| x as i64).collect();
+        let r = unsafe { ffi::wb_first_repetition_end(t.as_ptr(), t.len() as i64, period as i64) };
+        assert!(r >= 0, "attempt to subtract with overflow");   // the reference's `tokens.len() - period`
+        r as usize
+    }
+    /// transcribe.rs:395-419.
+    pub fn repetition_period(tokens: &[usize], min_repetitions: usize) -> Option<usize> {
+        let t: Vec<i64> = tokens.iter().map(|&x| x as i64).collect();
+        match unsafe { ffi::wb_repetition_period(t.as_ptr(), t.len() as i64, min_repetitions as i64) } { r if r > 0 => Some(r as usize), _ => None }
+    }
+    /// transcribe.rs:421-447.
+    pub fn find_repeated_tokens_index(tokens: &[usize], window_size: usize, min_repeat_count: usize) -> Option<(usize, usize)> {
+        let t: Vec<i64> = tokens.iter().map(|&x| x as i64).collect();
+        let (mut a, mut b) = (0i64, 0i64);
+        match unsafe { ffi::wb_find_repeated_tokens_index(t.as_ptr(), t.len() as i64, window_size as i64, min_repeat_count as i64, &mut a, &mut b) } {
+            1 => Some((a as usize, b as usize)),
+            0 => None,
+            _ => panic!("called `Option::unwrap()` on a `None` value"),   // the reference's second `repeats.next().unwrap()`
+        }
     }
 
     /// The `beamsearch_next` closure of transcribe.rs:253-307 as an object: KV-cached decoder steps for the beams of ONE window

@@ -168,3 +168,44 @@ def test_integration_excerpts_are_literal_and_shim_symbols_exist():
     header = (root / "include" / "whisper_b200.h").read_text()
     for sym in set(re.findall(r"pub fn (wb_\w+)\(", lib)):
         assert re.search(r"\b" + sym + r"\(", header), f"{sym} bound by the shim but not declared in the header"
+
+
+def test_repetition_heuristics_match_oracle():
+    """transcribe.rs:385-447 (compiled but unused by the reference's live path): C++ vs the oracle restatement on random
+    low-entropy sequences, crafted periodic tails, empty / short inputs, and the inputs on which the reference panics."""
+    import numpy as np
+    import pytest
+    from oracle import transcribe as o_tr
+    from whisper_burn_b200 import transcribe
+    rng = np.random.default_rng(5)
+    seqs = [[], [7], [1, 2, 3], [5] * 12, [1, 2, 3, 1, 2, 3, 1, 2, 3, 1, 2, 3, 1, 2, 3], [9, 8, 1, 2, 1, 2, 1, 2, 1, 2, 1, 2],
+            [4, 4, 1, 2, 3, 4, 5, 0, 1, 2, 3, 4, 5, 7, 1, 2, 3, 4, 5, 6, 6, 1, 2, 3, 4, 5, 1, 2, 3, 4, 5]]
+    for _ in range(300):
+        n = int(rng.integers(0, 40))
+        base = rng.integers(0, 3, size=n).tolist()
+        if n > 6 and rng.random() < 0.5:      # periodic tail
+            p = int(rng.integers(1, 5))
+            base = base[:n // 2] + (base[:p] * 12)[:n - n // 2]
+        seqs.append(base)
+
+    def both(fn_ours, fn_oracle, *a):
+        try:
+            want = fn_oracle(*a)
+        except ValueError:
+            with pytest.raises(ValueError):
+                fn_ours(*a)
+            return
+        assert fn_ours(*a) == want, (a, want)
+
+    for s in seqs:
+        for period in range(0, 7):
+            both(transcribe.first_repetition_end, o_tr.first_repetition_end, s, period)
+        for reps in range(0, 5):
+            both(transcribe.repetition_period, o_tr.repetition_period, s, reps)
+        for win in range(0, 6):
+            for cnt in range(0, 5):
+                both(transcribe.find_repeated_tokens_index, o_tr.find_repeated_tokens_index, s, win, cnt)
+    # the reference's own settings (transcribe.rs:359-360): window 5, four repeats
+    s = [4, 4, 1, 2, 3, 4, 5, 0, 1, 2, 3, 4, 5, 7, 1, 2, 3, 4, 5, 6, 6, 1, 2, 3, 4, 5, 1, 2, 3, 4, 5]
+    assert transcribe.find_repeated_tokens_index(s, 5, 4) == (2, 8)
+    assert transcribe.repetition_period([0, 9] + [1, 2, 3] * 5, 4) == 3

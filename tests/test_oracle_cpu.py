@@ -152,3 +152,17 @@ def test_wide_model_tokens_golden():
         assert transcribe.mels_to_tokens(w, dims, sp, mel, beam_size=1, max_depth=14, opts=model.OracleOptions(kv_dtype="f16")) == gold["test-c_greedy_depth14_f16"][i]
     mel = audio.prep_audio(torch.from_numpy(synth.waveform(42000 + 9000 * 2, seed=62))[None])
     assert transcribe.mels_to_tokens(w, dims, sp, mel, beam_size=5, max_depth=8) == gold["test-c_beam5_depth8_f32"][2]
+
+
+def test_repetition_heuristics_known_answers():
+    """Hand-evaluated cases of transcribe.rs:385-447."""
+    t = [0, 9] + [1, 2, 3] * 5
+    assert transcribe.repetition_period(t, 4) == 3          # suffix [1,2,3] preceded by four equal blocks
+    assert transcribe.repetition_period(t, 5) is None       # only four blocks precede the suffix
+    assert transcribe.repetition_period([1, 2, 3, 4], 1) is None
+    assert transcribe.first_repetition_end(t, 3) == 5       # first mismatch walking back: tokens[1..4] = [9,1,2] vs tokens[4..7] = [3,1,2] at i = 4
+    assert transcribe.first_repetition_end([5, 5, 5, 5], 1) == 1
+    s = [4, 4, 1, 2, 3, 4, 5, 0, 1, 2, 3, 4, 5, 7, 1, 2, 3, 4, 5, 6, 6, 1, 2, 3, 4, 5, 1, 2, 3, 4, 5]
+    assert transcribe.find_repeated_tokens_index(s, 5, 4) == (2, 8)
+    assert transcribe.find_repeated_tokens_index(s, 5, 5) is None
+    assert transcribe.find_repeated_tokens_index([1, 2, 3], 2, 1) is None    # 2 * window > len

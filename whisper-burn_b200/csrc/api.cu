@@ -7,6 +7,7 @@
 #include <new>
 
 #include "../host/beam.hpp"
+#include "../host/repeat.hpp"
 #include "session.h"
 
 struct wb_model {
@@ -510,6 +511,22 @@ int wb_find_chunk_overlap(const int64_t* prev, int64_t n_prev, const int64_t* cu
         if (curr_index) *curr_index = ci;
     }
     return found ? 1 : 0;
+}
+
+int64_t wb_first_repetition_end(const int64_t* tokens, int64_t n, int64_t period) {
+    if ((!tokens && n > 0) || n < 0) return -1;
+    return wb::repeat::first_repetition_end(tokens, n, period);
+}
+
+int64_t wb_repetition_period(const int64_t* tokens, int64_t n, int64_t min_repetitions) {
+    if ((!tokens && n > 0) || n < 0) return -1;
+    return wb::repeat::repetition_period(tokens, n, min_repetitions);
+}
+
+int wb_find_repeated_tokens_index(const int64_t* tokens, int64_t n, int64_t window_size, int64_t min_repeat_count, int64_t* first_repeat_index,
+                                  int64_t* end) {
+    if ((!tokens && n > 0) || n < 0 || !first_repeat_index || !end) return -1;
+    return wb::repeat::find_repeated_tokens_index(tokens, n, window_size, min_repeat_count, first_repeat_index, end);
 }
 
 int64_t wb_beam_get_top_elements(const double* scores, int64_t n, int64_t num, int64_t* idx_out) {

@@ -80,6 +80,9 @@ SYMBOLS = {
     "wb_window_count": (C.c_int64, [C.c_int64, C.c_int64, C.c_int64]),
     "wb_window_bounds": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, _I64, _I64]),
     "wb_find_chunk_overlap": (C.c_int, [_I64, C.c_int64, _I64, C.c_int64, C.c_int64, C.c_int64, _I64, _I64]),
+    "wb_first_repetition_end": (C.c_int64, [_I64, C.c_int64, C.c_int64]),
+    "wb_repetition_period": (C.c_int64, [_I64, C.c_int64, C.c_int64]),
+    "wb_find_repeated_tokens_index": (C.c_int, [_I64, C.c_int64, C.c_int64, C.c_int64, _I64, _I64]),
     "wb_beam_get_top_elements": (C.c_int64, [C.POINTER(C.c_double), C.c_int64, C.c_int64, _I64]),
     "wb_kernel_launch_count": (C.c_int64, []),
     "wb_kernel_launch_count_reset": (None, []),

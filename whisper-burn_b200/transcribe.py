@@ -181,3 +181,31 @@ def find_chunk_overlap(prev_tokens, curr_tokens, max_n_offsets: int, min_n_overl
     found = ffi.lib().wb_find_chunk_overlap(ffi.i64ptr(p), len(p), ffi.i64ptr(c), len(c), max_n_offsets, min_n_overlaps,
                                             C.byref(pi), C.byref(ci))
     return (pi.value, ci.value) if found else None
+
+
+def first_repetition_end(tokens, period: int) -> int:
+    """transcribe.rs:385-393 (ValueError where the reference's usize arithmetic underflows)."""
+    t = np.asarray(tokens, dtype=np.int64)
+    r = int(ffi.lib().wb_first_repetition_end(ffi.i64ptr(t), len(t), period))
+    if r < 0:
+        raise ValueError("first_repetition_end: period exceeds the token count")
+    return r
+
+
+def repetition_period(tokens, min_repetitions: int):
+    """transcribe.rs:395-419: the period, or None."""
+    t = np.asarray(tokens, dtype=np.int64)
+    r = int(ffi.lib().wb_repetition_period(ffi.i64ptr(t), len(t), min_repetitions))
+    if r < 0:
+        raise ValueError("repetition_period: invalid argument")
+    return r if r > 0 else None
+
+
+def find_repeated_tokens_index(tokens, window_size: int, min_repeat_count: int):
+    """transcribe.rs:421-447: (index of the first repeat, index of the second) or None (ValueError where the reference panics)."""
+    t = np.asarray(tokens, dtype=np.int64)
+    a, b = C.c_int64(0), C.c_int64(0)
+    r = int(ffi.lib().wb_find_repeated_tokens_index(ffi.i64ptr(t), len(t), window_size, min_repeat_count, C.byref(a), C.byref(b)))
+    if r < 0:
+        raise ValueError("find_repeated_tokens_index: the reference unwraps a repeat that does not exist")
+    return (a.value, b.value) if r else None
