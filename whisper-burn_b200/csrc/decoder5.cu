@@ -18,12 +18,16 @@
 //   * the 8 warps of a CTA split K; partial tiles are reduced through shared memory in a fixed order;
 //   * MLP2 (K = 4d) is split over CTAs into K slabs (3 x 4d/3 when that keeps the 8-warp split, else 4 x d): the
 //     partial sums are folded into x, in a fixed order, by the LayerNorm stage that consumes x next (only CTA r
-//     touches row r there, so the fold is in place);
-//   * cross attention streams the unit's contiguous head-major K/V block (encoder.cu ckv_relayout_kernel) with bulk
-//     copies into a per-warp mbarrier ring that aliases the (then dead) activation planes;
-//   * logits: E[V][d] is streamed once through the same MMA path into an L2-resident [R][V] buffer; a second
-//     stage turns it into per-slice (max, sum-exp, top candidates) records (compact code for greedy: this part
-//     runs once per step from a cold instruction cache), then one warp per row finishes.
+//     touches row r there, so the fold is in place).  The d x d projections (out, cross query, cross out) run the same way
+//     as d/256 slabs of 256 columns when that still fits one round of the grid (small.en: 144 items instead of 48, a third of
+//     the staging per CTA); the cross query's partials are folded where the attention stage loads q (session.cu builds the
+//     descriptors; the producers of the staged planes write them slab-major);
+//   * cross attention streams the unit's contiguous head-major K/V block (encoder.cu ckv_relayout_kernel) with 4 KB bulk
+//     copies (8 fp32 / 16 fp16 keys) into a per-warp mbarrier ring that aliases the (then dead) activation planes;
+//   * logits: E[V][d] is streamed once through the same MMA path into an L2-resident [R][V] buffer (vocabulary tiles dealt per
+//     CTA first, then per warp: every SM streams the same number); a second stage turns it into per-slice (max, sum-exp, top
+//     candidates) records (compact code for greedy: this part runs once per step from a cold instruction cache), then one
+//     warp per row finishes.
 // Code size matters: the layer loop must stay inside the instruction cache, so every building block (staging,
 // MMA tile, emit, attention) exists ONCE and the stages are driven by small descriptors (the first version
 // inlined six copies and ran 3x slower than its memory traffic explains).
