@@ -97,7 +97,6 @@ Session::Session(Model* model, int64_t max_w, int64_t max_b, int64_t max_text_le
             d3_layers.alloc((size_t)L);
             WB_CUDA(cudaMemcpy(d3_layers.p, lay.data(), lay.size() * sizeof(Dec3Layer), cudaMemcpyHostToDevice));
             if (h16) {   // decoder5.cu stage descriptors
-                std::vector<Dec5Desc> ds((size_t)L * 16 + 16);
                 auto gemm = [&](Dec5Desc& q, const void* Wp, const float* bias, int N, int n_slabs, int stage, int emit, int src) {
                     q.kind = D5_KIND_GEMM; q.W = Wp; q.bias = bias; q.N = N; q.n_slabs = n_slabs; q.stage = stage; q.emit = emit; q.src = src; q.ks = d;
                 };
@@ -110,36 +109,44 @@ Session::Session(Model* model, int64_t max_w, int64_t max_b, int64_t max_text_le
                 // ypart and are folded, in a fixed order, by the consumer (the next LayerNorm stage / the cross-attention query load).
                 const int psl = d / 256;
                 const char* e_split = getenv("WB200_D5_SPLIT");
-                const bool split_dd = !(e_split && e_split[0] == '0') && d % 256 == 0 && psl >= 2 && psl <= 4 && (d / 16) * psl <= n_sm;
-                for (int l = 0; l < L; ++l) {
-                    const DecBlockW& B = m->dec[(size_t)l];
-                    Dec5Desc* q = ds.data() + (size_t)l * 16;
-                    ln(q[0], B.attn_ln, l == 0 ? D5_ST_LN_EMB : D5_ST_LN_FOLD);
-                    gemm(q[1], B.qkv.w16, B.qkv.b, 3 * d, 1, D5_ST_PLANES, D5_EM_QKV, 3);
-                    q[2].kind = D5_KIND_ATTN;
-                    gemm(q[3], B.out.w16, B.out.b, d, 1, D5_ST_PLANES, D5_EM_RESID, 1);
-                    ln(q[4], B.cross_ln, D5_ST_LN_X);
-                    gemm(q[5], B.cq.w16, B.cq.b, d, 1, D5_ST_PLANES, D5_EM_CQ, 3);
-                    q[6].kind = D5_KIND_ATTN;
-                    gemm(q[7], B.cout.w16, B.cout.b, d, 1, D5_ST_CROSS, D5_EM_RESID, 1);
-                    ln(q[8], B.mlp_ln, D5_ST_LN_X);
-                    gemm(q[9], B.mlp1.w16, B.mlp1.b, 4 * d, 1, D5_ST_PLANES, D5_EM_HID, 3);
-                    gemm(q[10], B.mlp2.w16, B.mlp2.b, d, 4, D5_ST_PLANES, D5_EM_PART, 2);
-                    // MLP2 K = 4d: 3 slabs of 4d/3 when that keeps the 8-warp K split (multiple of 256, <= 1280): d/16 tiles x 3 slabs
-                    // = 144 items for small.en -> ONE round on 148 CTAs instead of 192 items in two
-                    if ((4 * d) % 3 == 0 && (4 * d / 3) % 256 == 0 && 4 * d / 3 <= 1280) { q[10].n_slabs = 3; q[10].ks = 4 * d / 3; }
-                    if (split_dd) {
-                        for (int sl : {3, 5, 7}) { q[sl].n_slabs = psl; q[sl].ks = 256; q[sl].emit = D5_EM_PART; }
-                        q[4].stage = D5_ST_LN_FOLD; q[4].n_fold = psl; q[4].ks = 256;   // folds the out projection, feeds the split cross query
-                        q[8].stage = D5_ST_LN_FOLD; q[8].n_fold = psl;                  // folds the cross out projection
+                const bool can_split = !(e_split && e_split[0] == '0') && d % 256 == 0 && psl >= 2 && psl <= 4 && (d / 16) * psl <= n_sm;
+                // Two tables: the split one is used by launches whose cross attention is NOT split over keys (n_splits == 1, i.e. at
+                // least one (row, head) unit per SM: the batched shapes the split is for); small batches keep the unsplit stages, whose
+                // cross-out staging merges the key-split partials over all d columns (launch_v3 picks per launch).
+                auto build = [&](bool split_dd, DevBuf<Dec5Desc>& dst) {
+                    std::vector<Dec5Desc> ds((size_t)L * 16 + 16);
+                    for (int l = 0; l < L; ++l) {
+                        const DecBlockW& B = m->dec[(size_t)l];
+                        Dec5Desc* q = ds.data() + (size_t)l * 16;
+                        ln(q[0], B.attn_ln, l == 0 ? D5_ST_LN_EMB : D5_ST_LN_FOLD);
+                        gemm(q[1], B.qkv.w16, B.qkv.b, 3 * d, 1, D5_ST_PLANES, D5_EM_QKV, 3);
+                        q[2].kind = D5_KIND_ATTN;
+                        gemm(q[3], B.out.w16, B.out.b, d, 1, D5_ST_PLANES, D5_EM_RESID, 1);
+                        ln(q[4], B.cross_ln, D5_ST_LN_X);
+                        gemm(q[5], B.cq.w16, B.cq.b, d, 1, D5_ST_PLANES, D5_EM_CQ, 3);
+                        q[6].kind = D5_KIND_ATTN;
+                        gemm(q[7], B.cout.w16, B.cout.b, d, 1, D5_ST_CROSS, D5_EM_RESID, 1);
+                        ln(q[8], B.mlp_ln, D5_ST_LN_X);
+                        gemm(q[9], B.mlp1.w16, B.mlp1.b, 4 * d, 1, D5_ST_PLANES, D5_EM_HID, 3);
+                        gemm(q[10], B.mlp2.w16, B.mlp2.b, d, 4, D5_ST_PLANES, D5_EM_PART, 2);
+                        // MLP2 K = 4d: 3 slabs of 4d/3 when that keeps the 8-warp K split (multiple of 256, <= 1280): d/16 tiles x 3 slabs
+                        // = 144 items for small.en -> ONE round on 148 CTAs instead of 192 items in two
+                        if ((4 * d) % 3 == 0 && (4 * d / 3) % 256 == 0 && 4 * d / 3 <= 1280) { q[10].n_slabs = 3; q[10].ks = 4 * d / 3; }
+                        if (split_dd) {
+                            for (int sl : {3, 5, 7}) { q[sl].n_slabs = psl; q[sl].ks = 256; q[sl].emit = D5_EM_PART; }
+                            q[4].stage = D5_ST_LN_FOLD; q[4].n_fold = psl; q[4].ks = 256;   // folds the out projection, feeds the split cross query
+                            q[8].stage = D5_ST_LN_FOLD; q[8].n_fold = psl;                  // folds the cross out projection
+                        }
+                        if (l > 0) q[0].n_fold = q[10].n_slabs;                             // folds MLP2 of the previous layer
                     }
-                    if (l > 0) q[0].n_fold = q[10].n_slabs;                             // folds MLP2 of the previous layer
-                }
-                ln(ds[(size_t)L * 16 + 11], m->dec_ln, D5_ST_LN_FOLD_NOPUB);
-                ds[(size_t)L * 16 + 11].n_fold = ds[(size_t)(L - 1) * 16 + 10].n_slabs;
-                gemm(ds[(size_t)L * 16 + 12], m->tok_emb16, nullptr, V, 1, D5_ST_PLANES, D5_EM_LOGITS, 3);
-                d5_desc.alloc(ds.size());
-                WB_CUDA(cudaMemcpy(d5_desc.p, ds.data(), ds.size() * sizeof(Dec5Desc), cudaMemcpyHostToDevice));
+                    ln(ds[(size_t)L * 16 + 11], m->dec_ln, D5_ST_LN_FOLD_NOPUB);
+                    ds[(size_t)L * 16 + 11].n_fold = ds[(size_t)(L - 1) * 16 + 10].n_slabs;
+                    gemm(ds[(size_t)L * 16 + 12], m->tok_emb16, nullptr, V, 1, D5_ST_PLANES, D5_EM_LOGITS, 3);
+                    dst.alloc(ds.size());
+                    WB_CUDA(cudaMemcpy(dst.p, ds.data(), ds.size() * sizeof(Dec5Desc), cudaMemcpyHostToDevice));
+                };
+                build(false, d5_desc);
+                if (can_split) build(true, d5_desc_split);
             }
         }
         ypart.alloc((size_t)4 * Rmax * d);   // decoder5.cu: MLP2 K-slab partial sums
@@ -458,13 +465,15 @@ void Session::launch_v3(int R_, int pos0, int n_steps, int logits_from, bool use
     a.E_tiled = m->tok_emb16_tiled;
     a.lnf_g = m->dec_ln.g; a.lnf_b = m->dec_ln.b; a.lnf_eps = m->dec_ln.eps;
     a.x = dx.p; a.q = dq.p; a.att = datt.p; a.hid = dhid.p;
-    a.ypart = ypart.p; a.lgbuf = logits.p; a.att_pl = att_pl.p; a.hid_pl = hid_pl.p; a.d5 = d5_desc.p; a.ckv_hm = ckv_hm ? 1 : 0;
+    a.ypart = ypart.p; a.lgbuf = logits.p; a.att_pl = att_pl.p; a.hid_pl = hid_pl.p; a.d5 = d5_desc.p; a.ckv_hm = ckv_hm ? 1 : 0;   // a.d5: see pick_d5 below (needs n_splits)
     a.lg_slices = std::max(1, std::min(16, n_sm / std::max(1, R_)));
     a.kv_half = kv_dtype == WB_KV_F16 ? 1 : 0;
     if (a.kv_half) { a.kc = kc16.p; a.vc = vc16.p; a.ckv = ckv16.p; } else { a.kc = kc.p; a.vc = vc.p; a.ckv = ckv.p; }
     a.row_window = row_window.p; a.win_row_off = d_win_row_off.p; a.win_T = d_win_T.p;
     a.anc = anc_identity ? nullptr : (anc_cur == 0 ? anc0.p : anc1.p);
     a.n_splits = std::max(1, std::min(16, n_sm / std::max(1, R_ * H)));
+    auto pick_d5 = [&](int n_splits) { return (n_splits == 1 && d5_desc_split.p != nullptr) ? d5_desc_split.p : d5_desc.p; };
+    a.d5 = pick_d5(a.n_splits);
     a.part_o = part_o.p; a.part_m = part_m.p; a.part_l = part_l.p;
     a.tokens = tokens.p; a.cur_tok = cur_tok.p; a.use_cur_tok = use_cur_tok ? 1 : 0;
     a.pos0 = pos0; a.n_steps = n_steps; a.logits_from = logits_from;
@@ -525,6 +534,7 @@ void Session::launch_v3(int R_, int pos0, int n_steps, int logits_from, bool use
                     if (g.logits_out) { g.logits_out += (int64_t)r0 * D.n_vocab; g.lgbuf = g.logits_out; }
                     g.lg_slices = std::max(1, std::min(16, n_sm / std::max(1, Rg)));
                     g.n_splits = std::max(1, std::min(16, n_sm / std::max(1, Rg * H)));
+                    g.d5 = pick_d5(g.n_splits);
                     g.steps_done = steps_done.p + std::min(gi, 127); g.n_unfinished = n_unfinished.p + std::min(gi, 127);
                     WB_CUDA(cudaMemsetAsync(d3_bar.p, 0, 4 * sizeof(unsigned int), st));
                     ok = launch_dec5(g, n_sm, true, st);

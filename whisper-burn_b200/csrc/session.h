@@ -53,7 +53,8 @@ struct Session {
     DevBuf<float> kc, vc;  // [L][Rmax][t_max][d] self keys (scaled) / values
     DevBuf<__half> kc16, vc16, ckv16;   // fp16 caches (WB_KV_F16)
     DevBuf<float> dx, dq, dhid, logits;
-    DevBuf<Dec5Desc> d5_desc;
+    DevBuf<Dec5Desc> d5_desc;         // decoder5.cu stage descriptors, d x d projections unsplit
+    DevBuf<Dec5Desc> d5_desc_split;   // the same with the d x d projections as K slabs (launches with unsplit cross attention); may be empty
     DevBuf<uint4> att_pl, hid_pl;   // decoder5.cu activation planes
     DevBuf<float> part_o, part_m, part_l;
     DevBuf<int> tokens, lengths, cur_tok, finished, row_window, anc0, anc1, parent, pos, n_unfinished, topk_id;
