@@ -257,8 +257,8 @@ def run_config(args, cfg, ctx):
     for _ in range(args.warmup):
         step_device()
         step_e2e()
-    # the cyclic collector stays off inside the timed regions (a collection over the weight dictionaries of the larger models
-    # costs milliseconds: one 14 ms step among 10.7 ms ones in the 8-GPU run of round 2)
+    # the cyclic collector stays off inside the timed regions: a collection over the weight dictionaries costs milliseconds on a
+    # 10 ms step (the 8-GPU run of round 2 had one 14 ms step among 10.7 ms ones; host-side noise of this kind, cause not isolated)
     import gc
     gc.collect()
     gc.disable()
