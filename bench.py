@@ -188,6 +188,18 @@ def run_reference(args):
     emit(line)
 
 
+def algorithmic_bytes(dims, window_lens, wbytes: int, kvb: int, steps: int) -> int:
+    """SURVEY.md 8d bytes of ONE persistent-decoder launch (3 prompt positions without logits + `steps` greedy positions) over the
+    windows of `window_lens` samples: decoder weights once per position for the whole batch, the vocabulary matrix on the positions
+    that produce logits, every window's cross K/V per position, every row's self K/V up to the current position."""
+    d, V, L, R = dims.n_text_state, dims.n_vocab, dims.n_text_layer, len(window_lens)
+    n_pos = steps + 3
+    T_rows = sum((min(l // 160, dims.n_audio_ctx - 10) + 10 - 1) // 2 + 1 for l in window_lens)
+    per_pos = L * 14 * d * d * wbytes + L * 2 * T_rows * d * kvb
+    self_kv = sum(L * 2 * (t + 1) * d * kvb * R for t in range(n_pos))
+    return per_pos * n_pos + steps * V * d * wbytes + self_kv
+
+
 def dram_traffic(model: str, kv: str, rows: int, dec: int):
     """DRAM bytes per decoder position of the dominant kernel from a COMMITTED ncu --set full capture
     (profiles/dram_traffic.json, keyed by workload), or None when no capture of this exact workload exists."""
@@ -321,15 +333,10 @@ def run_config(args, cfg, ctx):
     hbm_peak, peak_src = peaks()
     roof = None
     if rank == 0:
-        d, V, R, L = dims.n_text_state, dims.n_vocab, n_win, dims.n_text_layer
-        wbytes = 2 if wh.weights_fp16_exact else 4
-        kvb = 2 if kv == "f16" else 4
+        R = n_win
         prof_steps = args.max_depth
         n_pos = prof_steps + 3
-        T_rows = sum((min(l // 160, dims.n_audio_ctx - 10) + 10 - 1) // 2 + 1 for l in lens)
-        per_pos = L * 14 * d * d * wbytes + L * 2 * T_rows * d * kvb
-        self_kv = sum(L * 2 * (t + 1) * d * kvb * R for t in range(n_pos))
-        alg_bytes = per_pos * n_pos + prof_steps * V * d * wbytes + self_kv
+        alg_bytes = algorithmic_bytes(dims, lens, 2 if wh.weights_fp16_exact else 4, 2 if kv == "f16" else 4, prof_steps)
         try:
             k_ms, _ = sess.profile_decode(sp, prof_steps)          # per-position average of one timed launch (CUDA events, library stream)
             launch_ms = k_ms * n_pos

@@ -209,3 +209,24 @@ def test_repetition_heuristics_match_oracle():
     s = [4, 4, 1, 2, 3, 4, 5, 0, 1, 2, 3, 4, 5, 7, 1, 2, 3, 4, 5, 6, 6, 1, 2, 3, 4, 5, 1, 2, 3, 4, 5]
     assert transcribe.find_repeated_tokens_index(s, 5, 4) == (2, 8)
     assert transcribe.repetition_period([0, 9] + [1, 2, 3] * 5, 4) == 3
+
+
+def test_bench_algorithmic_bytes_tiny_en_headline():
+    """The numerator of the bench line's roofline for the headline workload, evaluated by hand: tiny.en, the three
+    reference windows of a 30 s chunk (750 + 750 + 314 encoder positions), fp16-exact weights, fp32 K/V, 103 positions."""
+    import importlib.util
+    from pathlib import Path
+    from whisper_burn_b200 import synth
+    spec = importlib.util.spec_from_file_location("bench_mod", Path(__file__).resolve().parent.parent / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    dims = synth.MODEL_DIMS["tiny.en"]
+    lens = [238559, 238559, 480000 - 381118]
+    d, L, V = 384, 4, 51864
+    weights = L * 14 * d * d * 2                       # 16.5 MB of layer weights per position
+    cross = L * 2 * (750 + 750 + 314) * d * 4          # 22.3 MB of cross K/V per position
+    self_kv = sum(L * 2 * (t + 1) * d * 4 * 3 for t in range(103))
+    want = (weights + cross) * 103 + 100 * V * d * 2 + self_kv
+    assert bench.algorithmic_bytes(dims, lens, 2, 4, 100) == want == 8177565696
+    # the fp16 cache halves the K/V terms only
+    assert bench.algorithmic_bytes(dims, lens, 2, 2, 100) == weights * 103 + (cross * 103 + self_kv) // 2 + 100 * V * d * 2 == 6930886656
